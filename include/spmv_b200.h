@@ -1,0 +1,283 @@
+/*
+ * spmv_b200.h -- C ABI of the B200-native SpMV engine (libspmvb200.so).
+ *
+ * Drop-in boundary for the hot path of jamtrott/spmv-cache-trace: fp64
+ * y += A*x for the COO, CSR, ELLPACK and hybrid (ELL+COO) formats.  Every
+ * entry point names the reference interface it stands in for (file:line into
+ * the reference tree).  Plain C types only: pointers, sizes, opaque handles.
+ * No exceptions cross this boundary: every function returns 0 on success and
+ * a non-zero spmvb200_status otherwise; spmvb200_last_error() gives the text.
+ *
+ * There is no CPU fallback.  Every compute entry point fails with
+ * SPMVB200_ERR_CUDA when no CUDA device is usable.
+ *
+ * INTEGRATION.md shows the reference-side adapter (Kernel subclasses) that
+ * binds these functions.
+ */
+#ifndef SPMV_B200_H
+#define SPMV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMVB200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    SPMVB200_OK = 0,
+    SPMVB200_ERR_INVALID = 1,  /* bad argument / handle                                   */
+    SPMVB200_ERR_PARSE = 2,    /* Matrix Market syntax  (matrix::matrix_error in the ref) */
+    SPMVB200_ERR_IO = 3,       /* file / gzip / tar     (matrix_error / std::system_error) */
+    SPMVB200_ERR_OVERFLOW = 4, /* rows*row_length etc. (ell-matrix.cpp:201-205)           */
+    SPMVB200_ERR_CUDA = 5,     /* CUDA runtime failure, or no device                      */
+    SPMVB200_ERR_NOMEM = 6,
+    SPMVB200_ERR_UNSUPPORTED = 7
+} spmvb200_status;
+
+typedef enum {
+    SPMVB200_CSR = 0,
+    SPMVB200_COO = 1,
+    SPMVB200_ELL = 2,
+    SPMVB200_HYB = 3
+} spmvb200_format;
+
+/* COO execution mode.  SEGMENTED: the builder keeps a row-sorted device copy
+ * (stable, so the column order inside a row is the file order) and the kernel
+ * is a segmented reduction -- the counterpart of coo_matrix::spmv
+ * (coo-matrix.cpp:313-335).  ATOMIC: file order kept, one fp64 reduction per
+ * entry -- the counterpart of coo_matrix::spmv_atomic (coo-matrix.cpp:337-358). */
+typedef enum { SPMVB200_COO_SEGMENTED = 0, SPMVB200_COO_ATOMIC = 1 } spmvb200_coo_mode;
+
+typedef enum {
+    SPMVB200_STENCIL_2D5 = 0, /* 2D 5-point Poisson:  4 on the diagonal, -1 neighbours  */
+    SPMVB200_STENCIL_3D7 = 1, /* 3D 7-point Poisson:  6 on the diagonal, -1 neighbours  */
+    SPMVB200_STENCIL_3D27 = 2 /* 3D 27-point:        26 on the diagonal, -1 neighbours  */
+} spmvb200_stencil;
+
+typedef struct spmvb200_mm_s *spmvb200_mm_t;         /* host Matrix Market matrix  */
+typedef struct spmvb200_matrix_s *spmvb200_matrix_t; /* device matrix + its x and y */
+
+/* What Kernel::print emits (csr-spmv.cpp:97-112, hybrid-spmv.cpp:113-131) plus
+ * the device-side facts.  matrix_size follows the reference's Matrix::size():
+ * stored index + value bytes in the reference layout (csr-matrix.cpp:46-60,
+ * coo-matrix.cpp:49-63, ell-matrix.cpp:52-65); for hybrid it is
+ * 12*num_ell_entries + 16*num_coo_entries, i.e. WITH the coo_row_index bytes
+ * that hybrid-matrix.cpp:80-86 forgets. */
+typedef struct {
+    int32_t format;          /* spmvb200_format                                  */
+    int32_t coo_mode;        /* spmvb200_coo_mode (COO / HYB tail)               */
+    int64_t rows, columns;
+    int64_t num_entries;     /* true non-zeros ("nonzeros")                      */
+    int64_t stored_entries;  /* CSR: row_ptr[rows]; ELL: rows*W; COO: nnz        */
+    int64_t row_alignment;   /* CSR                                              */
+    int64_t ell_row_length;  /* ELL / HYB                                        */
+    int64_t num_ell_entries; /* HYB: rows*W                                      */
+    int64_t num_coo_entries; /* HYB                                              */
+    int32_t skip_padding;    /* ELL / HYB: padding column = INT32_MAX sentinel   */
+    int32_t offsets_64bit;   /* device row_ptr is int64 (stored_entries >= 2^32) */
+    int64_t matrix_size;     /* bytes, reference layout (see above)              */
+    int64_t x_size, y_size;  /* 8*columns, 8*rows                                */
+    int64_t device_bytes;    /* bytes actually allocated on the GPU              */
+    int64_t row_offset;      /* first global row held (row-partitioned mode)     */
+} spmvb200_info;
+
+/* ---- errors, devices ----------------------------------------------------- */
+
+/* Text of the last failure on the calling thread ("" if none).
+ * Ref: what() of matrix::matrix_error (matrix-error.hpp:10-15) / kernel_error
+ * (kernels/kernel.hpp:11-16). */
+const char *spmvb200_last_error(void);
+int spmvb200_version(void);
+int spmvb200_device_count(int *count);
+int spmvb200_set_device(int device);
+/* sm_count, l2_bytes, total memory; name[] gets at most name_cap-1 chars. */
+int spmvb200_device_props(int device, char *name, size_t name_cap, int *sm_count,
+                          int64_t *l2_bytes, int64_t *mem_bytes, int *cc_major, int *cc_minor);
+/* Total number of kernels this library has launched in this process. */
+int64_t spmvb200_launch_count(void);
+/* Process-wide switches.  "force_offsets64" = 1 makes every CSR built afterwards keep int64 row
+ * offsets on the device (normally only when stored_entries >= 2^32) so that path can be tested. */
+int spmvb200_set_global_option(const char *key, int64_t value);
+
+/* ---- host side: Matrix Market --------------------------------------------- */
+
+/* matrix_market::fromStream (matrix/matrix-market.cpp:530-555): header line,
+ * '%' comment lines, size line, whitespace-separated coordinate records
+ * (real, complex -> real part, integer, pattern -> 1.0; matrix-market.cpp:243-277).
+ * Symmetry is parsed but entries are NOT expanded, like the reference. */
+int spmvb200_mm_parse(const char *text, size_t len, spmvb200_mm_t *out);
+/* matrix_market::load_matrix (matrix-market.cpp:777-861): .mtx, .gz, .tar.gz
+ * and .tgz (member <name>/<name>.mtx, :755-757).  A "__RCM" / "__GP<n>" path
+ * suffix (reordering, :786-802) is rejected with SPMVB200_ERR_UNSUPPORTED. */
+int spmvb200_mm_load(const char *path, spmvb200_mm_t *out);
+/* matrix_market::Matrix(Header, Comments, Size, vector<CoordinateEntryReal>)
+ * (matrix-market.hpp:81-84); i, j are 1-based. */
+int spmvb200_mm_from_entries(int32_t rows, int32_t columns, int32_t num_entries,
+                             const int32_t *i, const int32_t *j, const double *a, spmvb200_mm_t *out);
+/* Matrix::rows/columns/num_entries/field/symmetry (matrix-market.hpp:104-113);
+ * field: 0 real 1 complex 2 integer 3 pattern; symmetry: 0 general 1 symmetric
+ * 2 skew-symmetric 3 hermitian; format: 0 coordinate 1 array. */
+int spmvb200_mm_info(spmvb200_mm_t mm, int32_t *rows, int32_t *columns, int32_t *num_entries,
+                     int32_t *field, int32_t *symmetry, int32_t *format);
+/* Matrix::row_indices / column_indices / values_real (matrix-market.cpp:171-277);
+ * borrowed pointers, valid until spmvb200_mm_free. */
+int spmvb200_mm_entries(spmvb200_mm_t mm, const int32_t **i, const int32_t **j, const double **a);
+/* Matrix::max_row_length / row_lengths (matrix-market.cpp:279-307). */
+int spmvb200_mm_max_row_length(spmvb200_mm_t mm, int32_t *out);
+int spmvb200_mm_row_lengths(spmvb200_mm_t mm, int32_t *lengths /* rows */);
+/* sort_matrix_row_major / sort_matrix_column_major (matrix-market.cpp:863-929),
+ * in place and stable. */
+int spmvb200_mm_sort_row_major(spmvb200_mm_t mm);
+int spmvb200_mm_sort_column_major(spmvb200_mm_t mm);
+void spmvb200_mm_free(spmvb200_mm_t mm);
+
+/* ---- device builders from Matrix Market entries ---------------------------- */
+/* The conversions run on the GPU (sort, row pointer, padding, split) and leave
+ * the matrix resident in the padded, aligned device layout the kernels want.
+ * Each also allocates the kernel object's vectors, x = 1.0 and y = 0.0, as
+ * Kernel::init does (csr-spmv.cpp:35-36). */
+
+/* csr_matrix::from_matrix_market_row_aligned (matrix/csr-matrix.cpp:193-243);
+ * row_alignment 1 == from_matrix_market (:187-191). */
+int spmvb200_csr_from_mm(spmvb200_mm_t mm, int32_t row_alignment, spmvb200_matrix_t *out);
+/* coo_matrix::from_matrix_market (matrix/coo-matrix.cpp:220-243). */
+int spmvb200_coo_from_mm(spmvb200_mm_t mm, int32_t coo_mode, spmvb200_matrix_t *out);
+/* ell_matrix::from_matrix_market (matrix/ell-matrix.cpp:190-238). */
+int spmvb200_ell_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix_t *out);
+/* hybrid_matrix::from_matrix_market (matrix/hybrid-matrix.cpp:316-417). */
+int spmvb200_hyb_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix_t *out);
+
+/* ---- device matrices from arrays the caller already holds ------------------ */
+/* This is what a reference-side Kernel adapter calls from prepare(): it owns a
+ * converted host matrix and hands its arrays over once. */
+
+/* csr_matrix::Matrix{rows, columns, num_entries, row_ptr, column_index, value}
+ * (matrix/csr-matrix.hpp:22-65).  stored = row_ptr[rows]. */
+int spmvb200_csr_create(int32_t rows, int32_t columns, int32_t num_entries,
+                        const int32_t *row_ptr, const int32_t *column_index, const double *value,
+                        spmvb200_matrix_t *out);
+/* Same with 64-bit offsets, for matrices beyond the reference's int32 limit. */
+int spmvb200_csr_create64(int64_t rows, int64_t columns, int64_t num_entries,
+                          const int64_t *row_ptr, const int32_t *column_index, const double *value,
+                          spmvb200_matrix_t *out);
+/* coo_matrix::Matrix (matrix/coo-matrix.hpp:22-70); 0-based indices. */
+int spmvb200_coo_create(int32_t rows, int32_t columns, int64_t num_entries,
+                        const int32_t *row_index, const int32_t *column_index, const double *value,
+                        int32_t coo_mode, spmvb200_matrix_t *out);
+/* ell_matrix::Matrix (matrix/ell-matrix.hpp:22-65): ROW-MAJOR arrays of
+ * rows*row_length entries; re-laid out column-major on the device. */
+int spmvb200_ell_create(int32_t rows, int32_t columns, int32_t num_entries, int32_t row_length,
+                        const int32_t *column_index, const double *value, int32_t skip_padding,
+                        spmvb200_matrix_t *out);
+/* hybrid_matrix::Matrix (matrix/hybrid-matrix.hpp:24-96). */
+int spmvb200_hyb_create(int32_t rows, int32_t columns, int32_t num_entries,
+                        int32_t ell_row_length, const int32_t *ell_column_index, const double *ell_value,
+                        int32_t ell_skip_padding, int32_t num_coo_entries,
+                        const int32_t *coo_row_index, const int32_t *coo_column_index,
+                        const double *coo_value, spmvb200_matrix_t *out);
+
+/* ---- synthetic matrices generated on the device (BASELINE.json configs) ---- */
+
+/* Rows [row_begin, row_end) of the nx*ny*nz stencil matrix (nz = 1 for 2D), in
+ * row-major (x fastest) grid order, global column indices, columns sorted inside
+ * each row.  format: CSR, ELL, COO or HYB.  The matrix keeps `columns` = nx*ny*nz
+ * so x is full length; y holds row_end-row_begin entries. */
+int spmvb200_gen_stencil(int32_t kind, int64_t nx, int64_t ny, int64_t nz,
+                         int64_t row_begin, int64_t row_end, int32_t format, spmvb200_matrix_t *out);
+/* R-MAT power-law matrix: 2^scale rows/columns, edge_factor*2^scale edge draws
+ * with quadrant probabilities (a, b, c, 1-a-b-c), counter-based RNG keyed by
+ * (seed, edge id), duplicates removed, value = hash(i, j) in (-1, 1).
+ * Rows [row_begin, row_end) are kept (0, 0 = all). */
+int spmvb200_gen_rmat(int32_t scale, int32_t edge_factor, uint64_t seed, double a, double b, double c,
+                      int64_t row_begin, int64_t row_end, int32_t format, int32_t coo_mode,
+                      spmvb200_matrix_t *out);
+/* Device-side format change following the reference's conversion rules
+ * (CSR source only): arg = skip_padding for ELL/HYB, coo_mode for COO. */
+int spmvb200_convert(spmvb200_matrix_t src, int32_t format, int32_t arg, spmvb200_matrix_t *out);
+
+/* ---- inspection / export (reference layout) -------------------------------- */
+
+int spmvb200_matrix_info(spmvb200_matrix_t m, spmvb200_info *info);
+/* Copy the matrix back in the reference's host layout (for bit-exact
+ * conversion parity and for adapters that want the arrays).  NULL = skip. */
+int spmvb200_csr_export(spmvb200_matrix_t m, int64_t *row_ptr, int32_t *column_index, double *value);
+int spmvb200_coo_export(spmvb200_matrix_t m, int32_t *row_index, int32_t *column_index, double *value);
+int spmvb200_ell_export(spmvb200_matrix_t m, int32_t *column_index_row_major, double *value_row_major);
+int spmvb200_hyb_export(spmvb200_matrix_t m, int32_t *ell_column_index, double *ell_value,
+                        int32_t *coo_row_index, int32_t *coo_column_index, double *coo_value);
+
+/* ---- vectors (the Kernel object's x and y, csr-spmv.hpp:36-37) ------------- */
+
+int spmvb200_set_x(spmvb200_matrix_t m, const double *x_host);
+int spmvb200_set_y(spmvb200_matrix_t m, const double *y_host);
+int spmvb200_get_x(spmvb200_matrix_t m, double *x_host);
+int spmvb200_get_y(spmvb200_matrix_t m, double *y_host);
+int spmvb200_fill_x(spmvb200_matrix_t m, double value);
+int spmvb200_fill_y(spmvb200_matrix_t m, double value);
+/* Device pointers of x / y, and binding of caller-owned device buffers (e.g.
+ * the all-gathered x of the row-partitioned mode).  Bound buffers are not freed. */
+int spmvb200_x_device(spmvb200_matrix_t m, void **ptr);
+int spmvb200_y_device(spmvb200_matrix_t m, void **ptr);
+int spmvb200_bind_x(spmvb200_matrix_t m, void *device_ptr);
+int spmvb200_bind_y(spmvb200_matrix_t m, void *device_ptr);
+/* cudaStream_t to launch on (default: a stream owned by the matrix). */
+int spmvb200_set_stream(spmvb200_matrix_t m, void *cuda_stream);
+/* Pinned host memory for x / y staging of spmvb200_spmv_host. */
+int spmvb200_host_alloc(size_t bytes, void **ptr);
+int spmvb200_host_free(void *ptr);
+
+/* ---- the hot path ----------------------------------------------------------- */
+
+/* y += A*x on the device, asynchronous on the matrix's stream.
+ * Ref: csr_matrix::spmv (matrix/csr-matrix-spmv.cpp:148-167),
+ *      coo_matrix::spmv / spmv_atomic (matrix/coo-matrix.cpp:313-358),
+ *      ell_matrix::spmv (matrix/ell-matrix.cpp:311-335),
+ *      hybrid_matrix::spmv (matrix/hybrid-matrix.cpp:535-567),
+ * i.e. the bodies of Kernel::run (kernels/csr-spmv.cpp:64-67 etc.). */
+int spmvb200_spmv(spmvb200_matrix_t m);
+/* Wait for the matrix's stream. */
+int spmvb200_sync(spmvb200_matrix_t m);
+/* Host-buffer form: copies x (columns) and y (rows) to the device, runs
+ * y += A*x, copies y back, synchronises.  This is the end-to-end call. */
+int spmvb200_spmv_host(spmvb200_matrix_t m, const double *x_host, double *y_host);
+/* `reps` launches after `warmup` untimed ones, each bracketed by CUDA events on
+ * the launching stream; ms[r] = duration of launch r.  The protocol of
+ * profile_kernel_run (profile-kernel.cpp:137-179) with events for the clock. */
+int spmvb200_time(spmvb200_matrix_t m, int warmup, int reps, float *ms);
+/* Benchmark form of the same protocol for operands that fit in L2: the n matrices are copies of
+ * one workload (each with its own x and y); `steps` launches go round-robin over them on the
+ * stream of ms[0] so that no launch finds its operands in L2.  total_ms = CUDA-event time around
+ * the whole sequence of `steps` launches; per_launch_ms (may be NULL; steps entries) = event time
+ * of each launch, taken in a second, identical pass so the events do not perturb total_ms. */
+int spmvb200_time_rotating(const spmvb200_matrix_t *ms, int n, int warmup, int steps,
+                           float *total_ms, float *per_launch_ms);
+/* End-to-end variant: every step is spmvb200_spmv_host(ms[k], xs[k], ys[k]) (H2D x and y, kernel,
+ * D2H y, synchronise), k round-robin; total_ms = CUDA-event time around all `steps` steps. */
+int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double *const *xs,
+                                double *const *ys, int warmup, int steps, float *total_ms);
+/* Tuning: "csr.tile" (1024|2048|4096), "csr.stages", "csr.ctas_per_sm", "ell.rows_per_thread"
+ * (1|2|4), "ell.block", "coo.stages", "coo.ctas_per_sm", "beta0" (1: y = A*x).  0 = automatic. */
+int spmvb200_set_option(spmvb200_matrix_t m, const char *key, int64_t value);
+int spmvb200_get_option(spmvb200_matrix_t m, const char *key, int64_t *value);
+/* Name of the kernel spmvb200_spmv launches for this matrix. */
+const char *spmvb200_kernel_name(spmvb200_matrix_t m);
+
+int spmvb200_destroy(spmvb200_matrix_t m);
+
+/* ---- row partition of the multi-GPU mode ------------------------------------ */
+
+/* The reference rule (matrix/csr-matrix.cpp:77-83): start_p = min(rows, p*ceil(rows/P)). */
+int spmvb200_partition_rows_ref(int64_t rows, int32_t parts, int64_t *starts /* parts+1 */);
+/* Balanced non-zeros: start_p = first row r with row_ptr[r] >= floor(p*nnz/P). CSR only. */
+int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t *starts /* parts+1 */);
+/* New matrix holding rows [row_begin, row_end) of a CSR matrix (global columns). */
+int spmvb200_csr_row_block(spmvb200_matrix_t m, int64_t row_begin, int64_t row_end,
+                           spmvb200_matrix_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,123 @@
+"""ctypes declarations for libspmvb200.so -- one entry per function in include/spmv_b200.h.
+
+The library is loaded on first use.  There is no fallback of any kind: if the
+shared object is missing (not built) the import of the symbol table raises, and if
+no CUDA device is usable every compute entry point returns SPMVB200_ERR_CUDA, which
+the Python layer turns into `matrix_error`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libspmvb200.so")
+
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+f64p = C.POINTER(C.c_double)
+f32p = C.POINTER(C.c_float)
+vp = C.c_void_p
+vpp = C.POINTER(C.c_void_p)
+
+
+class Info(C.Structure):
+    """spmvb200_info"""
+    _fields_ = [
+        ("format", C.c_int32), ("coo_mode", C.c_int32),
+        ("rows", C.c_int64), ("columns", C.c_int64),
+        ("num_entries", C.c_int64), ("stored_entries", C.c_int64),
+        ("row_alignment", C.c_int64), ("ell_row_length", C.c_int64),
+        ("num_ell_entries", C.c_int64), ("num_coo_entries", C.c_int64),
+        ("skip_padding", C.c_int32), ("offsets_64bit", C.c_int32),
+        ("matrix_size", C.c_int64), ("x_size", C.c_int64), ("y_size", C.c_int64),
+        ("device_bytes", C.c_int64), ("row_offset", C.c_int64),
+    ]
+
+
+# name -> (restype, argtypes); the exported symbol set the tests check against the header
+SIGNATURES = {
+    "spmvb200_last_error": (C.c_char_p, []),
+    "spmvb200_version": (C.c_int, []),
+    "spmvb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "spmvb200_set_device": (C.c_int, [C.c_int]),
+    "spmvb200_device_props": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), i64p, i64p,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "spmvb200_launch_count": (C.c_int64, []),
+    "spmvb200_set_global_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "spmvb200_mm_parse": (C.c_int, [C.c_char_p, C.c_size_t, vpp]),
+    "spmvb200_mm_load": (C.c_int, [C.c_char_p, vpp]),
+    "spmvb200_mm_from_entries": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, i32p, i32p, f64p, vpp]),
+    "spmvb200_mm_info": (C.c_int, [vp, i32p, i32p, i32p, i32p, i32p, i32p]),
+    "spmvb200_mm_entries": (C.c_int, [vp, C.POINTER(i32p), C.POINTER(i32p), C.POINTER(f64p)]),
+    "spmvb200_mm_max_row_length": (C.c_int, [vp, i32p]),
+    "spmvb200_mm_row_lengths": (C.c_int, [vp, i32p]),
+    "spmvb200_mm_sort_row_major": (C.c_int, [vp]),
+    "spmvb200_mm_sort_column_major": (C.c_int, [vp]),
+    "spmvb200_mm_free": (None, [vp]),
+    "spmvb200_csr_from_mm": (C.c_int, [vp, C.c_int32, vpp]),
+    "spmvb200_coo_from_mm": (C.c_int, [vp, C.c_int32, vpp]),
+    "spmvb200_ell_from_mm": (C.c_int, [vp, C.c_int32, vpp]),
+    "spmvb200_hyb_from_mm": (C.c_int, [vp, C.c_int32, vpp]),
+    "spmvb200_csr_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, i32p, i32p, f64p, vpp]),
+    "spmvb200_csr_create64": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, i64p, i32p, f64p, vpp]),
+    "spmvb200_coo_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, i32p, i32p, f64p, C.c_int32, vpp]),
+    "spmvb200_ell_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, f64p, C.c_int32, vpp]),
+    "spmvb200_hyb_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, f64p, C.c_int32,
+                                      C.c_int32, i32p, i32p, f64p, vpp]),
+    "spmvb200_gen_stencil": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_int32, vpp]),
+    "spmvb200_gen_rmat": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_double, C.c_double, C.c_double,
+                                    C.c_int64, C.c_int64, C.c_int32, C.c_int32, vpp]),
+    "spmvb200_convert": (C.c_int, [vp, C.c_int32, C.c_int32, vpp]),
+    "spmvb200_matrix_info": (C.c_int, [vp, C.POINTER(Info)]),
+    "spmvb200_csr_export": (C.c_int, [vp, i64p, i32p, f64p]),
+    "spmvb200_coo_export": (C.c_int, [vp, i32p, i32p, f64p]),
+    "spmvb200_ell_export": (C.c_int, [vp, i32p, f64p]),
+    "spmvb200_hyb_export": (C.c_int, [vp, i32p, f64p, i32p, i32p, f64p]),
+    "spmvb200_set_x": (C.c_int, [vp, f64p]),
+    "spmvb200_set_y": (C.c_int, [vp, f64p]),
+    "spmvb200_get_x": (C.c_int, [vp, f64p]),
+    "spmvb200_get_y": (C.c_int, [vp, f64p]),
+    "spmvb200_fill_x": (C.c_int, [vp, C.c_double]),
+    "spmvb200_fill_y": (C.c_int, [vp, C.c_double]),
+    "spmvb200_x_device": (C.c_int, [vp, vpp]),
+    "spmvb200_y_device": (C.c_int, [vp, vpp]),
+    "spmvb200_bind_x": (C.c_int, [vp, vp]),
+    "spmvb200_bind_y": (C.c_int, [vp, vp]),
+    "spmvb200_set_stream": (C.c_int, [vp, vp]),
+    "spmvb200_host_alloc": (C.c_int, [C.c_size_t, vpp]),
+    "spmvb200_host_free": (C.c_int, [vp]),
+    "spmvb200_spmv": (C.c_int, [vp]),
+    "spmvb200_sync": (C.c_int, [vp]),
+    "spmvb200_spmv_host": (C.c_int, [vp, f64p, f64p]),
+    "spmvb200_time": (C.c_int, [vp, C.c_int, C.c_int, f32p]),
+    "spmvb200_time_rotating": (C.c_int, [vpp, C.c_int, C.c_int, C.c_int, f32p, f32p]),
+    "spmvb200_time_host_rotating": (C.c_int, [vpp, C.c_int, C.POINTER(f64p), C.POINTER(f64p), C.c_int, C.c_int,
+                                              f32p]),
+    "spmvb200_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+    "spmvb200_get_option": (C.c_int, [vp, C.c_char_p, i64p]),
+    "spmvb200_kernel_name": (C.c_char_p, [vp]),
+    "spmvb200_destroy": (C.c_int, [vp]),
+    "spmvb200_partition_rows_ref": (C.c_int, [C.c_int64, C.c_int32, i64p]),
+    "spmvb200_partition_rows_nnz": (C.c_int, [vp, C.c_int32, i64p]),
+    "spmvb200_csr_row_block": (C.c_int, [vp, C.c_int64, C.c_int64, vpp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m spmv_cache_trace_b200.build` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

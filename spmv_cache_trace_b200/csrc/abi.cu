@@ -1,0 +1,934 @@
+// abi.cu -- the extern "C" surface of libspmvb200.so (see include/spmv_b200.h).
+//
+// Thin by design: argument checks, handle bookkeeping, host<->device copies, and dispatch to the
+// builders (builders.cu, generators.cu) and kernel launchers (kernels.cu).  No arithmetic of the
+// SpMV path is done on the host anywhere in this library.
+#include "common.cuh"
+#include "mm_host.hpp"
+
+#include <atomic>
+#include <climits>
+#include <cstring>
+#include <vector>
+
+namespace spmvb200 {
+
+static thread_local std::string g_error;
+static std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_force_off64{0};
+
+void set_error(const std::string & msg) { g_error = msg; }
+int fail(int code, const std::string & msg)
+{
+    g_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char * what, const char * file, int line)
+{
+    const char * base = strrchr(file, '/');
+    g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + (base ? base + 1 : file) +
+              ":" + std::to_string(line) + ")";
+    return SPMVB200_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+// declared in builders.cu / generators.cu
+int store_offsets(Matrix * m, const int64_t * d_rp64, int64_t rows, int64_t stored);
+int gen_stencil(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end, Matrix * csr);
+int gen_rmat(int scale, int edge_factor, uint64_t seed, double a, double b, double c, int64_t row_begin,
+             int64_t row_end, Matrix * csr);
+
+__global__ void transpose_to_colmajor_kernel(int64_t rows, int64_t W, int64_t pitch, const int32_t * col_rm,
+                                             const double * val_rm, int32_t * ecol, double * eval)
+{
+    const int64_t total = rows * W;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = k / W, l = k - r * W;
+        ecol[l * pitch + r] = col_rm[k];
+        eval[l * pitch + r] = val_rm[k];
+    }
+}
+
+__global__ void transpose_to_rowmajor_kernel(int64_t rows, int64_t W, int64_t pitch, const int32_t * ecol,
+                                             const double * eval, int32_t * col_rm, double * val_rm)
+{
+    const int64_t total = rows * W;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = k / W, l = k - r * W;
+        col_rm[k] = ecol[l * pitch + r];
+        val_rm[k] = eval[l * pitch + r];
+    }
+}
+
+__global__ void zero_based_kernel(int64_t n, const int32_t * in, int32_t * out, int32_t limit, int * bad)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = in[k] - 1;
+        if (v < 0 || v >= limit) *bad = 1;
+        out[k] = v;
+    }
+}
+
+template <typename OffT>
+__global__ void partition_nnz_kernel(int64_t rows, const OffT * rp, int parts, int64_t * starts)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > parts) return;
+    if (p == 0) { starts[0] = 0; return; }
+    if (p == parts) { starts[p] = rows; return; }
+    const unsigned long long nnz = (unsigned long long)rp[rows];
+    const unsigned long long target = (unsigned long long)(((unsigned __int128)nnz * (unsigned)p) / (unsigned)parts);
+    int64_t lo = 0, hi = rows;  // first r in [0, rows] with rp[r] >= target
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if ((unsigned long long)rp[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    starts[p] = lo;
+}
+
+template <typename OffT>
+__global__ void rebase_offsets_kernel(int64_t n, const OffT * rp, int64_t first, int64_t * out)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        out[r] = (int64_t)rp[r] - first;
+}
+
+static int upload_ell_rowmajor(Matrix * m, int64_t rows, int64_t W, const int32_t * col, const double * val, int skip)
+{
+    cudaStream_t s = m->stream;
+    m->ell_w = W;
+    m->ell_pitch = round_up(std::max<int64_t>(rows, 1), 32);
+    m->skip_padding = skip;
+    const int64_t slots = m->ell_pitch * W, n = rows * W;
+    SPMV_TRY(alloc_streamed(m, &m->ell_col, slots));
+    SPMV_TRY(alloc_streamed(m, &m->ell_val, slots));
+    if (n > 0) {
+        Scratch<int32_t> dc;
+        Scratch<double> dv;
+        SPMV_TRY(dc.alloc(n)); SPMV_TRY(dv.alloc(n));
+        SPMV_CUDA(cudaMemcpyAsync(dc.p, col, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(dv.p, val, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemsetAsync(m->ell_col, 0, sizeof(int32_t) * (size_t)slots, s));
+        SPMV_CUDA(cudaMemsetAsync(m->ell_val, 0, sizeof(double) * (size_t)slots, s));
+        transpose_to_colmajor_kernel<<<grid_for(n), 256, 0, s>>>(rows, W, m->ell_pitch, dc.p, dv.p, m->ell_col, m->ell_val);
+        SPMV_CUDA(cudaGetLastError());
+        SPMV_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+static int upload_coo(Matrix * m, int64_t n, const int32_t * row, const int32_t * col, const double * val)
+{
+    cudaStream_t s = m->stream;
+    SPMV_TRY(alloc_streamed(m, &m->coo_row, n));
+    SPMV_TRY(alloc_streamed(m, &m->coo_col, n));
+    SPMV_TRY(alloc_streamed(m, &m->coo_val, n));
+    if (n > 0) {
+        SPMV_CUDA(cudaMemcpyAsync(m->coo_row, row, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(m->coo_col, col, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(m->coo_val, val, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    m->coo_n = n;
+    return 0;
+}
+
+struct Guard {  // frees a half-built matrix on early return
+    Matrix * m;
+    explicit Guard(Matrix * m) : m(m) {}
+    ~Guard() { if (m) matrix_free(m); }
+    Matrix * release() { Matrix * q = m; m = nullptr; return q; }
+};
+
+static int finish(Guard & g, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(matrix_alloc_vectors(g.m));
+    SPMV_CUDA(cudaStreamSynchronize(g.m->stream));
+    *out = g.release();
+    return 0;
+}
+
+static int check(spmvb200_matrix_t m)
+{
+    if (!m) return fail(SPMVB200_ERR_INVALID, "null matrix handle");
+    cudaError_t e = cudaSetDevice(m->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    return 0;
+}
+
+}  // namespace spmvb200
+
+using namespace spmvb200;
+
+extern "C" {
+
+const char * spmvb200_last_error(void) { return g_error.c_str(); }
+int spmvb200_version(void) { return SPMVB200_VERSION; }
+int64_t spmvb200_launch_count(void) { return g_launches.load(); }
+
+int spmvb200_set_global_option(const char * key, int64_t value)
+{
+    if (!key) return fail(SPMVB200_ERR_INVALID, "null argument");
+    if (!strcmp(key, "force_offsets64")) { g_force_off64 = value ? 1 : 0; return 0; }
+    return fail(SPMVB200_ERR_INVALID, std::string("unknown global option ") + key);
+}
+
+int spmvb200_device_count(int * count)
+{
+    if (!count) return fail(SPMVB200_ERR_INVALID, "null argument");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    return 0;
+}
+
+int spmvb200_set_device(int device)
+{
+    SPMV_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+int spmvb200_device_props(int device, char * name, size_t name_cap, int * sm_count, int64_t * l2_bytes,
+                          int64_t * mem_bytes, int * cc_major, int * cc_minor)
+{
+    cudaDeviceProp p;
+    SPMV_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name && name_cap) { strncpy(name, p.name, name_cap - 1); name[name_cap - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = p.l2CacheSize;
+    if (mem_bytes) *mem_bytes = (int64_t)p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return 0;
+}
+
+// ---- Matrix Market (host) ---------------------------------------------------------------------
+
+int spmvb200_mm_parse(const char * text, size_t len, spmvb200_mm_t * out)
+{
+    if (!text || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
+    return mm_parse_text(text, len, out);
+}
+int spmvb200_mm_load(const char * path, spmvb200_mm_t * out)
+{
+    if (!path || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
+    return mm_load_path(path, out);
+}
+int spmvb200_mm_from_entries(int32_t rows, int32_t columns, int32_t n, const int32_t * i, const int32_t * j,
+                             const double * a, spmvb200_mm_t * out)
+{
+    if (!out || rows < 0 || columns < 0 || n < 0 || (n > 0 && (!i || !j || !a)))
+        return fail(SPMVB200_ERR_INVALID, "bad argument");
+    return mm_from_entries(rows, columns, n, i, j, a, out);
+}
+int spmvb200_mm_info(spmvb200_mm_t mm, int32_t * rows, int32_t * columns, int32_t * n, int32_t * field,
+                     int32_t * symmetry, int32_t * format)
+{
+    if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
+    if (rows) *rows = mm->rows;
+    if (columns) *columns = mm->columns;
+    if (n) *n = mm->num_entries;
+    if (field) *field = mm->field;
+    if (symmetry) *symmetry = mm->symmetry;
+    if (format) *format = mm->format;
+    return 0;
+}
+int spmvb200_mm_entries(spmvb200_mm_t mm, const int32_t ** i, const int32_t ** j, const double ** a)
+{
+    if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
+    if (i) *i = mm->i.data();
+    if (j) *j = mm->j.data();
+    if (a) *a = mm->a.data();
+    return 0;
+}
+int spmvb200_mm_row_lengths(spmvb200_mm_t mm, int32_t * lengths)
+{
+    if (!mm || !lengths) return fail(SPMVB200_ERR_INVALID, "null argument");
+    return mm_row_lengths(mm, lengths);
+}
+int spmvb200_mm_max_row_length(spmvb200_mm_t mm, int32_t * out)
+{
+    if (!mm || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
+    std::vector<int32_t> len((size_t)std::max(mm->rows, 1));
+    SPMV_TRY(mm_row_lengths(mm, len.data()));
+    int32_t best = 0;
+    for (int32_t r = 0; r < mm->rows; r++) best = std::max(best, len[r]);
+    *out = best;
+    return 0;
+}
+int spmvb200_mm_sort_row_major(spmvb200_mm_t mm)
+{
+    if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
+    return mm_sort(mm, true);
+}
+int spmvb200_mm_sort_column_major(spmvb200_mm_t mm)
+{
+    if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
+    return mm_sort(mm, false);
+}
+void spmvb200_mm_free(spmvb200_mm_t mm) { delete mm; }
+
+// ---- builders from Matrix Market ----------------------------------------------------------------
+
+static int need_coordinate(spmvb200_mm_t mm, void * out)
+{
+    if (!mm || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
+    if (mm->format != 0)  // csr-matrix.cpp:197-198 and siblings
+        return fail(SPMVB200_ERR_PARSE, "Expected matrix in coordinate format");
+    return 0;
+}
+
+static int csr_from_mm(spmvb200_mm_t mm, int32_t row_alignment, Matrix ** out)
+{
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    SPMV_TRY(csr_from_entries_host(mm->rows, mm->columns, mm->num_entries, mm->i.data(), mm->j.data(), mm->a.data(),
+                                   row_alignment, m));
+    *out = g.release();
+    return 0;
+}
+
+int spmvb200_csr_from_mm(spmvb200_mm_t mm, int32_t row_alignment, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(need_coordinate(mm, out));
+    Matrix * m = nullptr;
+    SPMV_TRY(csr_from_mm(mm, row_alignment, &m));
+    Guard g(m);
+    return finish(g, out);
+}
+
+int spmvb200_coo_from_mm(spmvb200_mm_t mm, int32_t coo_mode, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(need_coordinate(mm, out));
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    const int64_t n = mm->num_entries;
+    cudaStream_t s = m->stream;
+    // file order kept, 1-based -> 0-based (coo-matrix.cpp:226-239), done on the device
+    int32_t *row = nullptr, *col = nullptr;
+    double * val = nullptr;
+    SPMV_TRY(alloc_streamed(m, &row, n));
+    SPMV_TRY(alloc_streamed(m, &col, n));
+    SPMV_TRY(alloc_streamed(m, &val, n));
+    m->coo_row = row; m->coo_col = col; m->coo_val = val;  // owned from here on
+    if (n > 0) {
+        Scratch<int32_t> t;
+        Scratch<int> bad;
+        SPMV_TRY(t.alloc(n)); SPMV_TRY(bad.alloc(1));
+        SPMV_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+        SPMV_CUDA(cudaMemcpyAsync(t.p, mm->i.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        zero_based_kernel<<<grid_for(n), 256, 0, s>>>(n, t.p, row, mm->rows, bad.p);
+        SPMV_CUDA(cudaMemcpyAsync(t.p, mm->j.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        zero_based_kernel<<<grid_for(n), 256, 0, s>>>(n, t.p, col, mm->columns, bad.p);
+        SPMV_CUDA(cudaGetLastError());
+        SPMV_CUDA(cudaMemcpyAsync(val, mm->a.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        int hbad = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        if (hbad) return fail(SPMVB200_ERR_INVALID, "entry index outside the matrix");
+    }
+    m->nnz = n;
+    SPMV_TRY(coo_adopt(m, mm->rows, mm->columns, n, row, col, val, coo_mode, false));
+    return finish(g, out);
+}
+
+int spmvb200_ell_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(need_coordinate(mm, out));
+    Matrix * csr = nullptr;
+    SPMV_TRY(csr_from_mm(mm, 1, &csr));
+    Guard gc(csr);
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    SPMV_TRY(ell_from_csr(csr, skip_padding, true, m));
+    return finish(g, out);
+}
+
+int spmvb200_hyb_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(need_coordinate(mm, out));
+    Matrix * csr = nullptr;
+    SPMV_TRY(csr_from_mm(mm, 1, &csr));
+    Guard gc(csr);
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    SPMV_TRY(hyb_from_csr(csr, skip_padding, true, m));
+    return finish(g, out);
+}
+
+// ---- from converted host arrays --------------------------------------------------------------------
+
+int spmvb200_csr_create64(int64_t rows, int64_t columns, int64_t num_entries, const int64_t * row_ptr,
+                          const int32_t * column_index, const double * value, spmvb200_matrix_t * out)
+{
+    if (!out || rows < 0 || columns < 0 || !row_ptr) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    if (rows >= INT32_MAX || columns >= INT32_MAX) return fail(SPMVB200_ERR_UNSUPPORTED, "rows/columns must fit int32");
+    const int64_t stored = row_ptr[rows];
+    if (stored < 0 || (stored > 0 && (!column_index || !value))) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    cudaStream_t s = m->stream;
+    m->format = SPMVB200_CSR;
+    m->rows = rows; m->cols = columns; m->nnz = num_entries; m->stored = stored;
+    SPMV_TRY(alloc_streamed(m, &m->col, stored));
+    SPMV_TRY(alloc_streamed(m, &m->val, stored));
+    if (stored > 0) {
+        SPMV_CUDA(cudaMemcpyAsync(m->col, column_index, sizeof(int32_t) * (size_t)stored, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(m->val, value, sizeof(double) * (size_t)stored, cudaMemcpyHostToDevice, s));
+    }
+    Scratch<int64_t> rp64;
+    SPMV_TRY(rp64.alloc(rows + 1));
+    SPMV_CUDA(cudaMemcpyAsync(rp64.p, row_ptr, sizeof(int64_t) * (size_t)(rows + 1), cudaMemcpyHostToDevice, s));
+    SPMV_TRY(store_offsets(m, rp64.p, rows, stored));
+    SPMV_TRY(csr_build_tiles(m));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return finish(g, out);
+}
+
+int spmvb200_csr_create(int32_t rows, int32_t columns, int32_t num_entries, const int32_t * row_ptr,
+                        const int32_t * column_index, const double * value, spmvb200_matrix_t * out)
+{
+    if (!out || rows < 0 || !row_ptr) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    std::vector<int64_t> rp((size_t)rows + 1);
+    for (int32_t r = 0; r <= rows; r++) rp[r] = row_ptr[r];
+    return spmvb200_csr_create64(rows, columns, num_entries, rp.data(), column_index, value, out);
+}
+
+int spmvb200_coo_create(int32_t rows, int32_t columns, int64_t n, const int32_t * row_index,
+                        const int32_t * column_index, const double * value, int32_t coo_mode,
+                        spmvb200_matrix_t * out)
+{
+    if (!out || rows < 0 || columns < 0 || n < 0 || (n > 0 && (!row_index || !column_index || !value)))
+        return fail(SPMVB200_ERR_INVALID, "bad argument");
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    SPMV_TRY(upload_coo(m, n, row_index, column_index, value));
+    m->nnz = n;
+    SPMV_TRY(coo_adopt(m, rows, columns, n, m->coo_row, m->coo_col, m->coo_val, coo_mode, false));
+    return finish(g, out);
+}
+
+int spmvb200_ell_create(int32_t rows, int32_t columns, int32_t num_entries, int32_t row_length,
+                        const int32_t * column_index, const double * value, int32_t skip_padding,
+                        spmvb200_matrix_t * out)
+{
+    if (!out || rows < 0 || columns < 0 || row_length < 0) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    if ((int64_t)rows * row_length > 0 && (!column_index || !value)) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    m->format = SPMVB200_ELL;
+    m->rows = rows; m->cols = columns; m->nnz = num_entries; m->stored = (int64_t)rows * row_length;
+    SPMV_TRY(upload_ell_rowmajor(m, rows, row_length, column_index, value, skip_padding));
+    return finish(g, out);
+}
+
+int spmvb200_hyb_create(int32_t rows, int32_t columns, int32_t num_entries, int32_t ell_row_length,
+                        const int32_t * ell_column_index, const double * ell_value, int32_t ell_skip_padding,
+                        int32_t num_coo_entries, const int32_t * coo_row_index, const int32_t * coo_column_index,
+                        const double * coo_value, spmvb200_matrix_t * out)
+{
+    if (!out || rows < 0 || columns < 0 || ell_row_length < 0 || num_coo_entries < 0)
+        return fail(SPMVB200_ERR_INVALID, "bad argument");
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    m->format = SPMVB200_HYB;
+    m->rows = rows; m->cols = columns; m->nnz = num_entries;
+    m->n_ell = (int64_t)rows * ell_row_length; m->n_coo = num_coo_entries;
+    m->stored = m->n_ell + m->n_coo;
+    SPMV_TRY(upload_ell_rowmajor(m, rows, ell_row_length, ell_column_index, ell_value, ell_skip_padding));
+    SPMV_TRY(upload_coo(m, num_coo_entries, coo_row_index, coo_column_index, coo_value));
+    // the reference builds the tail row-major sorted (hybrid-matrix.cpp:402-408); verify, sort if not
+    const int keep_format = m->format;
+    const int64_t keep_nnz = m->nnz, keep_stored = m->stored;
+    SPMV_TRY(coo_adopt(m, rows, columns, num_coo_entries, m->coo_row, m->coo_col, m->coo_val,
+                       SPMVB200_COO_SEGMENTED, false));
+    m->format = keep_format; m->nnz = keep_nnz; m->stored = keep_stored;
+    return finish(g, out);
+}
+
+// ---- generators / conversion -------------------------------------------------------------------------
+
+static int convert_from_csr(Matrix * csr, int32_t format, int32_t arg, bool check_int32, spmvb200_matrix_t * out)
+{
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    if (format == SPMVB200_ELL) SPMV_TRY(ell_from_csr(csr, arg, check_int32, m));
+    else if (format == SPMVB200_HYB) SPMV_TRY(hyb_from_csr(csr, arg, check_int32, m));
+    else if (format == SPMVB200_COO) SPMV_TRY(coo_from_csr(csr, arg, m));
+    else return fail(SPMVB200_ERR_INVALID, "unknown target format");
+    m->row_offset = csr->row_offset;
+    return finish(g, out);
+}
+
+int spmvb200_convert(spmvb200_matrix_t src, int32_t format, int32_t arg, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(check(src));
+    if (!out) return fail(SPMVB200_ERR_INVALID, "null argument");
+    if (src->format != SPMVB200_CSR || src->row_alignment != 1)
+        return fail(SPMVB200_ERR_UNSUPPORTED, "conversion source must be an unpadded CSR matrix");
+    SPMV_CUDA(cudaStreamSynchronize(src->stream));
+    return convert_from_csr(src, format, arg, false, out);
+}
+
+int spmvb200_gen_stencil(int32_t kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end,
+                         int32_t format, spmvb200_matrix_t * out)
+{
+    if (!out || nx < 1 || ny < 1 || nz < 1) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    const int64_t n = nx * ny * nz;
+    if (row_begin == 0 && row_end == 0) row_end = n;
+    if (row_begin < 0 || row_end > n || row_begin > row_end) return fail(SPMVB200_ERR_INVALID, "bad row range");
+    if (n >= INT32_MAX) return fail(SPMVB200_ERR_UNSUPPORTED, "grid too large for int32 column indices");
+    Matrix * csr = nullptr;
+    SPMV_TRY(matrix_new(&csr));
+    Guard g(csr);
+    SPMV_TRY(gen_stencil(kind, nx, ny, nz, row_begin, row_end, csr));
+    if (format == SPMVB200_CSR) return finish(g, out);
+    return convert_from_csr(csr, format, 0, false, out);
+}
+
+int spmvb200_gen_rmat(int32_t scale, int32_t edge_factor, uint64_t seed, double a, double b, double c,
+                      int64_t row_begin, int64_t row_end, int32_t format, int32_t coo_mode, spmvb200_matrix_t * out)
+{
+    if (!out || scale < 1 || scale > 30 || edge_factor < 1) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    const int64_t n = (int64_t)1 << scale;
+    if (row_begin == 0 && row_end == 0) row_end = n;
+    if (row_begin < 0 || row_end > n || row_begin > row_end) return fail(SPMVB200_ERR_INVALID, "bad row range");
+    Matrix * csr = nullptr;
+    SPMV_TRY(matrix_new(&csr));
+    Guard g(csr);
+    SPMV_TRY(gen_rmat(scale, edge_factor, seed, a, b, c, row_begin, row_end, csr));
+    if (format == SPMVB200_CSR) return finish(g, out);
+    return convert_from_csr(csr, format, format == SPMVB200_COO ? coo_mode : 0, false, out);
+}
+
+// ---- inspection / export ----------------------------------------------------------------------------------
+
+int spmvb200_matrix_info(spmvb200_matrix_t m, spmvb200_info * info)
+{
+    if (!m || !info) return fail(SPMVB200_ERR_INVALID, "null argument");
+    memset(info, 0, sizeof *info);
+    info->format = m->format; info->coo_mode = m->coo_mode;
+    info->rows = m->rows; info->columns = m->cols; info->num_entries = m->nnz;
+    info->stored_entries = m->stored; info->row_alignment = m->row_alignment;
+    info->ell_row_length = m->ell_w; info->num_ell_entries = m->n_ell; info->num_coo_entries = m->n_coo;
+    info->skip_padding = m->skip_padding; info->offsets_64bit = m->off64 ? 1 : 0;
+    switch (m->format) {
+    case SPMVB200_CSR: info->matrix_size = 12 * m->stored + 4 * (m->rows + 1); break;  // csr-matrix.cpp:46-60
+    case SPMVB200_COO: info->matrix_size = 16 * m->stored; break;                      // coo-matrix.cpp:49-63
+    case SPMVB200_ELL: info->matrix_size = 12 * m->rows * m->ell_w; break;             // ell-matrix.cpp:52-65
+    case SPMVB200_HYB: info->matrix_size = 12 * m->n_ell + 16 * m->n_coo; break;
+    }
+    info->x_size = 8 * m->cols; info->y_size = 8 * m->rows;
+    info->device_bytes = m->device_bytes; info->row_offset = m->row_offset;
+    return 0;
+}
+
+int spmvb200_csr_export(spmvb200_matrix_t m, int64_t * row_ptr, int32_t * column_index, double * value)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_CSR) return fail(SPMVB200_ERR_INVALID, "not a CSR matrix");
+    cudaStream_t s = m->stream;
+    if (row_ptr) {
+        if (m->off64) {
+            SPMV_CUDA(cudaMemcpyAsync(row_ptr, m->rp, sizeof(int64_t) * (size_t)(m->rows + 1), cudaMemcpyDeviceToHost, s));
+            SPMV_CUDA(cudaStreamSynchronize(s));
+        } else {
+            std::vector<uint32_t> t((size_t)m->rows + 1);
+            SPMV_CUDA(cudaMemcpyAsync(t.data(), m->rp, sizeof(uint32_t) * t.size(), cudaMemcpyDeviceToHost, s));
+            SPMV_CUDA(cudaStreamSynchronize(s));
+            for (size_t r = 0; r < t.size(); r++) row_ptr[r] = t[r];
+        }
+    }
+    if (column_index && m->stored) SPMV_CUDA(cudaMemcpyAsync(column_index, m->col, sizeof(int32_t) * (size_t)m->stored, cudaMemcpyDeviceToHost, s));
+    if (value && m->stored) SPMV_CUDA(cudaMemcpyAsync(value, m->val, sizeof(double) * (size_t)m->stored, cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int export_coo_arrays(Matrix * m, int32_t * row, int32_t * col, double * val)
+{
+    cudaStream_t s = m->stream;
+    const size_t n = (size_t)m->coo_n;
+    if (n) {
+        if (row) SPMV_CUDA(cudaMemcpyAsync(row, m->coo_row, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+        if (col) SPMV_CUDA(cudaMemcpyAsync(col, m->coo_col, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+        if (val) SPMV_CUDA(cudaMemcpyAsync(val, m->coo_val, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    }
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int export_ell_arrays(Matrix * m, int32_t * col_rm, double * val_rm)
+{
+    cudaStream_t s = m->stream;
+    const int64_t n = m->rows * m->ell_w;
+    if (n == 0) return 0;
+    Scratch<int32_t> dc;
+    Scratch<double> dv;
+    SPMV_TRY(dc.alloc(n)); SPMV_TRY(dv.alloc(n));
+    transpose_to_rowmajor_kernel<<<grid_for(n), 256, 0, s>>>(m->rows, m->ell_w, m->ell_pitch, m->ell_col, m->ell_val, dc.p, dv.p);
+    SPMV_CUDA(cudaGetLastError());
+    if (col_rm) SPMV_CUDA(cudaMemcpyAsync(col_rm, dc.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (val_rm) SPMV_CUDA(cudaMemcpyAsync(val_rm, dv.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int spmvb200_coo_export(spmvb200_matrix_t m, int32_t * row_index, int32_t * column_index, double * value)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_COO) return fail(SPMVB200_ERR_INVALID, "not a COO matrix");
+    return export_coo_arrays(m, row_index, column_index, value);
+}
+
+int spmvb200_ell_export(spmvb200_matrix_t m, int32_t * column_index, double * value)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_ELL) return fail(SPMVB200_ERR_INVALID, "not an ELL matrix");
+    return export_ell_arrays(m, column_index, value);
+}
+
+int spmvb200_hyb_export(spmvb200_matrix_t m, int32_t * ell_column_index, double * ell_value, int32_t * coo_row_index,
+                        int32_t * coo_column_index, double * coo_value)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_HYB) return fail(SPMVB200_ERR_INVALID, "not a hybrid matrix");
+    SPMV_TRY(export_ell_arrays(m, ell_column_index, ell_value));
+    return export_coo_arrays(m, coo_row_index, coo_column_index, coo_value);
+}
+
+// ---- vectors ---------------------------------------------------------------------------------------------------
+
+int spmvb200_set_x(spmvb200_matrix_t m, const double * x)
+{
+    SPMV_TRY(check(m));
+    if (!x) return fail(SPMVB200_ERR_INVALID, "null argument");
+    SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+int spmvb200_set_y(spmvb200_matrix_t m, const double * y)
+{
+    SPMV_TRY(check(m));
+    if (!y) return fail(SPMVB200_ERR_INVALID, "null argument");
+    SPMV_CUDA(cudaMemcpyAsync(m->y, y, sizeof(double) * (size_t)m->rows, cudaMemcpyHostToDevice, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+int spmvb200_get_x(spmvb200_matrix_t m, double * x)
+{
+    SPMV_TRY(check(m));
+    if (!x) return fail(SPMVB200_ERR_INVALID, "null argument");
+    SPMV_CUDA(cudaMemcpyAsync(x, m->x, sizeof(double) * (size_t)m->cols, cudaMemcpyDeviceToHost, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+int spmvb200_get_y(spmvb200_matrix_t m, double * y)
+{
+    SPMV_TRY(check(m));
+    if (!y) return fail(SPMVB200_ERR_INVALID, "null argument");
+    SPMV_CUDA(cudaMemcpyAsync(y, m->y, sizeof(double) * (size_t)m->rows, cudaMemcpyDeviceToHost, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+int spmvb200_fill_x(spmvb200_matrix_t m, double v)
+{
+    SPMV_TRY(check(m));
+    return fill_device(m->x, m->cols, v, m->stream);
+}
+int spmvb200_fill_y(spmvb200_matrix_t m, double v)
+{
+    SPMV_TRY(check(m));
+    return fill_device(m->y, m->rows, v, m->stream);
+}
+int spmvb200_x_device(spmvb200_matrix_t m, void ** p)
+{
+    if (!m || !p) return fail(SPMVB200_ERR_INVALID, "null argument");
+    *p = m->x;
+    return 0;
+}
+int spmvb200_y_device(spmvb200_matrix_t m, void ** p)
+{
+    if (!m || !p) return fail(SPMVB200_ERR_INVALID, "null argument");
+    *p = m->y;
+    return 0;
+}
+int spmvb200_bind_x(spmvb200_matrix_t m, void * p)
+{
+    SPMV_TRY(check(m));
+    if (!p) return fail(SPMVB200_ERR_INVALID, "null argument");
+    if (m->own_x) { cudaFree(m->x); m->device_bytes -= 8 * (m->cols + 8); }
+    m->x = (double *)p; m->own_x = false;
+    return 0;
+}
+int spmvb200_bind_y(spmvb200_matrix_t m, void * p)
+{
+    SPMV_TRY(check(m));
+    if (!p) return fail(SPMVB200_ERR_INVALID, "null argument");
+    if (m->own_y) { cudaFree(m->y); m->device_bytes -= 8 * (m->rows + 8); }
+    m->y = (double *)p; m->own_y = false;
+    return 0;
+}
+int spmvb200_set_stream(spmvb200_matrix_t m, void * stream)
+{
+    SPMV_TRY(check(m));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->own_stream) cudaStreamDestroy(m->stream);
+    m->stream = (cudaStream_t)stream; m->own_stream = false;
+    return 0;
+}
+int spmvb200_host_alloc(size_t bytes, void ** p)
+{
+    if (!p) return fail(SPMVB200_ERR_INVALID, "null argument");
+    SPMV_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return 0;
+}
+int spmvb200_host_free(void * p)
+{
+    SPMV_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+// ---- run ----------------------------------------------------------------------------------------------------------
+
+static int launch(Matrix * m)
+{
+    if (m->opt_beta0) SPMV_CUDA(cudaMemsetAsync(m->y, 0, sizeof(double) * (size_t)m->rows, m->stream));
+    switch (m->format) {
+    case SPMVB200_CSR: return launch_csr(m);
+    case SPMVB200_ELL: return launch_ell(m, true);
+    case SPMVB200_COO: return launch_coo(m);
+    case SPMVB200_HYB:
+        // ELL pass, then the COO tail adds into the same y (hybrid-matrix.cpp:547-566)
+        SPMV_TRY(launch_ell(m, true));
+        SPMV_TRY(launch_coo(m));
+        m->kernel_name = "ell_kernel+coo_segmented_kernel";
+        return 0;
+    }
+    return fail(SPMVB200_ERR_INVALID, "unknown format");
+}
+
+int spmvb200_spmv(spmvb200_matrix_t m)
+{
+    SPMV_TRY(check(m));
+    return launch(m);
+}
+
+int spmvb200_sync(spmvb200_matrix_t m)
+{
+    SPMV_TRY(check(m));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
+{
+    SPMV_TRY(check(m));
+    if (!x || !y) return fail(SPMVB200_ERR_INVALID, "null argument");
+    cudaStream_t s = m->stream;
+    SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
+    if (!m->opt_beta0) SPMV_CUDA(cudaMemcpyAsync(m->y, y, sizeof(double) * (size_t)m->rows, cudaMemcpyHostToDevice, s));
+    SPMV_TRY(launch(m));
+    SPMV_CUDA(cudaMemcpyAsync(y, m->y, sizeof(double) * (size_t)m->rows, cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int spmvb200_time(spmvb200_matrix_t m, int warmup, int reps, float * ms)
+{
+    SPMV_TRY(check(m));
+    if (reps < 0 || warmup < 0 || (reps > 0 && !ms)) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    for (int w = 0; w < warmup; w++) SPMV_TRY(launch(m));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    for (int r = 0; r < reps; r++) {
+        SPMV_CUDA(cudaEventRecord(m->ev0, m->stream));
+        SPMV_TRY(launch(m));
+        SPMV_CUDA(cudaEventRecord(m->ev1, m->stream));
+        SPMV_CUDA(cudaEventSynchronize(m->ev1));
+        SPMV_CUDA(cudaEventElapsedTime(&ms[r], m->ev0, m->ev1));
+    }
+    return 0;
+}
+
+int spmvb200_time_rotating(const spmvb200_matrix_t * ms, int n, int warmup, int steps, float * total_ms,
+                           float * per_launch_ms)
+{
+    if (!ms || n < 1 || steps < 1 || warmup < 0 || !total_ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    for (int k = 0; k < n; k++) SPMV_TRY(check(ms[k]));
+    cudaStream_t s = ms[0]->stream;
+    std::vector<cudaStream_t> saved(n);
+    for (int k = 0; k < n; k++) {
+        SPMV_CUDA(cudaStreamSynchronize(ms[k]->stream));
+        saved[k] = ms[k]->stream;
+        ms[k]->stream = s;
+    }
+    int rc = 0;
+    auto run = [&]() -> int {
+        for (int w = 0; w < warmup; w++) SPMV_TRY(launch(ms[w % n]));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        SPMV_CUDA(cudaEventRecord(ms[0]->ev0, s));
+        for (int k = 0; k < steps; k++) SPMV_TRY(launch(ms[(warmup + k) % n]));
+        SPMV_CUDA(cudaEventRecord(ms[0]->ev1, s));
+        SPMV_CUDA(cudaEventSynchronize(ms[0]->ev1));
+        SPMV_CUDA(cudaEventElapsedTime(total_ms, ms[0]->ev0, ms[0]->ev1));
+        if (per_launch_ms) {
+            std::vector<cudaEvent_t> ev((size_t)steps + 1);
+            for (auto & e : ev) SPMV_CUDA(cudaEventCreate(&e));
+            SPMV_CUDA(cudaEventRecord(ev[0], s));
+            for (int k = 0; k < steps; k++) {
+                SPMV_TRY(launch(ms[(warmup + k) % n]));
+                SPMV_CUDA(cudaEventRecord(ev[(size_t)k + 1], s));
+            }
+            SPMV_CUDA(cudaEventSynchronize(ev[(size_t)steps]));
+            for (int k = 0; k < steps; k++) SPMV_CUDA(cudaEventElapsedTime(&per_launch_ms[k], ev[k], ev[(size_t)k + 1]));
+            for (auto & e : ev) cudaEventDestroy(e);
+        }
+        return 0;
+    };
+    rc = run();
+    for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
+    return rc;
+}
+
+int spmvb200_time_host_rotating(const spmvb200_matrix_t * ms, int n, const double * const * xs, double * const * ys,
+                                int warmup, int steps, float * total_ms)
+{
+    if (!ms || !xs || !ys || n < 1 || steps < 1 || warmup < 0 || !total_ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    for (int k = 0; k < n; k++) SPMV_TRY(check(ms[k]));
+    cudaStream_t s = ms[0]->stream;
+    std::vector<cudaStream_t> saved(n);
+    for (int k = 0; k < n; k++) {
+        SPMV_CUDA(cudaStreamSynchronize(ms[k]->stream));
+        saved[k] = ms[k]->stream;
+        ms[k]->stream = s;
+    }
+    auto run = [&]() -> int {
+        for (int w = 0; w < warmup; w++) SPMV_TRY(spmvb200_spmv_host(ms[w % n], xs[w % n], ys[w % n]));
+        SPMV_CUDA(cudaEventRecord(ms[0]->ev0, s));
+        for (int k = 0; k < steps; k++) {
+            const int c = (warmup + k) % n;
+            SPMV_TRY(spmvb200_spmv_host(ms[c], xs[c], ys[c]));
+        }
+        SPMV_CUDA(cudaEventRecord(ms[0]->ev1, s));
+        SPMV_CUDA(cudaEventSynchronize(ms[0]->ev1));
+        SPMV_CUDA(cudaEventElapsedTime(total_ms, ms[0]->ev0, ms[0]->ev1));
+        return 0;
+    };
+    int rc = run();
+    for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
+    return rc;
+}
+
+static int64_t * option_slot(Matrix * m, const char * key)
+{
+    if (!strcmp(key, "csr.tile")) return &m->opt_csr_tile;
+    if (!strcmp(key, "csr.stages")) return &m->opt_csr_stages;
+    if (!strcmp(key, "csr.ctas_per_sm")) return &m->opt_csr_ctas;
+    if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
+    if (!strcmp(key, "ell.block")) return &m->opt_ell_block;
+    if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;
+    if (!strcmp(key, "coo.ctas_per_sm")) return &m->opt_coo_ctas;
+    if (!strcmp(key, "beta0")) return &m->opt_beta0;
+    return nullptr;
+}
+
+int spmvb200_set_option(spmvb200_matrix_t m, const char * key, int64_t value)
+{
+    if (!m || !key) return fail(SPMVB200_ERR_INVALID, "null argument");
+    int64_t * slot = option_slot(m, key);
+    if (!slot) return fail(SPMVB200_ERR_INVALID, std::string("unknown option ") + key);
+    *slot = value;
+    return 0;
+}
+
+int spmvb200_get_option(spmvb200_matrix_t m, const char * key, int64_t * value)
+{
+    if (!m || !key || !value) return fail(SPMVB200_ERR_INVALID, "null argument");
+    int64_t * slot = option_slot(m, key);
+    if (!slot) return fail(SPMVB200_ERR_INVALID, std::string("unknown option ") + key);
+    *value = *slot;
+    return 0;
+}
+
+const char * spmvb200_kernel_name(spmvb200_matrix_t m) { return m ? m->kernel_name : ""; }
+
+int spmvb200_destroy(spmvb200_matrix_t m)
+{
+    matrix_free(m);
+    return 0;
+}
+
+// ---- row partition ---------------------------------------------------------------------------------------------------
+
+int spmvb200_partition_rows_ref(int64_t rows, int32_t parts, int64_t * starts)
+{
+    if (rows < 0 || parts < 1 || !starts) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    const int64_t rpt = (rows + parts - 1) / parts;  // csr-matrix.cpp:79
+    for (int32_t p = 0; p <= parts; p++) starts[p] = std::min<int64_t>(rows, (int64_t)p * rpt);
+    return 0;
+}
+
+int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t * starts)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_CSR || parts < 1 || !starts) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    Scratch<int64_t> d;
+    SPMV_TRY(d.alloc(parts + 1));
+    const unsigned grid = (unsigned)((parts + 1 + 63) / 64);
+    if (m->off64) partition_nnz_kernel<int64_t><<<grid, 64, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, parts, d.p);
+    else partition_nnz_kernel<uint32_t><<<grid, 64, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, parts, d.p);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(cudaMemcpyAsync(starts, d.p, sizeof(int64_t) * (size_t)(parts + 1), cudaMemcpyDeviceToHost, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int spmvb200_csr_row_block(spmvb200_matrix_t src, int64_t row_begin, int64_t row_end, spmvb200_matrix_t * out)
+{
+    SPMV_TRY(check(src));
+    if (!out || src->format != SPMVB200_CSR || row_begin < 0 || row_end > src->rows || row_begin > row_end)
+        return fail(SPMVB200_ERR_INVALID, "bad argument");
+    cudaStream_t s0 = src->stream;
+    SPMV_CUDA(cudaStreamSynchronize(s0));
+    int64_t first = 0, last = 0;
+    const size_t osz = src->off64 ? 8 : 4;
+    uint64_t tmp[2] = {0, 0};
+    SPMV_CUDA(cudaMemcpy(&tmp[0], (const char *)src->rp + osz * (size_t)row_begin, osz, cudaMemcpyDeviceToHost));
+    SPMV_CUDA(cudaMemcpy(&tmp[1], (const char *)src->rp + osz * (size_t)row_end, osz, cudaMemcpyDeviceToHost));
+    first = src->off64 ? (int64_t)tmp[0] : (int64_t)(uint32_t)tmp[0];
+    last = src->off64 ? (int64_t)tmp[1] : (int64_t)(uint32_t)tmp[1];
+    const int64_t rows = row_end - row_begin, stored = last - first;
+    Matrix * m = nullptr;
+    SPMV_TRY(matrix_new(&m));
+    Guard g(m);
+    cudaStream_t s = m->stream;
+    m->format = SPMVB200_CSR;
+    m->rows = rows; m->cols = src->cols; m->nnz = stored; m->stored = stored;
+    m->row_alignment = src->row_alignment;
+    m->row_offset = src->row_offset + row_begin;
+    SPMV_TRY(alloc_streamed(m, &m->col, stored));
+    SPMV_TRY(alloc_streamed(m, &m->val, stored));
+    if (stored > 0) {
+        SPMV_CUDA(cudaMemcpyAsync(m->col, src->col + first, sizeof(int32_t) * (size_t)stored, cudaMemcpyDeviceToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(m->val, src->val + first, sizeof(double) * (size_t)stored, cudaMemcpyDeviceToDevice, s));
+    }
+    Scratch<int64_t> rp64;
+    SPMV_TRY(rp64.alloc(rows + 1));
+    if (src->off64) rebase_offsets_kernel<int64_t><<<grid_for(rows + 1), 256, 0, s>>>(rows + 1, (const int64_t *)src->rp + row_begin, first, rp64.p);
+    else rebase_offsets_kernel<uint32_t><<<grid_for(rows + 1), 256, 0, s>>>(rows + 1, (const uint32_t *)src->rp + row_begin, first, rp64.p);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_TRY(store_offsets(m, rp64.p, rows, stored));
+    SPMV_TRY(csr_build_tiles(m));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return finish(g, out);
+}
+
+}  // extern "C"

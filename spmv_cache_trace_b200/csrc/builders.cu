@@ -1,0 +1,561 @@
+// builders.cu -- device-resident matrix builders.
+//
+// They replace the reference's host converters
+//   csr_matrix::from_matrix_market_row_aligned   matrix/csr-matrix.cpp:193-243
+//   coo_matrix::from_matrix_market               matrix/coo-matrix.cpp:220-243
+//   ell_matrix::from_matrix_market               matrix/ell-matrix.cpp:190-238
+//   hybrid_matrix::from_matrix_market            matrix/hybrid-matrix.cpp:316-417
+// and must produce bit-identical arrays (checked by tests/test_gpu_parity.py through the export
+// functions).  Everything runs on the GPU: the row-major sort is a stable 64-bit LSD radix sort of
+// (row << 32 | column) keys, row pointers are binary searches in the sorted keys, padding and the
+// ELL/COO split are closed-form per row.  Sorting and prefix sums use CUB (shipped with the CUDA
+// toolkit); they are one-time set-up work, not part of the timed SpMV path.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <atomic>
+#include <climits>
+#include <vector>
+
+namespace spmvb200 {
+
+// ---------------------------------------------------------------------------------------------
+// handle life cycle
+// ---------------------------------------------------------------------------------------------
+
+__global__ void fill_kernel(double * p, int64_t n, double v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+int fill_device(double * p, int64_t n, double v, cudaStream_t s)
+{
+    if (n <= 0) return 0;
+    int64_t grid = std::min<int64_t>((n + 255) / 256, 148 * 16);
+    fill_kernel<<<(unsigned)grid, 256, 0, s>>>(p, n, v);
+    SPMV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int matrix_new(Matrix ** out)
+{
+    *out = nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice (is a CUDA device present?)", __FILE__, __LINE__);
+    Matrix * m = new Matrix();
+    m->device = dev;
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaDeviceGetAttribute", __FILE__, __LINE__); }
+    m->sm_count = sms > 0 ? sms : 148;
+    e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    m->own_stream = true;
+    cudaEventCreate(&m->ev0);
+    cudaEventCreate(&m->ev1);
+    *out = m;
+    return 0;
+}
+
+int matrix_alloc_vectors(Matrix * m)
+{
+    // x = 1.0, y = 0.0 as Kernel::init does (reference kernels/csr-spmv.cpp:35-36).
+    SPMV_TRY(dev_alloc(m, &m->x, m->cols + 8));
+    SPMV_TRY(dev_alloc(m, &m->y, m->rows + 8));
+    m->own_x = m->own_y = true;
+    SPMV_TRY(fill_device(m->x, m->cols + 8, 1.0, m->stream));
+    SPMV_CUDA(cudaMemsetAsync(m->y, 0, sizeof(double) * (size_t)(m->rows + 8), m->stream));
+    return 0;
+}
+
+void matrix_free(Matrix * m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->rp); cudaFree(m->col); cudaFree(m->val); cudaFree(m->tile_row);
+    cudaFree(m->ell_col); cudaFree(m->ell_val);
+    cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
+    if (m->own_x) cudaFree(m->x);
+    if (m->own_y) cudaFree(m->y);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+static int bits_for(int64_t n)  // number of bits needed to represent values in [0, n)
+{
+    int b = 1;
+    while (b < 63 && ((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR from unsorted 1-based entries
+// ---------------------------------------------------------------------------------------------
+
+__global__ void make_keys_kernel(int64_t n, const int32_t * i, const int32_t * j, int32_t rows, int32_t cols,
+                                 uint64_t * keys, uint32_t * idx, int * bad)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = i[k] - 1, c = j[k] - 1;
+        if (r < 0 || r >= rows || c < 0 || c >= cols) *bad = 1;
+        keys[k] = ((uint64_t)(uint32_t)r << 32) | (uint32_t)c;
+        idx[k] = (uint32_t)k;
+    }
+}
+
+// rp_raw[r] = number of sorted keys with row < r  (r in [0, rows])
+__global__ void row_lower_bound_kernel(int64_t rows, int64_t n, const uint64_t * keys, int64_t * rp_raw)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t target = (uint64_t)r << 32;
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        rp_raw[r] = lo;
+    }
+}
+
+__global__ void aligned_len_kernel(int64_t rows, const int64_t * rp_raw, int64_t align, int64_t * len_al)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x)
+        len_al[r] = r < rows ? (rp_raw[r + 1] - rp_raw[r] + align - 1) / align * align : 0;
+}
+
+template <typename OffT>
+__global__ void narrow_offsets_kernel(int64_t n, const int64_t * in, OffT * out)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        out[r] = (OffT)in[r];
+}
+
+// Sorted entry k (row r) goes to rp[r] + (k - rp_raw[r]).
+__global__ void scatter_sorted_kernel(int64_t n, const uint64_t * keys, const uint32_t * idx, const double * a,
+                                      const int64_t * rp_raw, const int64_t * rp, int32_t * col, double * val)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[k];
+        const int64_t r = (int64_t)(key >> 32);
+        const int64_t d = rp[r] + (k - rp_raw[r]);
+        col[d] = (int32_t)(uint32_t)key;
+        val[d] = a[idx[k]];
+    }
+}
+
+extern std::atomic<int> g_force_off64;
+
+int store_offsets(Matrix * m, const int64_t * d_rp64, int64_t rows, int64_t stored)
+{
+    m->off64 = stored >= ((int64_t)1 << 32) || g_force_off64.load() != 0;
+    if (m->off64) {
+        int64_t * rp = nullptr;
+        SPMV_TRY(dev_alloc(m, &rp, rows + 1 + 64));
+        SPMV_CUDA(cudaMemcpyAsync(rp, d_rp64, sizeof(int64_t) * (size_t)(rows + 1), cudaMemcpyDeviceToDevice, m->stream));
+        m->rp = rp;
+    } else {
+        uint32_t * rp = nullptr;
+        SPMV_TRY(dev_alloc(m, &rp, rows + 1 + 64));
+        narrow_offsets_kernel<uint32_t><<<grid_for(rows + 1), 256, 0, m->stream>>>(rows + 1, d_rp64, rp);
+        SPMV_CUDA(cudaGetLastError());
+        m->rp = rp;
+    }
+    return 0;
+}
+
+int csr_from_entries_host(int64_t rows, int64_t cols, int64_t n, const int32_t * hi, const int32_t * hj,
+                          const double * ha, int32_t row_alignment, Matrix * m)
+{
+    if (row_alignment < 1) return fail(SPMVB200_ERR_INVALID, "row_alignment must be >= 1");
+    cudaStream_t s = m->stream;
+    Scratch<int32_t> di, dj;
+    Scratch<double> da;
+    Scratch<uint64_t> keys, keys2;
+    Scratch<uint32_t> idx, idx2;
+    Scratch<int64_t> rp_raw, len_al, rp_al;
+    Scratch<int> bad;
+    Scratch<unsigned char> tmp;
+    SPMV_TRY(di.alloc(n)); SPMV_TRY(dj.alloc(n)); SPMV_TRY(da.alloc(n));
+    SPMV_TRY(keys.alloc(n)); SPMV_TRY(keys2.alloc(n)); SPMV_TRY(idx.alloc(n)); SPMV_TRY(idx2.alloc(n));
+    SPMV_TRY(rp_raw.alloc(rows + 1)); SPMV_TRY(bad.alloc(1));
+    SPMV_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+    if (n > 0) {
+        SPMV_CUDA(cudaMemcpyAsync(di.p, hi, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(dj.p, hj, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(da.p, ha, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        make_keys_kernel<<<grid_for(n), 256, 0, s>>>(n, di.p, dj.p, (int32_t)rows, (int32_t)cols, keys.p, idx.p, bad.p);
+        SPMV_CUDA(cudaGetLastError());
+        int hbad = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        if (hbad) return fail(SPMVB200_ERR_INVALID, "entry index outside the matrix");
+        // stable LSD radix sort by (row, column): sort_matrix_row_major (matrix-market.cpp:897-929)
+        size_t tmp_bytes = 0;
+        const int end_bit = 32 + bits_for(rows);
+        SPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys2.p, idx.p, idx2.p, n, 0, end_bit, s));
+        SPMV_TRY(tmp.alloc((int64_t)tmp_bytes));
+        SPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, idx.p, idx2.p, n, 0, end_bit, s));
+    }
+    row_lower_bound_kernel<<<grid_for(rows + 1), 256, 0, s>>>(rows, n, keys2.p, rp_raw.p);
+    SPMV_CUDA(cudaGetLastError());
+
+    const int64_t * rp64 = rp_raw.p;
+    int64_t stored = n;
+    if (row_alignment > 1) {
+        // padded row lengths and their prefix sum (csr-matrix.cpp:206-217)
+        SPMV_TRY(len_al.alloc(rows + 1)); SPMV_TRY(rp_al.alloc(rows + 1));
+        aligned_len_kernel<<<grid_for(rows + 1), 256, 0, s>>>(rows, rp_raw.p, row_alignment, len_al.p);
+        SPMV_CUDA(cudaGetLastError());
+        size_t tb = 0;
+        Scratch<unsigned char> t2;
+        SPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len_al.p, rp_al.p, rows + 1, s));
+        SPMV_TRY(t2.alloc((int64_t)tb));
+        SPMV_CUDA(cub::DeviceScan::ExclusiveSum(t2.p, tb, len_al.p, rp_al.p, rows + 1, s));
+        SPMV_CUDA(cudaMemcpyAsync(&stored, rp_al.p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        rp64 = rp_al.p;
+    }
+    if (stored > INT32_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR: number of stored entries exceeds int32");
+
+    m->format = SPMVB200_CSR;
+    m->rows = rows; m->cols = cols; m->nnz = n; m->stored = stored; m->row_alignment = row_alignment;
+    SPMV_TRY(alloc_streamed(m, &m->col, stored));
+    SPMV_TRY(alloc_streamed(m, &m->val, stored));
+    if (row_alignment > 1) {  // padding = (column 0, 0.0) (csr-matrix.cpp:232-236)
+        SPMV_CUDA(cudaMemsetAsync(m->col, 0, sizeof(int32_t) * (size_t)stored, s));
+        SPMV_CUDA(cudaMemsetAsync(m->val, 0, sizeof(double) * (size_t)stored, s));
+    }
+    if (n > 0) {
+        scatter_sorted_kernel<<<grid_for(n), 256, 0, s>>>(n, keys2.p, idx2.p, da.p, rp_raw.p, rp64, m->col, m->val);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    SPMV_TRY(store_offsets(m, rp64, rows, stored));
+    SPMV_TRY(csr_build_tiles(m));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Adopt device arrays that were allocated with alloc-compatible slack by the caller (generators).
+int csr_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t nnz, int64_t stored, bool off64, void * rp,
+              int32_t * col, double * val)
+{
+    m->format = SPMVB200_CSR;
+    m->rows = rows; m->cols = cols; m->nnz = nnz; m->stored = stored; m->off64 = off64;
+    m->rp = rp; m->col = col; m->val = val;
+    return csr_build_tiles(m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ELL / HYB / COO from a device CSR matrix (row_alignment 1)
+// ---------------------------------------------------------------------------------------------
+
+template <typename OffT>
+__global__ void max_len_kernel(int64_t rows, const OffT * rp, int * out)
+{
+    int best = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int len = (int)(rp[r + 1] - rp[r]);
+        best = len > best ? len : best;
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, best);
+}
+
+template <typename OffT>
+__global__ void len_hist_kernel(int64_t rows, const OffT * rp, unsigned long long * hist)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[rp[r + 1] - rp[r]], 1ull);
+}
+
+// ELL part with the reference's padding rule.  Row r, slot l < W:
+//   l < len(r): the l-th entry of the row;
+//   else: value 0.0, column = INT32_MAX (skip_padding) or the column of the last entry consumed so
+//   far by the reference's sequential fill, which is entry rp[r+1]-1 (ell-matrix.cpp:226-232,
+//   hybrid-matrix.cpp:387-392); 0 when nothing was consumed yet (the hybrid converter's guard; the
+//   ELL converter reads out of bounds there).
+// Rows with len >= W keep their first W entries (hybrid-matrix.cpp:394-400).
+template <typename OffT>
+__global__ void ell_fill_kernel(int64_t rows, int64_t W, int64_t pitch, int skip, const OffT * rp,
+                                const int32_t * col, const double * val, int32_t * ecol, double * eval)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = (int64_t)rp[r], e = (int64_t)rp[r + 1];
+        const int64_t len = e - b;
+        const int32_t padc = skip ? INT_MAX : (e > 0 ? col[e - 1] : 0);
+        for (int64_t l = 0; l < W; ++l) {
+            const bool real = l < len;
+            ecol[l * pitch + r] = real ? col[b + l] : padc;
+            eval[l * pitch + r] = real ? val[b + l] : 0.0;
+        }
+    }
+}
+
+template <typename OffT>
+__global__ void excess_len_kernel(int64_t rows, int64_t W, const OffT * rp, int64_t * excess)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t len = r < rows ? (int64_t)(rp[r + 1] - rp[r]) : 0;
+        excess[r] = len > W ? len - W : 0;
+    }
+}
+
+// COO tail of the hybrid format: entries W.. of every row longer than W, row-major (hybrid-matrix.cpp:402-408).
+template <typename OffT>
+__global__ void hyb_tail_kernel(int64_t rows, int64_t W, const OffT * rp, const int32_t * col, const double * val,
+                                const int64_t * off, int32_t * crow, int32_t * ccol, double * cval)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = (int64_t)rp[r], e = (int64_t)rp[r + 1];
+        int64_t d = off[r];
+        for (int64_t k = b + W; k < e; ++k, ++d) {
+            crow[d] = (int32_t)r;
+            ccol[d] = col[k];
+            cval[d] = val[k];
+        }
+    }
+}
+
+template <typename OffT>
+__global__ void expand_rows_kernel(int64_t rows, const OffT * rp, int32_t * crow)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t k = (int64_t)rp[r]; k < (int64_t)rp[r + 1]; ++k) crow[k] = (int32_t)r;
+}
+
+static void copy_shape(const Matrix * src, Matrix * dst)
+{
+    dst->rows = src->rows; dst->cols = src->cols; dst->nnz = src->nnz; dst->row_offset = src->row_offset;
+}
+
+template <typename OffT>
+static int max_row_length(const Matrix * src, cudaStream_t s, int64_t * out)
+{
+    Scratch<int> d;
+    SPMV_TRY(d.alloc(1));
+    SPMV_CUDA(cudaMemsetAsync(d.p, 0, sizeof(int), s));
+    if (src->rows > 0) {
+        max_len_kernel<OffT><<<grid_for(src->rows), 256, 0, s>>>(src->rows, (const OffT *)src->rp, d.p);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    int h = 0;
+    SPMV_CUDA(cudaMemcpyAsync(&h, d.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    *out = h;
+    return 0;
+}
+
+template <typename OffT>
+static int ell_part(const Matrix * src, int64_t W, int skip, Matrix * dst)
+{
+    cudaStream_t s = dst->stream;
+    dst->ell_w = W;
+    dst->ell_pitch = round_up(std::max<int64_t>(src->rows, 1), 32);
+    dst->skip_padding = skip;
+    const int64_t slots = dst->ell_pitch * W;
+    SPMV_TRY(alloc_streamed(dst, &dst->ell_col, slots));
+    SPMV_TRY(alloc_streamed(dst, &dst->ell_val, slots));
+    if (slots > 0) {
+        SPMV_CUDA(cudaMemsetAsync(dst->ell_col, 0, sizeof(int32_t) * (size_t)slots, s));
+        SPMV_CUDA(cudaMemsetAsync(dst->ell_val, 0, sizeof(double) * (size_t)slots, s));
+        ell_fill_kernel<OffT><<<grid_for(src->rows), 256, 0, s>>>(src->rows, W, dst->ell_pitch, skip,
+                                                                  (const OffT *)src->rp, src->col, src->val,
+                                                                  dst->ell_col, dst->ell_val);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <typename OffT>
+static int ell_from_csr_t(const Matrix * src, int skip, bool check_int32, Matrix * dst)
+{
+    int64_t W = 0;
+    SPMV_TRY(max_row_length<OffT>(src, dst->stream, &W));  // ell-matrix.cpp:199
+    if (check_int32 && src->rows * W > INT32_MAX)          // ell-matrix.cpp:200-205
+        return fail(SPMVB200_ERR_OVERFLOW,
+                    "Failed to convert to ELLPACK: Integer overflow when computing number of non-zeros");
+    copy_shape(src, dst);
+    dst->format = SPMVB200_ELL;
+    dst->stored = src->rows * W;
+    SPMV_TRY(ell_part<OffT>(src, W, skip, dst));
+    SPMV_CUDA(cudaStreamSynchronize(dst->stream));
+    return 0;
+}
+
+int ell_from_csr(const Matrix * src, int skip, bool check_int32, Matrix * dst)
+{
+    return src->off64 ? ell_from_csr_t<int64_t>(src, skip, check_int32, dst)
+                      : ell_from_csr_t<uint32_t>(src, skip, check_int32, dst);
+}
+
+template <typename OffT>
+static int hyb_from_csr_t(const Matrix * src, int skip, bool check_int32, Matrix * dst)
+{
+    cudaStream_t s = dst->stream;
+    int64_t maxlen = 0;
+    SPMV_TRY(max_row_length<OffT>(src, s, &maxlen));
+    // histogram of row lengths on the device, 2/3-quantile rule on the host (hybrid-matrix.cpp:329-344)
+    Scratch<unsigned long long> dh;
+    SPMV_TRY(dh.alloc(maxlen + 1));
+    SPMV_CUDA(cudaMemsetAsync(dh.p, 0, sizeof(unsigned long long) * (size_t)(maxlen + 1), s));
+    if (src->rows > 0) {
+        len_hist_kernel<OffT><<<grid_for(src->rows), 256, 0, s>>>(src->rows, (const OffT *)src->rp, dh.p);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    std::vector<unsigned long long> hist((size_t)maxlen + 1);
+    SPMV_CUDA(cudaMemcpyAsync(hist.data(), dh.p, sizeof(unsigned long long) * hist.size(), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    int64_t W = 0, below = 0;
+    const int64_t target = (2 * src->rows) / 3;
+    while (below < target) {
+        below += (int64_t)hist[(size_t)W];
+        W++;
+    }
+    W = W == 0 ? 0 : W - 1;
+    if (check_int32 && src->rows * W > INT32_MAX)  // hybrid-matrix.cpp:349-354
+        return fail(SPMVB200_ERR_OVERFLOW,
+                    "Failed to convert to HYBRID: Integer overflow when computing number of non-zeros");
+    copy_shape(src, dst);
+    dst->format = SPMVB200_HYB;
+    dst->n_ell = src->rows * W;
+    SPMV_TRY(ell_part<OffT>(src, W, skip, dst));
+
+    Scratch<int64_t> excess, off;
+    Scratch<unsigned char> tmp;
+    SPMV_TRY(excess.alloc(src->rows + 1)); SPMV_TRY(off.alloc(src->rows + 1));
+    excess_len_kernel<OffT><<<grid_for(src->rows + 1), 256, 0, s>>>(src->rows, W, (const OffT *)src->rp, excess.p);
+    SPMV_CUDA(cudaGetLastError());
+    size_t tb = 0;
+    SPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, excess.p, off.p, src->rows + 1, s));
+    SPMV_TRY(tmp.alloc((int64_t)tb));
+    SPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, excess.p, off.p, src->rows + 1, s));
+    int64_t ncoo = 0;
+    SPMV_CUDA(cudaMemcpyAsync(&ncoo, off.p + src->rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    dst->n_coo = ncoo;
+    dst->coo_n = ncoo;
+    dst->coo_sorted = true;
+    dst->coo_mode = SPMVB200_COO_SEGMENTED;
+    dst->stored = dst->n_ell + ncoo;
+    SPMV_TRY(alloc_streamed(dst, &dst->coo_row, ncoo));
+    SPMV_TRY(alloc_streamed(dst, &dst->coo_col, ncoo));
+    SPMV_TRY(alloc_streamed(dst, &dst->coo_val, ncoo));
+    if (ncoo > 0) {
+        hyb_tail_kernel<OffT><<<grid_for(src->rows), 256, 0, s>>>(src->rows, W, (const OffT *)src->rp, src->col,
+                                                                  src->val, off.p, dst->coo_row, dst->coo_col,
+                                                                  dst->coo_val);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int hyb_from_csr(const Matrix * src, int skip, bool check_int32, Matrix * dst)
+{
+    return src->off64 ? hyb_from_csr_t<int64_t>(src, skip, check_int32, dst)
+                      : hyb_from_csr_t<uint32_t>(src, skip, check_int32, dst);
+}
+
+int coo_from_csr(const Matrix * src, int mode, Matrix * dst)
+{
+    cudaStream_t s = dst->stream;
+    copy_shape(src, dst);
+    const int64_t n = src->stored;
+    int32_t *row = nullptr, *col = nullptr;
+    double * val = nullptr;
+    SPMV_TRY(alloc_streamed(dst, &row, n));
+    SPMV_TRY(alloc_streamed(dst, &col, n));
+    SPMV_TRY(alloc_streamed(dst, &val, n));
+    if (n > 0) {
+        if (src->off64) expand_rows_kernel<int64_t><<<grid_for(src->rows), 256, 0, s>>>(src->rows, (const int64_t *)src->rp, row);
+        else expand_rows_kernel<uint32_t><<<grid_for(src->rows), 256, 0, s>>>(src->rows, (const uint32_t *)src->rp, row);
+        SPMV_CUDA(cudaGetLastError());
+        SPMV_CUDA(cudaMemcpyAsync(col, src->col, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+        SPMV_CUDA(cudaMemcpyAsync(val, src->val, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    }
+    return coo_adopt(dst, src->rows, src->cols, n, row, col, val, mode, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// COO
+// ---------------------------------------------------------------------------------------------
+
+__global__ void is_sorted_kernel(int64_t n, const int32_t * row, int * unsorted)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        if (row[k] < row[k - 1]) *unsorted = 1;
+}
+
+__global__ void iota_kernel(int64_t n, uint32_t * idx)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        idx[k] = (uint32_t)k;
+}
+
+__global__ void gather_kernel(int64_t n, const uint32_t * idx, const int32_t * col, const double * val,
+                              int32_t * col2, double * val2)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        col2[k] = col[idx[k]];
+        val2[k] = val[idx[k]];
+    }
+}
+
+int coo_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t n, int32_t * row, int32_t * col, double * val,
+              int mode, bool already_sorted)
+{
+    cudaStream_t s = m->stream;
+    m->format = SPMVB200_COO;
+    m->coo_mode = mode;
+    m->rows = rows; m->cols = cols; m->stored = n; m->coo_n = n;
+    if (m->nnz == 0) m->nnz = n;
+    m->coo_row = row; m->coo_col = col; m->coo_val = val;
+    m->coo_sorted = already_sorted;
+    if (mode == SPMVB200_COO_SEGMENTED && !already_sorted && n > 1) {
+        if (n >= ((int64_t)1 << 32)) return fail(SPMVB200_ERR_UNSUPPORTED, "COO sort supports < 2^32 entries");
+        Scratch<int> flag;
+        SPMV_TRY(flag.alloc(1));
+        SPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+        is_sorted_kernel<<<grid_for(n), 256, 0, s>>>(n, row, flag.p);
+        SPMV_CUDA(cudaGetLastError());
+        int unsorted = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&unsorted, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        if (unsorted) {
+            // stable sort by row only: the column order inside a row stays the file order
+            Scratch<uint32_t> idx, idx2;
+            Scratch<unsigned char> tmp;
+            int32_t *row2 = nullptr, *col2 = nullptr;
+            double * val2 = nullptr;
+            SPMV_TRY(idx.alloc(n)); SPMV_TRY(idx2.alloc(n));
+            SPMV_TRY(alloc_streamed(m, &row2, n));
+            SPMV_TRY(alloc_streamed(m, &col2, n));
+            SPMV_TRY(alloc_streamed(m, &val2, n));
+            iota_kernel<<<grid_for(n), 256, 0, s>>>(n, idx.p);
+            size_t tb = 0;
+            const int end_bit = bits_for(rows);
+            SPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, row, row2, idx.p, idx2.p, n, 0, end_bit, s));
+            SPMV_TRY(tmp.alloc((int64_t)tb));
+            SPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, row, row2, idx.p, idx2.p, n, 0, end_bit, s));
+            gather_kernel<<<grid_for(n), 256, 0, s>>>(n, idx2.p, col, val, col2, val2);
+            SPMV_CUDA(cudaGetLastError());
+            SPMV_CUDA(cudaStreamSynchronize(s));
+            const int64_t cap = round_up(n, 4096) + kPadEntries;
+            cudaFree(row); cudaFree(col); cudaFree(val);
+            m->device_bytes -= cap * 16;
+            m->coo_row = row2; m->coo_col = col2; m->coo_val = val2;
+        }
+        m->coo_sorted = true;
+    }
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // namespace spmvb200

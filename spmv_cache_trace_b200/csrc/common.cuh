@@ -1,0 +1,184 @@
+// common.cuh -- internal declarations shared by the translation units of libspmvb200.so.
+//
+// Device layouts (all allocations 256 B aligned by cudaMalloc):
+//   CSR  row_ptr  uint32[rows+1] (int64 when stored >= 2^32), column_index int32[], value f64[];
+//        column_index/value are padded with (0, 0.0) up to a whole number of nnz tiles so a
+//        bulk-async (TMA) copy of any tile stays inside the allocation;
+//        tile_row int32[ntiles+1]: row that owns the first non-zero of each tile.
+//   ELL  COLUMN-MAJOR: slot l of row i lives at l*pitch + i (pitch = rows rounded up to 32), so
+//        the 32 lanes of a warp read 32 consecutive rows of one slot with 128-bit loads.
+//        (The reference layout is row-major, k = i*row_length + l, ell-matrix.cpp:254.)
+//   COO  row_index int32[], column_index int32[], value f64[], padded to whole tiles;
+//        SEGMENTED mode keeps them stably sorted by row.
+//   HYB  the ELL arrays plus the COO arrays of the tail (row-major sorted, as the reference builds them).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/spmv_b200.h"
+
+namespace spmvb200 {
+
+// ---- error plumbing ----------------------------------------------------------------------
+void set_error(const std::string & msg);
+int fail(int code, const std::string & msg);
+int cuda_fail(cudaError_t e, const char * what, const char * file, int line);
+void count_launch(int n = 1);
+
+#define SPMV_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) return ::spmvb200::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SPMV_TRY(call)                 \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+
+// ---- tiling constants ----------------------------------------------------------------------
+constexpr int kCsrThreads = 256;
+constexpr int kCooItems = 7;  // odd: blocked per-thread walks over shared memory stay bank-conflict free
+constexpr int kCooThreads = 256;
+constexpr int kCooTile = kCooThreads * kCooItems;  // 1792 entries = 28 KiB per stage
+constexpr int64_t kPadEntries = 8192;              // slack after every streamed array (>= largest tile)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace spmvb200
+
+// The opaque handle of the C ABI.
+struct spmvb200_matrix_s {
+    int32_t format = 0, coo_mode = 0;
+    int64_t rows = 0, cols = 0, nnz = 0, stored = 0, row_alignment = 1;
+    int64_t ell_w = 0, n_ell = 0, n_coo = 0;
+    int32_t skip_padding = 0;
+    bool off64 = false;
+    int64_t row_offset = 0;
+    int device = 0;
+
+    // CSR
+    void * rp = nullptr;  // uint32_t* or int64_t*
+    int32_t * col = nullptr;
+    double * val = nullptr;
+    int32_t * tile_row = nullptr;
+    int64_t ntiles = 0;
+    int csr_tile = 0;  // entries per tile the tile_row table was built for
+
+    // ELL (column-major)
+    int32_t * ell_col = nullptr;
+    double * ell_val = nullptr;
+    int64_t ell_pitch = 0;
+
+    // COO (whole matrix, or the hybrid tail)
+    int32_t * coo_row = nullptr;
+    int32_t * coo_col = nullptr;
+    double * coo_val = nullptr;
+    int64_t coo_n = 0;
+    bool coo_sorted = false;
+
+    // vectors
+    double * x = nullptr;
+    double * y = nullptr;
+    bool own_x = false, own_y = false;
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t device_bytes = 0;
+    int sm_count = 148;
+
+    // options (spmvb200_set_option)
+    int64_t opt_csr_tile = 0;     // 0 = auto
+    int64_t opt_csr_stages = 0;   // 0 = auto
+    int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
+    int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
+    int64_t opt_ell_block = 0;    // threads per block, 0 = auto
+    int64_t opt_coo_stages = 0;
+    int64_t opt_coo_ctas = 0;
+    int64_t opt_beta0 = 0;        // 1: y = A*x (y is cleared first) instead of y += A*x
+    const char * kernel_name = "";
+};
+
+namespace spmvb200 {
+
+using Matrix = spmvb200_matrix_s;
+
+// ---- allocation helpers (track device_bytes) ------------------------------------------------
+template <typename T>
+inline int dev_alloc(Matrix * m, T ** p, int64_t count)
+{
+    *p = nullptr;
+    size_t bytes = sizeof(T) * (size_t)(count > 0 ? count : 1);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    if (m) m->device_bytes += (int64_t)bytes;
+    return 0;
+}
+
+// Streamed arrays get kPadEntries zeroed elements of slack so whole-tile bulk copies and vector
+// loads never leave the allocation.
+template <typename T>
+inline int alloc_streamed(Matrix * m, T ** p, int64_t count)
+{
+    const int64_t cap = round_up(count, 4096) + kPadEntries;
+    int rc = dev_alloc(m, p, cap);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(*p + count, 0, sizeof(T) * (size_t)(cap - count), m->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__);
+    return 0;
+}
+
+// Scratch allocations that are not part of the resident matrix.
+template <typename T>
+struct Scratch {
+    T * p = nullptr;
+    Scratch() = default;
+    Scratch(const Scratch &) = delete;
+    Scratch & operator=(const Scratch &) = delete;
+    ~Scratch() { if (p) cudaFree(p); }
+    int alloc(int64_t n)
+    {
+        cudaError_t e = cudaMalloc((void **)&p, sizeof(T) * (size_t)(n > 0 ? n : 1));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
+        return 0;
+    }
+    T * release() { T * q = p; p = nullptr; return q; }
+};
+
+inline unsigned grid_for(int64_t n, int sm = 148)
+{
+    int64_t g = (n + 255) / 256;
+    if (g > (int64_t)sm * 16) g = (int64_t)sm * 16;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+int fill_device(double * p, int64_t n, double v, cudaStream_t s);
+
+// ---- launchers implemented in kernels.cu ---------------------------------------------------
+int launch_csr(Matrix * m);
+int launch_ell(Matrix * m, bool accumulate_into_y);
+int launch_coo(Matrix * m);
+int csr_build_tiles(Matrix * m);  // (re)build tile_row for the configured tile size
+
+// ---- builders.cu -----------------------------------------------------------------------------
+int matrix_new(Matrix ** out);
+int matrix_alloc_vectors(Matrix * m);
+void matrix_free(Matrix * m);
+// Take ownership of device CSR arrays (unpadded, `stored` entries) and finish the layout.
+int csr_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t nnz, int64_t stored, bool off64,
+              void * rp, int32_t * col, double * val);
+int coo_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t n, int32_t * row, int32_t * col,
+              double * val, int mode, bool already_sorted);
+int ell_from_csr(const Matrix * src, int skip_padding, bool check_int32, Matrix * dst);
+int hyb_from_csr(const Matrix * src, int skip_padding, bool check_int32, Matrix * dst);
+int coo_from_csr(const Matrix * src, int mode, Matrix * dst);
+int csr_from_entries_host(int64_t rows, int64_t cols, int64_t n, const int32_t * i, const int32_t * j,
+                          const double * a, int32_t row_alignment, Matrix * dst);
+
+}  // namespace spmvb200

@@ -1,0 +1,538 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Mirrors the reference's test/test_{csr,coo,ell,hybrid}-matrix.cpp case by case, then widens:
+  * conversions are BIT-EXACT (exported device arrays == reference arrays);
+  * y: the reference's own tolerance on the poisson2D fixture (||y - z||_2 < DBL_EPSILON) and
+    BASELINE.json's bound everywhere, |y_gpu - y_ref| <= 1e-12 * sum_j |a_ij x_j| per row;
+    CSR rows that fit a tile and all ELL rows are summed in the reference's order with separate
+    multiply/add roundings, so there the result is required to be bit-identical;
+  * full BASELINE sizes (config 1: 1000x1000 5-point; config 2: 128^3 7-point) against the oracle;
+  * edge cases: empty matrices, empty rows, rows cut by tile boundaries, rows longer than a tile,
+    unsorted/column-major input, 1xN and Nx1, skip_padding, row-aligned CSR, accumulate semantics.
+"""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import spmv_cache_trace_b200 as sp
+from conftest import l2norm
+from oracle.generators_ref import rmat_entries, stencil_entries
+from spmv_cache_trace_b200 import (COO_ATOMIC, COO_SEGMENTED, coo_matrix, csr_matrix, ell_matrix,
+                                   hybrid_matrix, matrix_market)
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # BASELINE.json: |y_gpu - y_ref| <= 1e-12 * sum_j |a_ij x_j|
+
+
+def bound_of(oracle, rows, cols, i, j, a, x):
+    return oracle.csr_abs_rowsum(oracle.csr(rows, cols, i, j, a), x)
+
+
+def assert_within(y, yref, bound, what=""):
+    err = np.abs(np.asarray(y) - np.asarray(yref))
+    lim = TOL * bound + 0.0
+    bad = np.nonzero(err > lim)[0]
+    assert bad.size == 0, f"{what}: {bad.size} rows out of tolerance, first {bad[:5]}, err {err[bad[:5]]}, lim {lim[bad[:5]]}"
+
+
+def build(fmt, mm, **kw):
+    if fmt == "csr":
+        return csr_matrix.from_matrix_market_row_aligned(mm, kw.get("align", 1))
+    if fmt == "coo":
+        return coo_matrix.from_matrix_market(mm, kw.get("mode", COO_SEGMENTED))
+    if fmt == "ell":
+        return ell_matrix.from_matrix_market(mm, kw.get("skip", False))
+    return hybrid_matrix.from_matrix_market(mm, kw.get("skip", False))
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's own tests
+# --------------------------------------------------------------------------------------------
+
+def test_csr_from_matrix_market(kats):
+    k = kats["csr"]
+    A = csr_matrix.from_matrix_market(matrix_market.fromStream(io.StringIO(k["mtx"])))
+    assert (A.rows, A.columns, A.num_entries) == (4, 5, 7)
+    e = A.export()
+    assert e["row_ptr"].tolist() == k["row_ptr"]
+    assert e["column_index"].tolist() == k["column_index"]
+    assert e["value"].tolist() == k["value"]
+
+
+def test_csr_from_matrix_market_row_aligned(kats):
+    k = kats["csr"]
+    A = csr_matrix.from_matrix_market_row_aligned(matrix_market.fromStream(k["mtx"]), 2)
+    e = A.export()
+    ra = k["row_aligned_2"]
+    assert e["row_ptr"].tolist() == ra["row_ptr"]
+    assert e["column_index"].tolist() == ra["column_index"]
+    assert e["value"].tolist() == ra["value"]
+
+
+def test_csr_matrix_vector_multiplication(kats):
+    k = kats["csr"]
+    A = csr_matrix.Matrix(4, 5, 7, 1, k["row_ptr"], k["column_index"], k["value"])
+    y = A * np.array(kats["x"])
+    assert l2norm(y - np.array(k["y"])) == 0.0
+
+
+def test_coo_from_matrix_market_and_multiply(kats):
+    k = kats["coo"]
+    for mode in (COO_SEGMENTED, COO_ATOMIC):
+        A = coo_matrix.from_matrix_market(matrix_market.fromStream(k["mtx"]), mode)
+        e = A.export()
+        assert e["row_index"].tolist() == k["row_index"]
+        assert e["column_index"].tolist() == k["column_index"]
+        assert e["value"].tolist() == k["value"]
+        assert l2norm(A * np.array(kats["x"]) - np.array(k["y"])) == 0.0
+
+
+def test_coo_column_major(kats):
+    k = kats["coo_column_major"]
+    for mode in (COO_SEGMENTED, COO_ATOMIC):
+        A = coo_matrix.from_matrix_market(matrix_market.fromStream(k["mtx"]), mode)
+        assert l2norm(A * np.array(kats["x"]) - np.array(k["y"])) == 0.0
+
+
+def test_ell_from_matrix_market_and_multiply(kats):
+    k = kats["ell"]
+    A = ell_matrix.from_matrix_market(matrix_market.fromStream(k["mtx"]))
+    assert (A.rows, A.columns, A.num_entries, A.row_length) == (4, 5, 8, 3)
+    e = A.export()
+    assert e["column_index"].tolist() == k["column_index"]  # incl. the padding-column rule
+    assert e["value"].tolist() == k["value"]
+    assert l2norm(A * np.array(kats["x"]) - np.array(k["y"])) == 0.0
+    B = ell_matrix.Matrix(4, 5, 8, 3, k["column_index"], k["value"])
+    assert l2norm(B * np.array(kats["x"]) - np.array(k["y"])) == 0.0
+
+
+def test_hybrid_from_matrix_market_and_multiply(kats):
+    k = kats["hybrid"]
+    A = hybrid_matrix.from_matrix_market(matrix_market.fromStream(k["mtx"]), False, sys.stderr, False)
+    assert (A.ell_row_length, A.num_ell_entries, A.num_coo_entries) == (2, 8, 2)
+    e = A.export()
+    assert e["ell_column_index"].tolist() == k["ell_column_index"]
+    assert e["ell_value"].tolist() == k["ell_value"]
+    assert e["coo_row_index"].tolist() == k["coo_row_index"]
+    assert e["coo_column_index"].tolist() == k["coo_column_index"]
+    assert e["coo_value"].tolist() == k["coo_value"]
+    assert l2norm(A * np.array(kats["x"]) - np.array(k["y"])) == 0.0
+    B = hybrid_matrix.Matrix(4, 5, 9, 2, 8, k["ell_column_index"], k["ell_value"], False, 2,
+                             k["coo_row_index"], k["coo_column_index"], k["coo_value"])
+    assert l2norm(B * np.array(kats["x"]) - np.array(k["y"])) == 0.0
+
+
+@pytest.mark.parametrize("fmt,kw", [("csr", {}), ("csr", {"align": 2}), ("csr", {"align": 4}),
+                                    ("coo", {}), ("coo", {"mode": COO_ATOMIC}), ("ell", {}),
+                                    ("ell", {"skip": True}), ("hybrid", {}), ("hybrid", {"skip": True})])
+def test_poisson2D(oracle, kats, poisson2d, fmt, kw):
+    text, b, z = poisson2d
+    mm = matrix_market.fromStream(text)
+    if fmt == "coo":  # the reference test sorts first (test_coo-matrix.cpp:112-113)
+        mm = matrix_market.sort_matrix_row_major(mm)
+    A = build(fmt, mm, **kw)
+    y = A * b
+    assert l2norm(y - z) < kats["poisson2D"]["l2_tolerance"]
+    o = oracle.mm_parse(text)
+    yref = oracle.csr_spmv(oracle.csr(o.rows, o.columns, o.i, o.j, o.a), b)
+    assert_within(y, yref, bound_of(oracle, o.rows, o.columns, o.i, o.j, o.a, b), fmt)
+    if fmt in ("csr", "ell"):
+        assert np.array_equal(y, yref)  # same summation order, same roundings
+    if fmt == "ell":
+        assert A.row_length == kats["poisson2D"]["probed"]["ell_row_length"]
+    if fmt == "hybrid":
+        assert A.ell_row_length == kats["poisson2D"]["probed"]["hybrid_ell_row_length"]
+        assert A.num_coo_entries == kats["poisson2D"]["probed"]["hybrid_num_coo_entries"]
+
+
+# --------------------------------------------------------------------------------------------
+# arrays and products produced by the reference library itself (tests/golden/ref_vectors.npz)
+# --------------------------------------------------------------------------------------------
+
+def test_ref_vectors(oracle, ref_vectors):
+    rv = ref_vectors
+    for name in [str(n) for n in rv["names"]]:
+        p = name + "/"
+        rows, cols, n = (int(v) for v in rv[p + "shape"])
+        i, j, a, x, y0 = rv[p + "i"], rv[p + "j"], rv[p + "a"], rv[p + "x"], rv[p + "y0"]
+        mm = matrix_market.from_entries(rows, cols, i, j, a)
+        bound = bound_of(oracle, rows, cols, i, j, a, x) + np.abs(y0)
+        maxlen = int(rv[p + "max_row_length"][0])
+        assert mm.max_row_length() == maxlen
+        for align in (1, 2, 4):
+            q = f"{p}csr{align}/"
+            A = csr_matrix.from_matrix_market_row_aligned(mm, align)
+            e = A.export()
+            assert np.array_equal(e["row_ptr"], rv[q + "row_ptr"]), name
+            assert np.array_equal(e["column_index"], rv[q + "col"]), name
+            assert np.array_equal(e["value"], rv[q + "val"]), name
+            assert A.size() == int(rv[q + "size"][0])
+            y = csr_matrix.spmv(A, x, y0.copy())
+            assert_within(y, rv[q + "y_t1"], bound, name)
+            if maxlen <= 96 and len(e["value"]) <= 1024:
+                assert np.array_equal(y, rv[q + "y_t1"]), name
+        for mode in (COO_ATOMIC, COO_SEGMENTED):
+            q = p + "coo/"
+            A = coo_matrix.from_matrix_market(mm, mode)
+            e = A.export()
+            if mode == COO_ATOMIC:  # file order kept
+                assert np.array_equal(e["row_index"], rv[q + "row"]) and np.array_equal(e["column_index"], rv[q + "col"])
+                assert np.array_equal(e["value"], rv[q + "val"]) and A.size() == int(rv[q + "size"][0])
+            else:  # stable sort by row of the same arrays
+                order = np.argsort(rv[q + "row"], kind="stable")
+                assert np.array_equal(e["row_index"], rv[q + "row"][order])
+                assert np.array_equal(e["column_index"], rv[q + "col"][order])
+                assert np.array_equal(e["value"], rv[q + "val"][order])
+            y = coo_matrix.spmv(1, A, x, y0.copy())
+            for T in (1, 2, 3):
+                assert_within(y, rv[f"{q}y_t{T}"], bound, name)
+        for skip in (0, 1):
+            q = f"{p}ell{skip}/"
+            A = ell_matrix.from_matrix_market(mm, bool(skip))
+            e = A.export()
+            assert A.row_length == int(rv[q + "row_length"][0])
+            assert np.array_equal(e["column_index"], rv[q + "col"]), name
+            assert np.array_equal(e["value"], rv[q + "val"]), name
+            assert A.size() == int(rv[q + "size"][0])
+            y = ell_matrix.spmv(A, x, y0.copy())
+            assert np.array_equal(y, rv[q + "y_t1"]), name  # bit-exact
+            q = f"{p}hyb{skip}/"
+            A = hybrid_matrix.from_matrix_market(mm, bool(skip))
+            e = A.export()
+            assert [A.ell_row_length, A.num_ell_entries, A.num_coo_entries] == rv[q + "dims"].tolist(), name
+            assert np.array_equal(e["ell_column_index"], rv[q + "ell_col"]), name
+            assert np.array_equal(e["ell_value"], rv[q + "ell_val"])
+            assert np.array_equal(e["coo_row_index"], rv[q + "coo_row"])
+            assert np.array_equal(e["coo_column_index"], rv[q + "coo_col"])
+            assert np.array_equal(e["coo_value"], rv[q + "coo_val"])
+            y = hybrid_matrix.spmv(1, A, x, y0.copy())
+            for T in (1, 2, 3):
+                assert_within(y, rv[f"{q}y_t{T}"], bound, name)
+
+
+# --------------------------------------------------------------------------------------------
+# semantics and edge cases
+# --------------------------------------------------------------------------------------------
+
+def test_run_accumulates_like_the_reference(oracle, kats):
+    """Kernel::run is y += A x; profile mode calls it repeatedly on the same y."""
+    k = kats["ell"]
+    x = np.array(kats["x"])
+    for fmt in ("csr", "coo", "ell", "hybrid"):
+        A = build(fmt, matrix_market.fromStream(k["mtx"]))
+        A.set_x(x)
+        A.fill_y(0.0)
+        for _ in range(3):
+            A.spmv()
+        assert np.array_equal(A.get_y(), 3 * np.array(k["y"])), fmt
+
+
+def test_init_vectors_are_one_and_zero(kats):
+    A = csr_matrix.from_matrix_market(matrix_market.fromStream(kats["csr"]["mtx"]))
+    assert np.array_equal(A.get_x(), np.ones(5)) and np.array_equal(A.get_y(), np.zeros(4))
+
+
+def test_spmv_host_end_to_end(oracle, poisson2d):
+    text, b, z = poisson2d
+    A = csr_matrix.from_matrix_market(matrix_market.fromStream(text))
+    y = np.full(A.rows, 0.25)
+    A.spmv_host(b, y)
+    o = oracle.mm_parse(text)
+    yref = oracle.csr_spmv(oracle.csr(o.rows, o.columns, o.i, o.j, o.a), b, np.full(A.rows, 0.25))
+    assert np.array_equal(y, yref)
+
+
+def test_size_mismatch_raises(kats):
+    A = csr_matrix.from_matrix_market(matrix_market.fromStream(kats["csr"]["mtx"]))
+    with pytest.raises(sp.matrix_error, match="Size mismatch"):
+        A * np.ones(4)
+
+
+def test_empty_and_degenerate_matrices(oracle):
+    # no entries at all
+    mm = matrix_market.fromStream("%%MatrixMarket matrix coordinate real general\n5 7 0\n")
+    for fmt in ("csr", "coo", "ell", "hybrid"):
+        A = build(fmt, mm)
+        assert np.array_equal(A * np.ones(7), np.zeros(5)), fmt
+    # 1 x N and N x 1
+    rng = np.random.default_rng(3)
+    for rows, cols in ((1, 300), (300, 1), (1, 1)):
+        dense = rng.uniform(-1, 1, (rows, cols))
+        ii, jj = np.nonzero(np.ones_like(dense))
+        a = dense[ii, jj]
+        x = rng.uniform(-1, 1, cols)
+        mm = matrix_market.from_entries(rows, cols, ii + 1, jj + 1, a)
+        yref = oracle.csr_spmv(oracle.csr(rows, cols, ii + 1, jj + 1, a), x)
+        bound = bound_of(oracle, rows, cols, ii + 1, jj + 1, a, x)
+        for fmt in ("csr", "coo", "ell", "hybrid"):
+            assert_within(build(fmt, mm) * x, yref, bound, f"{fmt} {rows}x{cols}")
+
+
+def test_array_format_is_rejected():
+    mm = matrix_market.fromStream("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
+    for fmt in ("csr", "coo", "ell", "hybrid"):
+        with pytest.raises(sp.matrix_error, match="Expected matrix in coordinate format"):
+            build(fmt, mm)
+
+
+def ragged_matrix(rng, rows, cols, long_rows, long_len, short_max, empty_every=0):
+    """Rows of wildly different length: some empty, most short, a few longer than a CSR tile."""
+    lens = rng.integers(0, short_max + 1, rows)
+    if empty_every:
+        lens[::empty_every] = 0
+    for r in long_rows:
+        lens[r] = long_len
+    lens = np.minimum(lens, cols)
+    ii = np.repeat(np.arange(rows), lens)
+    jj = np.concatenate([np.sort(rng.choice(cols, l, replace=False)) for l in lens]) if lens.sum() else np.zeros(0, int)
+    a = rng.uniform(-1, 1, len(ii))
+    return (ii + 1).astype(np.int32), (jj + 1).astype(np.int32), a
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
+    rng = np.random.default_rng(seed)
+    rows, cols = 6000, 20000
+    i, j, a = ragged_matrix(rng, rows, cols, long_rows=(0, 17, 2999, 3000, 5999), long_len=9000, short_max=9,
+                            empty_every=7)
+    if 1 not in i:  # reference ELL needs a non-empty first row
+        i = np.concatenate([[1], i]).astype(np.int32); j = np.concatenate([[1], j]).astype(np.int32); a = np.concatenate([[0.5], a])
+    p = rng.permutation(len(i))
+    i, j, a = i[p], j[p], a[p]  # unsorted input
+    x = rng.uniform(-1, 1, cols)
+    y0 = rng.uniform(-1, 1, rows)
+    O = oracle.csr(rows, cols, i, j, a)
+    yref = oracle.csr_spmv(O, x, y0)
+    bound = oracle.csr_abs_rowsum(O, x) + np.abs(y0)
+    mm = matrix_market.from_entries(rows, cols, i, j, a)
+    A = csr_matrix.from_matrix_market(mm)
+    e = A.export()
+    assert np.array_equal(e["row_ptr"], O.row_ptr) and np.array_equal(e["column_index"], O.column_index)
+    assert np.array_equal(e["value"], O.value)
+    for tile, stages in ((1024, 1), (1024, 4), (2048, 1), (2048, 2), (2048, 3), (4096, 1), (4096, 2)):
+        A.set_option("csr.tile", tile)
+        A.set_option("csr.stages", stages)
+        y = csr_matrix.spmv(A, x, y0.copy())
+        assert_within(y, yref, bound, f"csr tile={tile} stages={stages}")
+    for fmt, kw in (("coo", {}), ("coo", {"mode": COO_ATOMIC}), ("hybrid", {})):
+        B = build(fmt, mm, **kw)
+        y = B * x + y0
+        assert_within(y, yref, bound + np.abs(yref), fmt)
+    H = hybrid_matrix.from_matrix_market(mm)
+    OH = oracle.hyb(rows, cols, i, j, a)
+    eh = H.export()
+    assert (H.ell_row_length, H.num_coo_entries) == (OH.ell_row_length, OH.num_coo_entries)
+    assert np.array_equal(eh["ell_column_index"], OH.ell_column_index) and np.array_equal(eh["coo_value"], OH.coo_value)
+
+
+def test_forced_64bit_offsets(oracle):
+    rng = np.random.default_rng(5)
+    i, j, a = ragged_matrix(rng, 3000, 5000, long_rows=(10,), long_len=4000, short_max=12)
+    x = rng.uniform(-1, 1, 5000)
+    O = oracle.csr(3000, 5000, i, j, a)
+    yref = oracle.csr_spmv(O, x)
+    sp.set_global_option("force_offsets64", 1)
+    try:
+        A = csr_matrix.from_matrix_market(matrix_market.from_entries(3000, 5000, i, j, a))
+        assert A.info.offsets_64bit == 1
+        assert np.array_equal(A.export()["row_ptr"], O.row_ptr)
+        assert_within(A * x, yref, oracle.csr_abs_rowsum(O, x), "csr int64 offsets")
+        E = A.convert(sp.ELL)
+        assert_within(E * x, yref, oracle.csr_abs_rowsum(O, x), "ell from int64 csr")
+    finally:
+        sp.set_global_option("force_offsets64", 0)
+
+
+def test_create_from_reference_arrays(oracle):
+    """spmvb200_*_create: what a reference-side Kernel adapter hands over in prepare()."""
+    rng = np.random.default_rng(21)
+    i, j, a = ragged_matrix(rng, 500, 400, long_rows=(3,), long_len=350, short_max=6)
+    if 1 not in i:
+        i = np.concatenate([[1], i]).astype(np.int32); j = np.concatenate([[1], j]).astype(np.int32); a = np.concatenate([[0.5], a])
+    p = rng.permutation(len(i))
+    i, j, a = i[p], j[p], a[p]
+    x = rng.uniform(-1, 1, 400)
+    O = oracle.csr(500, 400, i, j, a, 2)
+    yref = oracle.csr_spmv(O, x)
+    bound = oracle.csr_abs_rowsum(O, x)
+    A = csr_matrix.Matrix(500, 400, len(i), 2, O.row_ptr, O.column_index, O.value)
+    assert_within(A * x, yref, bound, "csr_create")
+    C_ = oracle.coo(500, 400, i, j, a)
+    for mode in (COO_SEGMENTED, COO_ATOMIC):
+        B = coo_matrix.Matrix(500, 400, len(i), C_.row_index, C_.column_index, C_.value, mode)
+        assert_within(B * x, yref, bound, "coo_create")
+    E = oracle.ell(500, 400, i, j, a)
+    B = ell_matrix.Matrix(500, 400, len(i), E.row_length, E.column_index, E.value)
+    assert np.array_equal(B * x, oracle.ell_spmv(E, x))
+    H = oracle.hyb(500, 400, i, j, a)
+    B = hybrid_matrix.Matrix(500, 400, len(i), H.ell_row_length, H.num_ell_entries, H.ell_column_index, H.ell_value,
+                             False, H.num_coo_entries, H.coo_row_index, H.coo_column_index, H.coo_value)
+    assert_within(B * x, yref, bound, "hyb_create")
+
+
+# --------------------------------------------------------------------------------------------
+# generators and BASELINE-size configurations
+# --------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind,dims", [(0, (37, 23, 1)), (1, (9, 14, 11)), (2, (8, 7, 9)), (2, (1, 5, 3))])
+def test_stencil_generator_matches_numpy_restatement(oracle, kind, dims):
+    nx, ny, nz = dims
+    i, j, a = stencil_entries(kind, nx, ny, nz)
+    n = nx * ny * nz
+    O = oracle.csr(n, n, i, j, a)
+    A = sp.generators.stencil(kind, nx, ny, nz)
+    e = A.export()
+    assert np.array_equal(e["row_ptr"], O.row_ptr) and np.array_equal(e["column_index"], O.column_index)
+    assert np.array_equal(e["value"], O.value)
+    # a row block (the multi-GPU partition) holds exactly those rows
+    b0, b1 = n // 3, (2 * n) // 3
+    B = sp.generators.stencil(kind, nx, ny, nz, row_begin=b0, row_end=b1)
+    eb = B.export()
+    assert np.array_equal(eb["row_ptr"], O.row_ptr[b0:b1 + 1] - O.row_ptr[b0])
+    assert np.array_equal(eb["column_index"], O.column_index[O.row_ptr[b0]:O.row_ptr[b1]])
+    assert B.info.row_offset == b0
+    # device-side conversions follow the reference rules
+    E, H = A.convert(sp.ELL), A.convert(sp.HYB)
+    OE, OH = oracle.ell(n, n, i, j, a), oracle.hyb(n, n, i, j, a)
+    ee, eh = E.export(), H.export()
+    assert np.array_equal(ee["column_index"], OE.column_index) and np.array_equal(ee["value"], OE.value)
+    assert (H.ell_row_length, H.num_coo_entries) == (OH.ell_row_length, OH.num_coo_entries)
+    assert np.array_equal(eh["ell_column_index"], OH.ell_column_index) and np.array_equal(eh["coo_column_index"], OH.coo_column_index)
+
+
+def test_rmat_generator_matches_numpy_restatement(oracle):
+    scale, ef, seed = 12, 16, 0x5EED0003
+    r, c, v = rmat_entries(scale, ef, seed)
+    A = sp.generators.rmat(scale, ef, seed)
+    e = A.export()
+    n = 1 << scale
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, r + 1, 1)
+    rp = np.cumsum(rp)
+    assert A.num_entries == len(r)
+    assert np.array_equal(e["row_ptr"], rp) and np.array_equal(e["column_index"], c) and np.array_equal(e["value"], v)
+
+
+@pytest.mark.parametrize("fmt", [sp.CSR, sp.ELL, sp.COO, sp.HYB])
+def test_config1_poisson2d_1000x1000_full_size(oracle, fmt):
+    """BASELINE config 1: 1 000 000 rows, 4 996 000 nnz, against the oracle at full size."""
+    n = 1000
+    i, j, a = stencil_entries(0, n, n)
+    N = n * n
+    assert len(i) == 4996000
+    x = 1.0 + (np.arange(N) % 7) / 8.0  # exactly representable
+    O = oracle.csr(N, N, i, j, a)
+    yref = oracle.csr_spmv(O, x)
+    A = sp.generators.stencil(sp.STENCIL_2D5, n, n, 1, fmt=fmt)
+    assert A.num_entries == 4996000
+    if fmt == sp.CSR:
+        assert A.algorithmic_bytes() == 79952004
+    y = A * x
+    assert_within(y, yref, oracle.csr_abs_rowsum(O, x), "config 1")
+    if fmt in (sp.CSR, sp.ELL):
+        # integer-valued data: every partial sum is exact, any order gives the same bits
+        assert np.array_equal(y, yref)
+
+
+def test_config2_poisson3d_128_ell_full_size(oracle):
+    """BASELINE config 2: 128^3 7-point, ELL W=7, 14 680 064 slots."""
+    n = 128
+    i, j, a = stencil_entries(1, n, n, n)
+    N = n ** 3
+    rng = np.random.default_rng(2)
+    x = rng.uniform(0.5, 1.5, N)
+    O = oracle.csr(N, N, i, j, a)
+    yref = oracle.csr_spmv(O, x)
+    A = sp.generators.stencil(sp.STENCIL_3D7, n, n, n, fmt=sp.ELL)
+    assert (A.row_length, A.num_entries) == (7, 14581760)
+    assert A.algorithmic_bytes() == 209715200
+    y = A * x
+    assert np.array_equal(y, yref)  # same order and roundings as the reference's row loop
+    for rows_per_thread in (1, 2, 4):
+        A.set_option("ell.rows_per_thread", rows_per_thread)
+        assert np.array_equal(A * x, yref)
+
+
+def test_rmat_cross_format_agreement_and_linearity(oracle):
+    """Power-law rows (BASELINE configs 3/4 at reduced scale): all formats agree with the oracle."""
+    scale, ef, seed = 16, 16, 0x5EED0003
+    r, c, v = rmat_entries(scale, ef, seed)
+    n = 1 << scale
+    rng = np.random.default_rng(9)
+    x1, x2 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    O = oracle.csr(n, n, r + 1, c + 1, v)
+    A = sp.generators.rmat(scale, ef, seed)
+    for x in (x1, x2):
+        yref = oracle.csr_spmv(O, x)
+        bound = oracle.csr_abs_rowsum(O, x)
+        assert_within(A * x, yref, bound, "rmat csr")
+        for fmt, arg in ((sp.COO, COO_SEGMENTED), (sp.COO, COO_ATOMIC), (sp.HYB, 0), (sp.ELL, 0)):
+            assert_within(A.convert(fmt, arg) * x, yref, bound, f"rmat fmt {fmt}/{arg}")
+    # linearity: A(x1 + 2 x2) = A x1 + 2 A x2 within the bound
+    y12 = A * (x1 + 2 * x2)
+    lin = (A * x1) + 2 * (A * x2)
+    assert_within(y12, lin, 4 * (oracle.csr_abs_rowsum(O, np.abs(x1) + 2 * np.abs(x2))), "linearity")
+    OH = oracle.hyb(n, n, r + 1, c + 1, v)
+    H = A.convert(sp.HYB)
+    assert (H.ell_row_length, H.num_coo_entries) == (OH.ell_row_length, OH.num_coo_entries)
+
+
+def test_stencil27_rowsum_property_large():
+    """Size-independent property at a large size: with x = 1, row i of the 27-point operator sums to
+    26 - (#neighbours), which is 0 in the interior.  256^3 = 16.7 M rows, 449 M non-zeros."""
+    n = 256
+    A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+    assert A.num_entries == (3 * n - 2) ** 3
+    y = A * np.ones(n ** 3)
+    y3 = y.reshape(n, n, n)
+    assert np.all(y3[1:-1, 1:-1, 1:-1] == 0.0)
+    idx = np.arange(n)
+    span = np.where((idx == 0) | (idx == n - 1), 2, 3)
+    expect = 27.0 - (span[:, None, None] * span[None, :, None] * span[None, None, :])
+    assert np.array_equal(y3, expect)
+
+
+# --------------------------------------------------------------------------------------------
+# row partition (the "N ranks in one process" analogue of the reference's 2-thread tests)
+# --------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_row_partition_concatenates_to_the_full_product(oracle, P):
+    n = 48
+    i, j, a = stencil_entries(2, n, n, n)
+    N = n ** 3
+    rng = np.random.default_rng(P)
+    x = rng.uniform(-1, 1, N)
+    O = oracle.csr(N, N, i, j, a)
+    yref = oracle.csr_spmv(O, x)
+    A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+    for starts, ostarts in ((sp.partition.rows_ref(N, P), oracle.partition_rows_ref(N, P)),
+                            (sp.partition.rows_nnz(A, P), oracle.partition_rows_nnz(O.row_ptr, P))):
+        assert np.array_equal(starts, ostarts)  # the partition is bit-exact
+        parts = []
+        for p in range(P):
+            B = A.row_block(int(starts[p]), int(starts[p + 1]))
+            G = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, row_begin=int(starts[p]), row_end=int(starts[p + 1]))
+            yb = B * x
+            assert np.array_equal(yb, G * x)
+            parts.append(yb)
+        assert_within(np.concatenate(parts), yref, oracle.csr_abs_rowsum(O, x), f"P={P}")
+    # reference partition helpers (csr-matrix.cpp:77-95)
+    for t in range(P):
+        assert csr_matrix.spmv_rows_per_thread(A, t, P) == oracle.csr_rows_per_thread(N, t, P)
+        assert csr_matrix.spmv_nonzeros_per_thread(A, t, P) == oracle.csr_nonzeros_per_thread(O.row_ptr, N, t, P)
+
+
+def test_kernels_really_launch():
+    before = sp.launch_count()
+    A = sp.generators.stencil(sp.STENCIL_2D5, 64, 64, 1)
+    A.spmv()
+    A.sync()
+    assert sp.launch_count() == before + 1
+    assert A.kernel_name == "csr_stream_kernel"
