@@ -831,6 +831,10 @@ static int64_t * option_slot(Matrix * m, const char * key)
 {
     if (!strcmp(key, "csr.tile")) return &m->opt_csr_tile;
     if (!strcmp(key, "csr.stages")) return &m->opt_csr_stages;
+    if (!strcmp(key, "csr.threads")) return &m->opt_csr_threads;
+    if (!strcmp(key, "pdl")) return &m->opt_pdl;
+    if (!strcmp(key, "csr.algo")) return &m->opt_csr_algo;
+    if (!strcmp(key, "csr.lanes")) return &m->opt_csr_lanes;
     if (!strcmp(key, "csr.ctas_per_sm")) return &m->opt_csr_ctas;
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;

@@ -77,7 +77,7 @@ void matrix_free(Matrix * m)
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    cudaFree(m->rp); cudaFree(m->col); cudaFree(m->val); cudaFree(m->tile_row);
+    cudaFree(m->rp); cudaFree(m->col); cudaFree(m->val); cudaFree(m->tile_row); cudaFree(m->span_row);
     cudaFree(m->ell_col); cudaFree(m->ell_val);
     cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
     if (m->own_x) cudaFree(m->x);
@@ -157,12 +157,12 @@ int store_offsets(Matrix * m, const int64_t * d_rp64, int64_t rows, int64_t stor
     m->off64 = stored >= ((int64_t)1 << 32) || g_force_off64.load() != 0;
     if (m->off64) {
         int64_t * rp = nullptr;
-        SPMV_TRY(dev_alloc(m, &rp, rows + 1 + 64));
+        SPMV_TRY(dev_alloc(m, &rp, rows + 1 + 2048));  // slack: the CSR kernel bulk-copies fixed-size row-pointer windows
         SPMV_CUDA(cudaMemcpyAsync(rp, d_rp64, sizeof(int64_t) * (size_t)(rows + 1), cudaMemcpyDeviceToDevice, m->stream));
         m->rp = rp;
     } else {
         uint32_t * rp = nullptr;
-        SPMV_TRY(dev_alloc(m, &rp, rows + 1 + 64));
+        SPMV_TRY(dev_alloc(m, &rp, rows + 1 + 2048));  // slack: the CSR kernel bulk-copies fixed-size row-pointer windows
         narrow_offsets_kernel<uint32_t><<<grid_for(rows + 1), 256, 0, m->stream>>>(rows + 1, d_rp64, rp);
         SPMV_CUDA(cudaGetLastError());
         m->rp = rp;
@@ -349,6 +349,16 @@ static int max_row_length(const Matrix * src, cudaStream_t s, int64_t * out)
     SPMV_CUDA(cudaMemcpyAsync(&h, d.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     SPMV_CUDA(cudaStreamSynchronize(s));
     *out = h;
+    return 0;
+}
+
+// Longest row of a CSR matrix (cached in the handle; used to pick the SpMV kernel).
+int csr_max_row_length(Matrix * m)
+{
+    if (m->csr_maxlen >= 0) return 0;
+    int64_t v = 0;
+    SPMV_TRY(m->off64 ? max_row_length<int64_t>(m, m->stream, &v) : max_row_length<uint32_t>(m, m->stream, &v));
+    m->csr_maxlen = v;
     return 0;
 }
 

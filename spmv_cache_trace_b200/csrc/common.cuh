@@ -68,7 +68,12 @@ struct spmvb200_matrix_s {
     double * val = nullptr;
     int32_t * tile_row = nullptr;
     int64_t ntiles = 0;
-    int csr_tile = 0;  // entries per tile the tile_row table was built for
+    int csr_tile = 0;  // entries per tile the tile table was built for
+    int csr_grid = 0;  // ... and the persistent grid size
+    int64_t csr_chunk = 0;  // non-zeros per CTA
+    int csr_tpc = 0;        // tiles per CTA
+    int32_t * span_row = nullptr;  // warp kernel: row holding the first entry of every 256-entry span
+    int64_t csr_maxlen = -1;       // longest row (computed on first use)
 
     // ELL (column-major)
     int32_t * ell_col = nullptr;
@@ -96,6 +101,10 @@ struct spmvb200_matrix_s {
     // options (spmvb200_set_option)
     int64_t opt_csr_tile = 0;     // 0 = auto
     int64_t opt_csr_stages = 0;   // 0 = auto
+    int64_t opt_csr_threads = 0;  // threads per CTA (128, 256), 0 = auto
+    int64_t opt_pdl = 1;          // programmatic dependent launch
+    int64_t opt_csr_lanes = 0;    // lanes per row in direct mode (1, 2, 4, 8), 0 = auto
+    int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto

@@ -142,8 +142,13 @@ def test_poisson2D(oracle, kats, poisson2d, fmt, kw):
     o = oracle.mm_parse(text)
     yref = oracle.csr_spmv(oracle.csr(o.rows, o.columns, o.i, o.j, o.a), b)
     assert_within(y, yref, bound_of(oracle, o.rows, o.columns, o.i, o.j, o.a, b), fmt)
-    if fmt in ("csr", "ell"):
+    if fmt == "ell":
         assert np.array_equal(y, yref)  # same summation order, same roundings
+    if fmt == "csr" and not kw:
+        # one lane per row: only rows cut by a tile boundary may differ in the last bit; this small
+        # matrix (2417 entries) is cut into 16-entry chunks, so at most one row per chunk
+        A.set_option("csr.lanes", 1)
+        assert (A * b != yref).sum() <= (2417 + 15) // 16
     if fmt == "ell":
         assert A.row_length == kats["poisson2D"]["probed"]["ell_row_length"]
     if fmt == "hybrid":
@@ -175,8 +180,6 @@ def test_ref_vectors(oracle, ref_vectors):
             assert A.size() == int(rv[q + "size"][0])
             y = csr_matrix.spmv(A, x, y0.copy())
             assert_within(y, rv[q + "y_t1"], bound, name)
-            if maxlen <= 96 and len(e["value"]) <= 1024:
-                assert np.array_equal(y, rv[q + "y_t1"]), name
         for mode in (COO_ATOMIC, COO_SEGMENTED):
             q = p + "coo/"
             A = coo_matrix.from_matrix_market(mm, mode)
@@ -244,7 +247,12 @@ def test_spmv_host_end_to_end(oracle, poisson2d):
     y = np.full(A.rows, 0.25)
     A.spmv_host(b, y)
     o = oracle.mm_parse(text)
-    yref = oracle.csr_spmv(oracle.csr(o.rows, o.columns, o.i, o.j, o.a), b, np.full(A.rows, 0.25))
+    O = oracle.csr(o.rows, o.columns, o.i, o.j, o.a)
+    yref = oracle.csr_spmv(O, b, np.full(A.rows, 0.25))
+    assert_within(y, yref, oracle.csr_abs_rowsum(O, b) + 0.25, "spmv_host")
+    E = ell_matrix.from_matrix_market(matrix_market.fromStream(text))
+    y = np.full(E.rows, 0.25)
+    E.spmv_host(b, y)
     assert np.array_equal(y, yref)
 
 
@@ -315,11 +323,20 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
     e = A.export()
     assert np.array_equal(e["row_ptr"], O.row_ptr) and np.array_equal(e["column_index"], O.column_index)
     assert np.array_equal(e["value"], O.value)
-    for tile, stages in ((1024, 1), (1024, 4), (2048, 1), (2048, 2), (2048, 3), (4096, 1), (4096, 2)):
+    for threads, tile, stages, lanes, algo in ((128, 512, 2, 1, 0), (128, 512, 3, 2, 0), (128, 1024, 3, 4, 0),
+                                               (256, 1024, 2, 8, 0), (256, 2048, 3, 1, 0), (256, 2048, 2, 0, 2),
+                                               (128, 512, 2, 0, 2), (256, 1024, 3, 0, 2), (0, 0, 0, 0, 0)):
+        A.set_option("csr.threads", threads)
         A.set_option("csr.tile", tile)
         A.set_option("csr.stages", stages)
-        y = csr_matrix.spmv(A, x, y0.copy())
-        assert_within(y, yref, bound, f"csr tile={tile} stages={stages}")
+        A.set_option("csr.lanes", lanes)
+        A.set_option("csr.algo", algo)
+        for pdl, ctas in ((1, 0), (0, 0), (1, 1)):
+            A.set_option("pdl", pdl)
+            A.set_option("csr.ctas_per_sm", ctas)
+            y = csr_matrix.spmv(A, x, y0.copy())
+            assert_within(y, yref, bound, f"csr threads={threads} tile={tile} stages={stages} lanes={lanes} "
+                                          f"algo={algo} pdl={pdl} ctas={ctas}")
     for fmt, kw in (("coo", {}), ("coo", {"mode": COO_ATOMIC}), ("hybrid", {})):
         B = build(fmt, mm, **kw)
         y = B * x + y0
@@ -457,6 +474,13 @@ def test_config2_poisson3d_128_ell_full_size(oracle):
     for rows_per_thread in (1, 2, 4):
         A.set_option("ell.rows_per_thread", rows_per_thread)
         assert np.array_equal(A * x, yref)
+    # CSR, one lane per row: every row that is not cut by a tile boundary is bit-identical too
+    C = sp.generators.stencil(sp.STENCIL_3D7, n, n, n, fmt=sp.CSR)
+    C.set_option("csr.lanes", 1)
+    yc = C * x
+    assert_within(yc, yref, oracle.csr_abs_rowsum(O, x), "config 2 csr")
+    tiles = 148 * 8 * (14581760 // (148 * 8 * 1024) + 2)
+    assert (yc != yref).sum() <= tiles
 
 
 def test_rmat_cross_format_agreement_and_linearity(oracle):
@@ -535,4 +559,4 @@ def test_kernels_really_launch():
     A.spmv()
     A.sync()
     assert sp.launch_count() == before + 1
-    assert A.kernel_name == "csr_stream_kernel"
+    assert A.kernel_name.startswith("csr_stream_kernel")
