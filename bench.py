@@ -377,7 +377,9 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-extra", action="store_true", help="skip the per-format / per-config block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
-    ap.add_argument("--iterations", type=int, default=10, help="N>1: SpMV iterations per timed run")
+    ap.add_argument("--exchange", default=None, choices=["allgather", "halo", "auto"],
+                    help="N>1: how x is exchanged (default: measure allgather and halo, headline = faster)")
+    ap.add_argument("--no-single", action="store_true", help="N>1: skip the one-GPU run of the same matrix")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

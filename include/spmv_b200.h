@@ -276,6 +276,16 @@ int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t *sta
 /* New matrix holding rows [row_begin, row_end) of a CSR matrix (global columns). */
 int spmvb200_csr_row_block(spmvb200_matrix_t m, int64_t row_begin, int64_t row_end,
                            spmvb200_matrix_t *out);
+/* What a rank of the row-partitioned mode needs from the others.  For a CSR matrix whose rows own
+ * columns [col_begin, col_end) of x (the analogue of the reference tagging every x[j] with the
+ * thread that owns its page, matrix/csr-matrix.cpp:132-136):
+ *   col_min, col_max   smallest / largest column index referenced by any row (-1 if no entries);
+ *   lo_end             1 + last row that references a column <  col_begin (0 if none);
+ *   hi_begin           first row that references a column >= col_end (rows if none).
+ * Rows [lo_end, hi_begin) -- if that range is not empty -- reference only the rank's own columns
+ * and can run while the exchange of x is still in flight. */
+int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col_end,
+                             int64_t *col_min, int64_t *col_max, int64_t *lo_end, int64_t *hi_begin);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,10 @@ def device_count() -> int:
     return n.value if rc == 0 else 0
 
 
+def set_device(device: int) -> None:
+    _check(_abi.lib().spmvb200_set_device(int(device)))
+
+
 def launch_count() -> int:
     """Number of kernels this library launched so far in this process."""
     return int(_abi.lib().spmvb200_launch_count())
@@ -368,6 +372,12 @@ class DeviceMatrix:
         h = C.c_void_p()
         _check(_abi.lib().spmvb200_convert(self._h, fmt, arg, C.byref(h)))
         return DeviceMatrix(h)
+
+    def column_span(self, col_begin: int, col_end: int) -> dict:
+        """Columns this (CSR) row block references and its rows that need no remote x (see spmv_b200.h)."""
+        v = [C.c_int64() for _ in range(4)]
+        _check(_abi.lib().spmvb200_csr_column_span(self._h, col_begin, col_end, *[C.byref(t) for t in v]))
+        return dict(col_min=v[0].value, col_max=v[1].value, lo_end=v[2].value, hi_begin=v[3].value)
 
     def row_block(self, row_begin: int, row_end: int) -> "DeviceMatrix":
         h = C.c_void_p()

@@ -93,6 +93,39 @@ __global__ void rebase_offsets_kernel(int64_t n, const OffT * rp, int64_t first,
         out[r] = (int64_t)rp[r] - first;
 }
 
+// out[0] = min column, out[1] = max column, out[2] = lo_end, out[3] = hi_begin (see spmv_b200.h)
+template <typename OffT>
+__global__ void column_span_kernel(int64_t rows, const OffT * rp, const int32_t * col, int64_t cb, int64_t ce,
+                                   long long * out)
+{
+    long long cmin = LLONG_MAX, cmax = -1, lo_end = 0, hi_begin = rows;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        long long rmin = LLONG_MAX, rmax = -1;
+        for (int64_t k = (int64_t)rp[r]; k < (int64_t)rp[r + 1]; ++k) {
+            const long long c = col[k];
+            rmin = c < rmin ? c : rmin;
+            rmax = c > rmax ? c : rmax;
+        }
+        if (rmax < 0) continue;
+        cmin = rmin < cmin ? rmin : cmin;
+        cmax = rmax > cmax ? rmax : cmax;
+        if (rmin < cb && r + 1 > lo_end) lo_end = r + 1;
+        if (rmax >= ce && r < hi_begin) hi_begin = r;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        lo_end = max(lo_end, __shfl_xor_sync(0xffffffffu, lo_end, o));
+        hi_begin = min(hi_begin, __shfl_xor_sync(0xffffffffu, hi_begin, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], cmin);
+        atomicMax(&out[1], cmax);
+        atomicMax(&out[2], lo_end);
+        atomicMin(&out[3], hi_begin);
+    }
+}
+
 static int upload_ell_rowmajor(Matrix * m, int64_t rows, int64_t W, const int32_t * col, const double * val, int skip)
 {
     cudaStream_t s = m->stream;
@@ -892,6 +925,29 @@ int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t * st
     SPMV_CUDA(cudaGetLastError());
     SPMV_CUDA(cudaMemcpyAsync(starts, d.p, sizeof(int64_t) * (size_t)(parts + 1), cudaMemcpyDeviceToHost, m->stream));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col_end, int64_t * col_min,
+                             int64_t * col_max, int64_t * lo_end, int64_t * hi_begin)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_CSR) return fail(SPMVB200_ERR_INVALID, "not a CSR matrix");
+    Scratch<long long> d;
+    SPMV_TRY(d.alloc(4));
+    long long h[4] = {LLONG_MAX, -1, 0, (long long)m->rows};
+    SPMV_CUDA(cudaMemcpyAsync(d.p, h, sizeof h, cudaMemcpyHostToDevice, m->stream));
+    if (m->rows > 0) {
+        if (m->off64) column_span_kernel<int64_t><<<grid_for(m->rows), 256, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, m->col, col_begin, col_end, d.p);
+        else column_span_kernel<uint32_t><<<grid_for(m->rows), 256, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, m->col, col_begin, col_end, d.p);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    SPMV_CUDA(cudaMemcpyAsync(h, d.p, sizeof h, cudaMemcpyDeviceToHost, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    if (col_min) *col_min = h[1] < 0 ? -1 : h[0];
+    if (col_max) *col_max = h[1];
+    if (lo_end) *lo_end = h[2];
+    if (hi_begin) *hi_begin = h[3];
     return 0;
 }
 

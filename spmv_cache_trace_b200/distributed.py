@@ -1,5 +1,355 @@
-"""Row-partitioned multi-GPU SpMV (one process per GPU, torch.distributed / NCCL).  Filled in below."""
+"""Row-partitioned multi-GPU SpMV: one process per GPU, torch.distributed for the plumbing.
+
+The reference is a single-process OpenMP code; what it has is the PARTITION (every thread owns
+ceil(rows/T) consecutive rows, matrix/csr-matrix.cpp:77-95) and a model of who owns which part of x
+(aligned-allocator.hpp:156-211).  This module turns that into a distributed iteration
+x_{k+1} = A x_k on the GPUs of one NVSwitch domain:
+
+  * rank p owns rows [s_p, s_{p+1}) of A (global column indices) and the matching slice of x and y;
+    the partition is the reference rule (`partition.rows_ref`) or balanced non-zeros (`rows_nnz`);
+  * x lives in two full-length device buffers used in ping-pong: iteration k reads X_k and writes its
+    rows of A X_k straight into its slice of X_{k+1}, so there is no y -> x copy;
+  * the exchange fills the other ranks' slices of X_k, either with one NCCL all-gather (in place) or,
+    when a rank only needs a narrow band of columns (stencils: one grid plane from each neighbour),
+    with NCCL send/recv of exactly those columns ("halo");
+  * the local rows are split in three CSR blocks -- rows that reference columns below the rank's own
+    slice, rows that reference only own columns (interior), rows that reference columns above --
+    the interior block runs on the compute stream WHILE the exchange runs on the communication
+    stream; the two boundary blocks run after the exchange's event.
+
+Everything that is not the SpMV kernel itself (partition arithmetic, the exchange plan, the
+ping-pong bookkeeping) is plain Python and is exercised on CPU by tests/test_distributed_gloo.py
+with world_size 2 over gloo, with the oracle standing in for the local kernel.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
 
 
-def bench_main(args):
-    raise SystemExit("multi-GPU bench not wired yet")
+# --------------------------------------------------------------------------------------------
+# pure bookkeeping (no GPU needed)
+# --------------------------------------------------------------------------------------------
+
+def partition_rows_ref(rows: int, parts: int):
+    """The reference rule, start_p = min(rows, p * ceil(rows/P)) (matrix/csr-matrix.cpp:77-83)."""
+    rpt = (rows + parts - 1) // parts
+    return np.minimum(rows, np.arange(parts + 1, dtype=np.int64) * rpt)
+
+
+def owner_of(starts, col: int) -> int:
+    """Rank whose slice of x holds column `col`."""
+    return int(np.searchsorted(starts, col, side="right") - 1)
+
+
+@dataclass
+class ExchangePlan:
+    """Who sends which columns of x to whom.  sends/recvs: lists of (peer, lo, hi), hi exclusive."""
+    mode: str
+    sends: list = field(default_factory=list)
+    recvs: list = field(default_factory=list)
+    recv_bytes: int = 0
+
+
+def make_exchange_plan(starts, need, rank: int, mode: str = "auto", halo_fraction: float = 0.25) -> ExchangePlan:
+    """`need[q] = (lo, hi)`: the column range rank q's rows reference (hi exclusive; lo >= hi: nothing).
+
+    mode "allgather": every rank receives every other slice.  "halo": rank q receives
+    need[q] minus its own slice, from the owners.  "auto": halo if every rank's remote need is at
+    most `halo_fraction` of the vector, else allgather.
+    """
+    P = len(starts) - 1
+    n = int(starts[-1])
+
+    def remote(q):
+        lo, hi = need[q]
+        out = []
+        if hi <= lo:
+            return out
+        for o in range(P):
+            if o == q:
+                continue
+            a, b = max(lo, int(starts[o])), min(hi, int(starts[o + 1]))
+            if b > a:
+                out.append((o, a, b))
+        return out
+
+    if mode == "auto":
+        worst = max((sum(b - a for _, a, b in remote(q)) for q in range(P)), default=0)
+        mode = "halo" if worst <= halo_fraction * n else "allgather"
+    plan = ExchangePlan(mode)
+    if mode == "allgather":
+        plan.recv_bytes = 8 * (n - int(starts[rank + 1] - starts[rank]))
+        return plan
+    plan.recvs = remote(rank)
+    for q in range(P):
+        if q != rank:
+            plan.sends += [(q, a, b) for o, a, b in remote(q) if o == rank]
+    plan.recv_bytes = 8 * sum(b - a for _, a, b in plan.recvs)
+    return plan
+
+
+def exchange(dist, x_full, starts, rank: int, plan: ExchangePlan):
+    """Fill the remote parts of x_full this rank needs.  Works on CPU (gloo) and CUDA (nccl) tensors."""
+    P = len(starts) - 1
+    if P == 1:
+        return
+    if plan.mode == "allgather":
+        sizes = np.diff(starts)
+        mine = x_full[int(starts[rank]):int(starts[rank + 1])]
+        if np.all(sizes == sizes[0]) and hasattr(dist, "all_gather_into_tensor") and x_full.is_cuda:
+            dist.all_gather_into_tensor(x_full[: int(starts[-1])], mine)  # in place
+        else:  # uneven slices (or gloo): one broadcast per owner
+            for q in range(P):
+                dist.broadcast(x_full[int(starts[q]):int(starts[q + 1])], src=q)
+        return
+    ops = []
+    for peer, a, b in plan.sends:
+        ops.append(dist.P2POp(dist.isend, x_full[a:b], peer))
+    for peer, a, b in plan.recvs:
+        ops.append(dist.P2POp(dist.irecv, x_full[a:b], peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def split_rows(lo_end: int, hi_begin: int, rows: int):
+    """Row blocks (begin, end, needs_remote_x) of a rank: [0,lo_end) boundary, [lo_end,hi_begin) interior,
+    [hi_begin,rows) boundary.  If the interior is empty the whole rank is one boundary block."""
+    if lo_end >= hi_begin:
+        return [(0, rows, True)]
+    blocks = []
+    if lo_end > 0:
+        blocks.append((0, lo_end, True))
+    blocks.append((lo_end, hi_begin, False))
+    if hi_begin < rows:
+        blocks.append((hi_begin, rows, True))
+    return blocks
+
+
+# --------------------------------------------------------------------------------------------
+# the GPU executor
+# --------------------------------------------------------------------------------------------
+
+class DistributedSpMV:
+    """Iterated x <- A x on a row partition of A, local rows already resident as a CSR DeviceMatrix."""
+
+    def __init__(self, sp, torch, dist, local, starts, rank: int, mode: str = "auto", overlap: bool = True):
+        self.sp, self.torch, self.dist = sp, torch, dist
+        self.rank, self.starts = rank, np.asarray(starts, dtype=np.int64)
+        self.P = len(starts) - 1
+        self.n = int(starts[-1])
+        self.s, self.e = int(starts[rank]), int(starts[rank + 1])
+        self.rows = self.e - self.s
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # ping-pong x buffers (+ slack so vector loads past the end stay in bounds)
+        self.X = [torch.zeros(self.n + 16, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.compute = torch.cuda.Stream()
+        self.comm = torch.cuda.Stream()
+        span = local.column_span(self.s, self.e)
+        need = [(0, 0)] * self.P
+        mine = torch.tensor([span["col_min"], span["col_max"] + 1], dtype=torch.int64, device=dev)
+        if self.P > 1:
+            allneed = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(self.P)]
+            dist.all_gather(allneed, mine)
+            need = [tuple(int(v) for v in t.tolist()) for t in allneed]
+        else:
+            need = [tuple(int(v) for v in mine.tolist())]
+        self.plan = make_exchange_plan(self.starts, need, rank, mode)
+        blocks = split_rows(span["lo_end"], span["hi_begin"], self.rows) if overlap and self.P > 1 else [(0, self.rows, True)]
+        self.blocks = []
+        for b, e, remote in blocks:
+            A = local if (b, e) == (0, self.rows) else local.row_block(b, e)
+            A.set_stream(self.compute.cuda_stream)
+            self.blocks.append((A, b, e, remote))
+        self.local = local
+        self.k = 0
+        self.nnz_local = local.num_entries
+        self.launches_per_step = len(self.blocks)
+
+    def set_x(self, x_local):
+        """Set this rank's slice of the current x (host or device tensor/array of `rows` values)."""
+        t = self.torch.as_tensor(x_local, dtype=self.torch.float64).to(self.X[0].device)
+        self.X[self.k % 2][self.s:self.e].copy_(t)
+        self.torch.cuda.synchronize()
+
+    def x_local(self):
+        return self.X[self.k % 2][self.s:self.e]
+
+    def step(self, scale: float = 0.0):
+        """One iteration: exchange x_k, y = A x_k written into x_{k+1}'s local slice.
+        `scale` != 0 multiplies the new slice by it (keeps long benchmark iterations finite)."""
+        torch = self.torch
+        cur, nxt = self.X[self.k % 2], self.X[(self.k + 1) % 2]
+        ready = torch.cuda.Event()
+        self.comm.wait_stream(self.compute)  # x_k's local slice was produced on the compute stream
+        with torch.cuda.stream(self.comm):
+            exchange(self.dist, cur, self.starts, self.rank, self.plan)
+            ready.record(self.comm)
+        with torch.cuda.stream(self.compute):
+            nxt[self.s:self.e].zero_()  # the kernels accumulate: y += A x
+            waited = False
+            # interior block first (no remote x), then the boundary blocks after the exchange
+            for A, b, e, remote in sorted(self.blocks, key=lambda t: t[3]):
+                if remote and not waited:
+                    self.compute.wait_event(ready)
+                    waited = True
+                A.bind_x(cur.data_ptr())
+                A.bind_y(nxt.data_ptr() + 8 * (self.s + b))
+                A.spmv()
+            if not waited:
+                self.compute.wait_event(ready)
+            if scale:
+                nxt[self.s:self.e].mul_(scale)
+        self.k += 1
+
+    def synchronize(self):
+        self.torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------
+# bench.py --gpus N  (N > 1)
+# --------------------------------------------------------------------------------------------
+
+def bench_main(args) -> int:
+    import torch
+    import torch.distributed as dist
+
+    import spmv_cache_trace_b200 as sp
+    from bench import METRIC, NOMINAL_HBM_GBS, UNIT, ClockSampler, cpu_baseline, measured_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    sp.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = int(os.environ.get("SPMV_BENCH_GRID", "512"))
+    N = n ** 3
+    starts = partition_rows_ref(N, world)
+    s, e = int(starts[rank]), int(starts[rank + 1])
+    peak, peak_src = measured_peak()
+
+    # every rank generates only its own rows of the 27-point operator, on its own GPU
+    local = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR, row_begin=s, row_end=e)
+    nnz_local = torch.tensor([local.num_entries], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_local)
+    nnz = int(nnz_local.item())
+    B = 4 * (N + 1) + 12 * nnz + 16 * N  # matrix_size + x_size + y_size, reference-equivalent
+
+    # x_(k+1) = A x_k / 52: every eigenvalue of the 27-point operator (26 on the diagonal, -1 off it)
+    # lies within 52 of zero, so the iterates stay finite however many steps are timed.  The scaling
+    # is one tiny elementwise kernel on the rank's slice (8 B/row next to ~330 B/row of matrix).
+    SCALE = 1.0 / 52.0
+    results = {}
+    modes = [args.exchange] if getattr(args, "exchange", None) else ["allgather", "halo"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    marks = {}
+    for mode in modes:
+        eng = DistributedSpMV(sp, torch, dist, local, starts, rank, mode=mode, overlap=True)
+        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        eng.set_x(torch.rand(e - s, generator=g, dtype=torch.float64) - 0.5)
+        for _ in range(max(args.warmup, 3)):
+            eng.step(scale=SCALE)
+        eng.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = sp.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks[mode] = [time.perf_counter(), None]
+        ev0.record(eng.compute)
+        for _ in range(args.steps):
+            eng.step(scale=SCALE)
+        ev1.record(eng.compute)
+        torch.cuda.synchronize()
+        marks[mode][1] = time.perf_counter()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        t = float(ms.item()) * 1e-3 / args.steps
+        xnorm = float(torch.linalg.vector_norm(eng.x_local()).item())
+        results[mode] = {"ms_per_step": t * 1e3, "gbs": B / t / 1e9, "gflops": 2.0 * nnz / t / 1e9,
+                         "recv_bytes_per_step_per_rank": eng.plan.recv_bytes, "plan": eng.plan.mode,
+                         "row_blocks": [(b, e2, r) for _, b, e2, r in eng.blocks],
+                         "gpu_launches": int(sp.launch_count() - launches0), "x_norm": xnorm}
+        # end to end: this rank's slice of x from pinned host memory each step, its slice of y back
+        hx = torch.empty(e - s, dtype=torch.float64).pin_memory()
+        hy = torch.empty(e - s, dtype=torch.float64).pin_memory()
+        hx.copy_(torch.rand(e - s, dtype=torch.float64) - 0.5)
+        e2e_steps = max(3, min(args.steps, 10))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0.record(eng.compute)
+        for _ in range(e2e_steps):
+            with torch.cuda.stream(eng.compute):
+                eng.x_local().copy_(hx, non_blocking=True)
+            eng.step(scale=SCALE)
+            with torch.cuda.stream(eng.compute):
+                hy.copy_(eng.x_local(), non_blocking=True)
+            eng.compute.synchronize()
+        ev1.record(eng.compute)
+        torch.cuda.synchronize()
+        ems = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        results[mode]["e2e_ms_per_step"] = float(ems.item()) / e2e_steps
+        del eng
+    sampler.stop()
+
+    # one-GPU time of the SAME matrix measured in the same job on rank 0 (strong-scaling reference)
+    single = None
+    if world > 1 and rank == 0 and not getattr(args, "no_single", False):
+        try:
+            full = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR)
+            total_ms, _ = sp.time_rotating([full], max(3, min(args.steps, 10)), 3, False)
+            single = total_ms / max(3, min(args.steps, 10))
+            del full
+        except Exception as ex:  # e.g. not enough memory left
+            single = None
+            results["single_gpu_error"] = str(ex)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        best = min(results, key=lambda m: results[m]["ms_per_step"] if isinstance(results[m], dict) and "ms_per_step" in results[m] else 1e30)
+        r = results[best]
+        t = r["ms_per_step"] * 1e-3
+        clocks = sampler.summary(*marks[best])
+        per_rank_bytes = B / world
+        line = {
+            "metric": METRIC, "value": r["gbs"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c5_csr_row_partitioned", "description": f"row-partitioned CSR, 3D 27-point {n}^3 "
+                       f"(config 5), x_(k+1) = A x_k, one step = exchange of x + SpMV", "rows": N, "nonzeros": nnz,
+                       "algorithmic_bytes": B, "partition": "reference rule ceil(rows/P) (csr-matrix.cpp:77-83)",
+                       "exchange": best, "overlap": "interior rows run during the exchange",
+                       "l2": "working set per rank far larger than L2"},
+            "gflops": r["gflops"], "frac_of_8TBs_nominal_per_gpu": r["gbs"] / world / NOMINAL_HBM_GBS,
+            "roofline": {"bound": "hbm", "achieved": per_rank_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": per_rank_bytes / t / 1e9 / peak, "traffic": None,
+                         "kernel": "csr_stream_kernel (per rank; step time includes the exchange)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_rank_bytes)},
+            "e2e": {"value": B / (r["e2e_ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N, "ms_per_step": r["e2e_ms_per_step"],
+                    "call": "per rank: pinned x slice -> device, exchange + SpMV, y slice -> pinned host"},
+            "gpu_launches": r["gpu_launches"], "clocks": clocks, "exchange_variants": results,
+        }
+        if single:
+            line["single_gpu"] = {"ms_per_step": single, "gbs": B / (single * 1e-3) / 1e9,
+                                  "speedup": single / r["ms_per_step"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
