@@ -106,6 +106,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_lanes = 0;    // lanes per row in direct mode (1, 2, 4, 8), 0 = auto
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
+    int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto
     int64_t opt_coo_stages = 0;

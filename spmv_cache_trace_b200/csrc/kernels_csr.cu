@@ -331,7 +331,10 @@ static int launch_csr_variant(Matrix * m)
         SPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, THREADS, smem));
         if (occupancy < 1) return fail(SPMVB200_ERR_CUDA, "csr_stream_kernel does not fit on an SM");
     }
-    const int ctas = m->opt_csr_ctas ? (int)std::min<int64_t>(m->opt_csr_ctas, occupancy) : occupancy;
+    // csr.spare_ctas: leave that many CTA slots per SM free, e.g. for the NCCL kernel of an exchange
+    // that should run concurrently (a persistent grid at full occupancy would lock it out).
+    int ctas = m->opt_csr_ctas ? (int)std::min<int64_t>(m->opt_csr_ctas, occupancy) : occupancy;
+    ctas = std::max<int>(1, ctas - (int)m->opt_csr_spare);
     // persistent grid: one wave, but never more CTAs than there are 16-entry groups
     int64_t grid = std::min<int64_t>((int64_t)m->sm_count * ctas, std::max<int64_t>(1, (m->stored + 15) / 16));
     if (!m->tile_row || m->csr_tile != TILE || m->csr_grid != (int)grid) SPMV_TRY(csr_build_table<OffT>(m, TILE, (int)grid));
