@@ -18,6 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libspmvb200.so")
+CLI = os.path.join(HERE, "bin", "spmv-b200")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 CUDA_SOURCES = ["abi.cu", "kernels_csr.cu", "kernels_csr_warp.cu", "kernels_ell.cu", "kernels_coo.cu", "builders.cu", "generators.cu"]
@@ -85,6 +86,14 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         _run([nvcc, "-ccbin", cxx, "-shared", "-o", LIB] + objs + ["-lz", "-Xlinker", "--no-undefined"], verbose)
     if ptxas_info:
         print("\n".join(outputs))
+    # the C++ host layer above the C ABI: Kernel-plugin mirror + the profile-mode CLI
+    plugin = os.path.join(CSRC, "plugin")
+    srcs = [os.path.join(plugin, f) for f in ("main.cpp", "cuda_spmv_kernels.cpp")]
+    deps = srcs + [os.path.join(plugin, f) for f in ("kernel.hpp", "cuda_spmv_kernels.hpp")] + [LIB]
+    if force or not _newer(CLI, deps):
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        _run([cxx, "-O2", "-std=c++17", "-fopenmp", "-Wall", "-I", INCLUDE, "-o", CLI] + srcs +
+             ["-L", LIBDIR, "-lspmvb200", "-Wl,-rpath,$ORIGIN/../lib"], verbose)
     return LIB
 
 

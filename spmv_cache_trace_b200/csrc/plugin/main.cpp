@@ -1,0 +1,145 @@
+// spmv-b200 -- the profile mode of the reference CLI for the CUDA kernels.
+//
+//   spmv-b200 --spmv-format cuda-csr|cuda-coo|cuda-coo-atomic|cuda-ell|cuda-hybrid \
+//             --matrix PATH [--profile N] [--threads T] [--verbose]
+//
+// Follows src/main.cpp (option names :166-187, kernel factory :209-232, error mapping :261-270) and
+// the protocol of profile_kernel (src/profile-kernel.cpp:197-313): an omp parallel region of T
+// threads, prepare, one warm-up run, then N runs each bracketed barrier / clock / barrier -- and,
+// because the host clock around an asynchronous launch says little, the same N runs timed again
+// with CUDA events.  Output: one JSON document in the reference's shape ("kernel",
+// "execution_time" with print_sample's statistics, src/util/sample.hpp:137-165) plus "roofline".
+// The cache-trace mode (--profile 0 in the reference) stays with the reference binary.
+#include "cuda_spmv_kernels.hpp"
+
+#include <getopt.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static void print_sample(std::ostream & o, std::vector<double> v, const char * unit)
+{
+    const size_t n = v.size();
+    double mn = 0, mx = 0, mean = 0, med = 0, var = 0, skew = NAN, kurt = NAN;
+    if (n) {
+        std::sort(v.begin(), v.end());
+        mn = v.front(); mx = v.back(); med = v[n / 2];  // upper median, like sample.hpp:51-53
+        for (double x : v) mean += x;
+        mean /= (double)n;
+        double m2 = 0, m3 = 0, m4 = 0;
+        for (double x : v) { const double d = x - mean; m2 += d * d; m3 += d * d * d; m4 += d * d * d * d; }
+        m2 /= (double)n; m3 /= (double)n; m4 /= (double)n;
+        var = n > 1 ? m2 * (double)n / (double)(n - 1) : 0.0;
+        if (m2 > 0) { skew = m3 / std::pow(m2, 1.5); kurt = m4 / (m2 * m2); }
+    }
+    auto num = [&](double x) { if (std::isnan(x)) o << "\"nan\""; else o << x; };
+    o << "{\n\"samples\": " << n << ",\n\"min\": "; num(mn);
+    o << ",\n\"max\": "; num(mx);
+    o << ",\n\"mean\": "; num(mean);
+    o << ",\n\"median\": "; num(med);
+    o << ",\n\"variance\": "; num(var);
+    o << ",\n\"standard_deviation\": "; num(std::sqrt(var));
+    o << ",\n\"skewness\": "; num(skew);
+    o << ",\n\"kurtosis\": "; num(kurt);
+    o << ",\n\"unit\": \"" << unit << "\"\n}";
+}
+
+int main(int argc, char ** argv)
+{
+    std::string format, matrix_path;
+    int profile = 10, threads = 1;
+    bool verbose = false;
+    static option longopts[] = {{"spmv-format", required_argument, nullptr, 'f'}, {"matrix", required_argument, nullptr, 'm'},
+                                {"profile", required_argument, nullptr, 'p'}, {"threads", required_argument, nullptr, 't'},
+                                {"verbose", no_argument, nullptr, 'v'}, {"help", no_argument, nullptr, 'h'},
+                                {nullptr, 0, nullptr, 0}};
+    int c;
+    while ((c = getopt_long(argc, argv, "f:m:p:t:vh", longopts, nullptr)) != -1) {
+        switch (c) {
+        case 'f': format = optarg; break;
+        case 'm': matrix_path = optarg; break;
+        case 'p': profile = std::atoi(optarg); break;
+        case 't': threads = std::max(1, std::atoi(optarg)); break;
+        case 'v': verbose = true; break;
+        default:
+            std::cout << "Usage: spmv-b200 --spmv-format FMT --matrix PATH [--profile N] [--threads T] [--verbose]\n"
+                         "  FMT: cuda-csr, cuda-coo, cuda-coo-atomic, cuda-ell, cuda-hybrid\n";
+            return c == 'h' ? EXIT_SUCCESS : EXIT_FAILURE;
+        }
+    }
+    std::unique_ptr<Kernel> kernel = make_cuda_kernel(format, matrix_path);
+    if (!kernel) {
+        std::cerr << "spmv-b200: invalid argument for --spmv-format\n";
+        return EXIT_FAILURE;
+    }
+    try {
+        TraceConfig trace_config(threads);
+        kernel->init(trace_config, std::cerr, verbose);
+        std::vector<double> host_ns((size_t)std::max(profile, 0));
+#ifdef _OPENMP
+        omp_set_num_threads(threads);
+#endif
+        std::string failure;
+#pragma omp parallel
+        {
+            try {
+                kernel->prepare(trace_config);
+                kernel->run(trace_config);  // warm-up (profile-kernel.cpp:263-264)
+                for (int r = 0; r < profile; r++) {
+                    std::chrono::steady_clock::time_point t0, t1;
+#pragma omp barrier
+#pragma omp master
+                    t0 = std::chrono::steady_clock::now();
+#pragma omp barrier
+                    kernel->run(trace_config);
+#pragma omp barrier
+#pragma omp master
+                    {
+                        t1 = std::chrono::steady_clock::now();
+                        host_ns[(size_t)r] = (double)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+                    }
+#pragma omp barrier
+                }
+            } catch (std::exception const & e) {  // profile-kernel.cpp:299-307
+#pragma omp critical
+                failure = e.what();
+            }
+        }
+        if (!failure.empty()) throw kernel_error(failure);
+
+        auto * gpu = dynamic_cast<cuda_spmv_kernel *>(kernel.get());
+        std::vector<float> ms((size_t)std::max(profile, 0));
+        if (profile > 0 && spmvb200_time(gpu->handle(), 0, profile, ms.data()) != 0) throw kernel_error(spmvb200_last_error());
+        std::vector<double> dev_ns(ms.begin(), ms.end());
+        for (double & v : dev_ns) v *= 1e6;
+        spmvb200_info info{};
+        spmvb200_matrix_info(gpu->handle(), &info);
+        const double bytes = (double)(info.matrix_size + info.x_size + info.y_size);
+        double best = 0;
+        if (!dev_ns.empty()) best = *std::min_element(dev_ns.begin(), dev_ns.end());
+
+        std::cout << "{\n\"kernel\": " << *kernel << ",\n\"execution_time\": ";
+        print_sample(std::cout, dev_ns, "ns");
+        std::cout << ",\n\"host_execution_time\": ";
+        print_sample(std::cout, host_ns, "ns");
+        std::cout << ",\n\"roofline\": {\n\"bytes\": " << (long long)bytes << ",\n\"flops\": " << 2 * info.num_entries
+                  << ",\n\"gpu_kernel\": \"" << spmvb200_kernel_name(gpu->handle()) << "\""
+                  << ",\n\"best_gbs\": " << (best > 0 ? bytes / best : 0.0)
+                  << ",\n\"best_gflops\": " << (best > 0 ? 2.0 * (double)info.num_entries / best : 0.0)
+                  << ",\n\"fraction_of_8TBs\": " << (best > 0 ? bytes / best / 8000.0 : 0.0) << "\n}\n}\n";
+    } catch (kernel_error const & e) {
+        std::cerr << kernel->name() << ": " << e.what() << '\n';
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
