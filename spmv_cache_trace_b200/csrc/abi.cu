@@ -762,11 +762,89 @@ int spmvb200_sync(spmvb200_matrix_t m)
     return 0;
 }
 
+// Host-buffer form of y += A*x.  The bytes that must cross PCIe are fixed (x and y up, y down), so
+// the only lever is to use both directions at once: for ELL the rows are cut into chunks; x goes up
+// first, then the y chunks go up on a second stream while, chunk by chunk, the kernel runs and the
+// finished part of y comes back down on the compute stream (H2D and D2H copy engines overlap).
+// Other formats, tiny matrices and pageable buffers take the plain sequence.
+static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chunks, double * y_dev_visible)
+{
+    cudaStream_t s = m->stream;
+    if (!m->upload_stream) {
+        SPMV_CUDA(cudaStreamCreateWithFlags(&m->upload_stream, cudaStreamNonBlocking));
+        SPMV_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
+        for (auto & e : m->ev_chunk) SPMV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t up = m->upload_stream;
+    const int64_t per = round_up((m->rows + chunks - 1) / chunks, 1024);
+    SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, up));
+    SPMV_CUDA(cudaEventRecord(m->ev_x, up));
+    int used = 0;
+    for (int c = 0; c < chunks; c++) {
+        const int64_t b = (int64_t)c * per, e = std::min<int64_t>(m->rows, b + per);
+        if (b >= e) break;
+        if (m->opt_beta0) SPMV_CUDA(cudaMemsetAsync(m->y + b, 0, sizeof(double) * (size_t)(e - b), up));
+        else SPMV_CUDA(cudaMemcpyAsync(m->y + b, y + b, sizeof(double) * (size_t)(e - b), cudaMemcpyHostToDevice, up));
+        SPMV_CUDA(cudaEventRecord(m->ev_chunk[c], up));
+        used = c + 1;
+    }
+    SPMV_CUDA(cudaStreamWaitEvent(s, m->ev_x, 0));
+    const int64_t keep_beta0 = m->opt_beta0;
+    m->opt_beta0 = 0;  // y was prepared chunk by chunk above
+    int rc = 0;
+    for (int c = 0; c < used && rc == 0; c++) {
+        const int64_t b = (int64_t)c * per, e = std::min<int64_t>(m->rows, b + per);
+        cudaStreamWaitEvent(s, m->ev_chunk[c], 0);
+        m->range_begin = b;
+        m->range_end = e;
+        if (y_dev_visible) {  // the kernel adds onto the uploaded chunk and stores the result in host memory
+            m->host_y_in = m->y;
+            m->host_y_out = y_dev_visible;
+        }
+        rc = launch_ell(m, true);
+        m->host_y_in = nullptr;
+        m->host_y_out = nullptr;
+        if (!y_dev_visible && rc == 0 &&
+            cudaMemcpyAsync(y + b, m->y + b, sizeof(double) * (size_t)(e - b), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            rc = fail(SPMVB200_ERR_CUDA, "cudaMemcpyAsync(y chunk)");
+    }
+    m->range_begin = m->range_end = 0;
+    m->opt_beta0 = keep_beta0;
+    if (rc) return rc;
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
 {
     SPMV_TRY(check(m));
     if (!x || !y) return fail(SPMVB200_ERR_INVALID, "null argument");
     cudaStream_t s = m->stream;
+    if (m->format == SPMVB200_ELL && m->opt_host_zero_copy && m->rows > 0 && m->ell_w > 0) {
+        // pinned (page-locked, mapped) buffers: x goes up with the copy engine, then ONE kernel reads
+        // y_old from and writes y_new to host memory while it streams the matrix from HBM
+        cudaPointerAttributes ay{};
+        if (cudaPointerGetAttributes(&ay, y) == cudaSuccess && ay.type == cudaMemoryTypeHost && ay.devicePointer) {
+            if (m->opt_host_zero_copy == 2 && m->rows >= 64 * 1024)  // y up by DMA in chunks, results stored by the kernel
+                return spmv_host_pipelined(m, x, y, (int)(m->opt_host_chunks ? std::min<int64_t>(m->opt_host_chunks, 16) : 4),
+                                           (double *)ay.devicePointer);
+            SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
+            m->host_y_in = m->opt_beta0 ? nullptr : (const double *)ay.devicePointer;
+            m->host_y_out = (double *)ay.devicePointer;
+            const int64_t keep = m->opt_beta0;
+            m->opt_beta0 = 0;
+            const int rc = launch_ell(m, true);
+            m->opt_beta0 = keep;
+            m->host_y_in = nullptr;
+            m->host_y_out = nullptr;
+            if (rc) return rc;
+            SPMV_CUDA(cudaStreamSynchronize(s));
+            return 0;
+        }
+        cudaGetLastError();  // not a registered host pointer: fall through to the copying paths
+    }
+    const int chunks = (int)(m->opt_host_chunks ? std::min<int64_t>(m->opt_host_chunks, 16) : 4);
+    if (m->format == SPMVB200_ELL && chunks > 1 && m->rows >= 64 * 1024) return spmv_host_pipelined(m, x, y, chunks, nullptr);
     SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
     if (!m->opt_beta0) SPMV_CUDA(cudaMemcpyAsync(m->y, y, sizeof(double) * (size_t)m->rows, cudaMemcpyHostToDevice, s));
     SPMV_TRY(launch(m));
@@ -866,6 +944,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.stages")) return &m->opt_csr_stages;
     if (!strcmp(key, "csr.threads")) return &m->opt_csr_threads;
     if (!strcmp(key, "pdl")) return &m->opt_pdl;
+    if (!strcmp(key, "independent_launches")) return &m->opt_independent;
     if (!strcmp(key, "csr.algo")) return &m->opt_csr_algo;
     if (!strcmp(key, "csr.lanes")) return &m->opt_csr_lanes;
     if (!strcmp(key, "csr.ctas_per_sm")) return &m->opt_csr_ctas;
@@ -875,6 +954,8 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;
     if (!strcmp(key, "coo.ctas_per_sm")) return &m->opt_coo_ctas;
     if (!strcmp(key, "beta0")) return &m->opt_beta0;
+    if (!strcmp(key, "host.chunks")) return &m->opt_host_chunks;
+    if (!strcmp(key, "host.zero_copy")) return &m->opt_host_zero_copy;
     return nullptr;
 }
 

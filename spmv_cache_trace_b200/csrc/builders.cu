@@ -82,6 +82,9 @@ void matrix_free(Matrix * m)
     cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
     if (m->own_x) cudaFree(m->x);
     if (m->own_y) cudaFree(m->y);
+    if (m->upload_stream) cudaStreamDestroy(m->upload_stream);
+    if (m->ev_x) cudaEventDestroy(m->ev_x);
+    for (auto & e : m->ev_chunk) if (e) cudaEventDestroy(e);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);

@@ -87,6 +87,14 @@ struct spmvb200_matrix_s {
     int64_t coo_n = 0;
     bool coo_sorted = false;
 
+    // optional row range for the next launches (ELL): [range_begin, range_end), range_end <= 0 = all rows
+    int64_t range_begin = 0, range_end = 0;
+    const double * host_y_in = nullptr;    // zero-copy host-buffer path (ELL): device-visible host pointers
+    double * host_y_out = nullptr;
+    cudaStream_t upload_stream = nullptr;  // second stream of the pipelined host-buffer path
+    cudaEvent_t ev_x = nullptr;
+    cudaEvent_t ev_chunk[16] = {};
+
     // vectors
     double * x = nullptr;
     double * y = nullptr;
@@ -103,6 +111,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_stages = 0;   // 0 = auto
     int64_t opt_csr_threads = 0;  // threads per CTA (128, 256), 0 = auto
     int64_t opt_pdl = 1;          // programmatic dependent launch
+    int64_t opt_independent = 0;  // caller promises: the previous kernel in the stream does not write this x
     int64_t opt_csr_lanes = 0;    // lanes per row in direct mode (1, 2, 4, 8), 0 = auto
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
@@ -111,6 +120,8 @@ struct spmvb200_matrix_s {
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto
     int64_t opt_coo_stages = 0;
     int64_t opt_coo_ctas = 0;
+    int64_t opt_host_zero_copy = 1;  // spmvb200_spmv_host: let the ELL kernel read/write pinned host y directly
+    int64_t opt_host_chunks = 0;  // row chunks of the pipelined spmvb200_spmv_host (ELL), 0 = 8, 1 = off
     int64_t opt_beta0 = 0;        // 1: y = A*x (y is cleared first) instead of y += A*x
     const char * kernel_name = "";
 };

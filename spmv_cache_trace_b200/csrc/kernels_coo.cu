@@ -23,7 +23,7 @@ using namespace ptx;
 // row indices.  Work per thread is constant whatever the row-length distribution is.
 template <int STAGES>
 __global__ void __launch_bounds__(kCooThreads)
-coo_segmented_kernel(int64_t n, int64_t ntiles, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
+coo_segmented_kernel(int64_t n, int64_t ntiles, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
                      const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y)
 {
     constexpr int T = kCooThreads, TILE = kCooTile, ITEMS = kCooItems;
@@ -58,7 +58,7 @@ coo_segmented_kernel(int64_t n, int64_t ntiles, const int32_t * __restrict__ row
             if (t < ntiles) issue(s, t);
         }
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     int64_t it = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -112,13 +112,13 @@ coo_segmented_kernel(int64_t n, int64_t ntiles, const int32_t * __restrict__ row
 // Entries in file order: one fp64 reduction per entry, two entries per thread and iteration
 // (64/128-bit loads; the arrays are padded so the vector loads stay in bounds).
 __global__ void __launch_bounds__(256)
-coo_atomic_kernel(int64_t n, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
+coo_atomic_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
                   const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
     const uint64_t pol = policy_evict_first();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; k < n; k += stride) {
         const int2 r = ldg_stream_i2(row + k, pol);
         const int2 c = ldg_stream_i2(col + k, pol);
@@ -143,7 +143,7 @@ static int launch_coo_seg(Matrix * m)
     const int64_t ntiles = (m->coo_n + kCooTile - 1) / kCooTile;
     int64_t grid = std::min<int64_t>(ntiles, (int64_t)m->sm_count * ctas);
     if (grid < 1) return 0;
-    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, kCooThreads, smem, m->stream, m->opt_pdl != 0, m->coo_n, ntiles,
+    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, kCooThreads, smem, m->stream, m->opt_pdl != 0, m->coo_n, ntiles, (int)(m->opt_independent != 0),
                             (const int32_t *)m->coo_row, (const int32_t *)m->coo_col, (const double *)m->coo_val,
                             (const double *)m->x, m->y));
     count_launch();
@@ -157,7 +157,7 @@ int launch_coo(Matrix * m)
         m->kernel_name = "coo_atomic_kernel";
         const int64_t pairs = (m->coo_n + 1) / 2;
         int64_t grid = std::min<int64_t>((pairs + 255) / 256, (int64_t)m->sm_count * 8 * 4);
-        SPMV_CUDA(launch_kernel(coo_atomic_kernel, (unsigned)grid, 256u, 0, m->stream, m->opt_pdl != 0, m->coo_n,
+        SPMV_CUDA(launch_kernel(coo_atomic_kernel, (unsigned)grid, 256u, 0, m->stream, m->opt_pdl != 0, m->coo_n, (int)(m->opt_independent != 0),
                                 (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
                                 (const double *)m->coo_val, (const double *)m->x, m->y));
         count_launch();

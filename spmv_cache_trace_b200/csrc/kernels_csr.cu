@@ -86,7 +86,7 @@ constexpr size_t csr_smem_bytes()
 // G > 0: direct mode with G lanes per row.  G == 0: product mode.
 template <typename OffT, int THREADS, int TILE, int STAGES, int G>
 __global__ void __launch_bounds__(THREADS)
-csr_stream_kernel(int64_t stored, int64_t chunk, int tpc, const OffT * __restrict__ rp,
+csr_stream_kernel(int64_t stored, int64_t chunk, int tpc, int independent, const OffT * __restrict__ rp,
                   const int32_t * __restrict__ col, const double * __restrict__ val,
                   const int2 * __restrict__ table, const double * __restrict__ x, double * __restrict__ y)
 {
@@ -147,7 +147,7 @@ csr_stream_kernel(int64_t stored, int64_t chunk, int tpc, const OffT * __restric
     }
 
     // Everything above reads only the immutable matrix; x and y may come from the previous launch.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     for (int i = 0; i < ntiles; ++i) {
         const int s = i % STAGES;
@@ -339,7 +339,7 @@ static int launch_csr_variant(Matrix * m)
     int64_t grid = std::min<int64_t>((int64_t)m->sm_count * ctas, std::max<int64_t>(1, (m->stored + 15) / 16));
     if (!m->tile_row || m->csr_tile != TILE || m->csr_grid != (int)grid) SPMV_TRY(csr_build_table<OffT>(m, TILE, (int)grid));
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, THREADS, smem, m->stream, m->opt_pdl != 0, m->stored, m->csr_chunk,
-                            m->csr_tpc, (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
+                            m->csr_tpc, (int)(m->opt_independent != 0), (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
                             (const int2 *)m->tile_row, (const double *)m->x, m->y));
     count_launch();
     return 0;

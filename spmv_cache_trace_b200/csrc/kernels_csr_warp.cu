@@ -54,7 +54,7 @@ __global__ void csr_span_rows_kernel(int64_t rows, int64_t nspans, int64_t span,
 
 template <typename OffT, int G, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-csr_warp_kernel(int64_t stored, int64_t nspans, const OffT * __restrict__ rp, const int32_t * __restrict__ col,
+csr_warp_kernel(int64_t stored, int64_t nspans, int independent, const OffT * __restrict__ rp, const int32_t * __restrict__ col,
                 const double * __restrict__ val, const int32_t * __restrict__ span_row,
                 const double * __restrict__ x, double * __restrict__ y)
 {
@@ -104,7 +104,7 @@ csr_warp_kernel(int64_t stored, int64_t nspans, const OffT * __restrict__ rp, co
     __syncwarp();
 
     // The matrix is immutable; x and y may have been written by the previous launch.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // 4. row pass
     for (int rw = r0; rw <= r1; rw += RPW) {  // warp-uniform
@@ -175,7 +175,7 @@ static int launch_warp_variant(Matrix * m)
     const int64_t nspans = (m->stored + kWarpSpan - 1) / kWarpSpan;
     const unsigned grid = (unsigned)((nspans + WARPS - 1) / WARPS);
     SPMV_CUDA(launch_kernel(csr_warp_kernel<OffT, G, WARPS>, grid, WARPS * 32u, 0, m->stream, m->opt_pdl != 0, m->stored,
-                            nspans, (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
+                            nspans, (int)(m->opt_independent != 0), (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
                             (const int32_t *)m->span_row, (const double *)m->x, m->y));
     count_launch();
     return 0;

@@ -54,12 +54,30 @@ struct EllLoad<4> {
 // so all of a thread's matrix loads are issued before the first gather returns.
 template <int R, int W_STATIC, bool SKIP>
 __global__ void __launch_bounds__(256)
-ell_kernel(int64_t rows, int64_t pitch, int w_runtime, const int32_t * __restrict__ col,
-           const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y)
+ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int independent, const int32_t * __restrict__ col,
+           const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y,
+           const double * __restrict__ y_in_host, double * __restrict__ y_out_host)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * R;
+    // rows [row0, rows) of the matrix (row0 a multiple of 4: the vector loads stay aligned)
+    const int64_t i0 = row0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * R;
     if (i0 >= rows) return;
+    // Zero-copy form (spmvb200_spmv_host with pinned buffers): y_old is read from and y_new written
+    // to mapped HOST memory by this kernel, so the two PCIe directions run at the same time.
+    // (y_in_host may also point at device memory: the chunked path uploads y with the copy engine.)
+    double yo[R];
+    const bool whole = i0 + R <= rows;  // vector access keeps PCIe transactions full-width
+    if (y_in_host && whole && R == 2) {
+        const double2 t = __ldcs(reinterpret_cast<const double2 *>(y_in_host + i0));
+        yo[0] = t.x; yo[R - 1] = t.y;
+    } else if (y_in_host && whole && R == 4) {
+        const double2 t = __ldcs(reinterpret_cast<const double2 *>(y_in_host + i0));
+        const double2 u = __ldcs(reinterpret_cast<const double2 *>(y_in_host + i0 + 2));
+        yo[0] = t.x; yo[1 % R] = t.y; yo[2 % R] = u.x; yo[3 % R] = u.y;
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) yo[r] = (y_in_host && i0 + r < rows) ? __ldcs(y_in_host + i0 + r) : 0.0;
+    }
     const int W = W_STATIC > 0 ? W_STATIC : w_runtime;
     const uint64_t pol = policy_evict_first();
     double z[R];
@@ -76,7 +94,7 @@ ell_kernel(int64_t rows, int64_t pitch, int w_runtime, const int32_t * __restric
             EllLoad<R>::vals(val + (int64_t)l * pitch + i0, a[l], pol);
         }
         // The matrix is immutable; x and y may have been written by the previous launch.
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
         double xv[W_STATIC > 0 ? W_STATIC : 1][R];
 #pragma unroll
         for (int l = 0; l < W_STATIC; ++l)
@@ -91,7 +109,7 @@ ell_kernel(int64_t rows, int64_t pitch, int w_runtime, const int32_t * __restric
             for (int r = 0; r < R; ++r)
                 if (!SKIP || c[l][r] != INT_MAX) z[r] = __dadd_rn(z[r], __dmul_rn(a[l][r], xv[l][r]));
     } else {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll 4
         for (int l = 0; l < W; ++l) {
             int c[R];
@@ -105,6 +123,21 @@ ell_kernel(int64_t rows, int64_t pitch, int w_runtime, const int32_t * __restric
             }
         }
     }
+    if (y_out_host) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[r] = __dadd_rn(yo[r], z[r]);
+        if (whole && R == 2) {
+            __stcs(reinterpret_cast<double2 *>(y_out_host + i0), make_double2(z[0], z[R - 1]));
+        } else if (whole && R == 4) {
+            __stcs(reinterpret_cast<double2 *>(y_out_host + i0), make_double2(z[0], z[1 % R]));
+            __stcs(reinterpret_cast<double2 *>(y_out_host + i0 + 2), make_double2(z[2 % R], z[3 % R]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (i0 + r < rows) __stcs(y_out_host + i0 + r, z[r]);
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r)
         if (i0 + r < rows) red_add_f64(y + i0 + r, z[r]);
@@ -113,23 +146,28 @@ ell_kernel(int64_t rows, int64_t pitch, int w_runtime, const int32_t * __restric
 template <int R, bool SKIP>
 static int launch_ell_rw(Matrix * m, int block)
 {
-    const int64_t threads = (m->rows + R - 1) / R;
+    // optional row range (the pipelined host-buffer path runs the matrix in row chunks)
+    const int64_t row0 = m->range_end > 0 ? m->range_begin : 0;
+    const int64_t row1 = m->range_end > 0 ? m->range_end : m->rows;
+    const int64_t threads = (row1 - row0 + R - 1) / R;
     const unsigned grid = (unsigned)((threads + block - 1) / block);
     const int w = (int)m->ell_w;
     const bool pdl = m->opt_pdl != 0;
+    const int indep = m->opt_independent != 0;
     cudaError_t e;
 #define SPMV_ELL_CASE(WS)                                                                                      \
     case WS:                                                                                                   \
-        e = launch_kernel(ell_kernel<R, WS, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, m->rows,          \
-                          m->ell_pitch, w, (const int32_t *)m->ell_col, (const double *)m->ell_val,            \
-                          (const double *)m->x, m->y);                                                         \
+        e = launch_kernel(ell_kernel<R, WS, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, row0, row1,    \
+                          m->ell_pitch, w, indep, (const int32_t *)m->ell_col, (const double *)m->ell_val,            \
+                          (const double *)m->x, m->y, (const double *)m->host_y_in, m->host_y_out);              \
         break;
     switch (w) {
         SPMV_ELL_CASE(1) SPMV_ELL_CASE(2) SPMV_ELL_CASE(3) SPMV_ELL_CASE(4) SPMV_ELL_CASE(5)
         SPMV_ELL_CASE(6) SPMV_ELL_CASE(7) SPMV_ELL_CASE(8) SPMV_ELL_CASE(9)
     default:
-        e = launch_kernel(ell_kernel<R, 0, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, m->rows, m->ell_pitch, w,
-                          (const int32_t *)m->ell_col, (const double *)m->ell_val, (const double *)m->x, m->y);
+        e = launch_kernel(ell_kernel<R, 0, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, row0, row1, m->ell_pitch, w, indep,
+                          (const int32_t *)m->ell_col, (const double *)m->ell_val, (const double *)m->x, m->y,
+                          (const double *)m->host_y_in, m->host_y_out);
     }
 #undef SPMV_ELL_CASE
     SPMV_CUDA(e);

@@ -234,6 +234,13 @@ def test_run_accumulates_like_the_reference(oracle, kats):
         for _ in range(3):
             A.spmv()
         assert np.array_equal(A.get_y(), 3 * np.array(k["y"])), fmt
+        # x constant, y accumulated with commutative reductions: consecutive launches may be declared
+        # independent (they then overlap at their boundaries) without changing the result
+        A.set_option("independent_launches", 1)
+        A.fill_y(0.0)
+        for _ in range(5):
+            A.spmv()
+        assert np.array_equal(A.get_y(), 5 * np.array(k["y"])), fmt
 
 
 def test_init_vectors_are_one_and_zero(kats):
