@@ -258,8 +258,20 @@ int spmvb200_time_rotating(const spmvb200_matrix_t *ms, int n, int warmup, int s
  * D2H y, synchronise), k round-robin; total_ms = CUDA-event time around all `steps` steps. */
 int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double *const *xs,
                                 double *const *ys, int warmup, int steps, float *total_ms);
-/* Tuning: "csr.tile" (1024|2048|4096), "csr.stages", "csr.ctas_per_sm", "ell.rows_per_thread"
- * (1|2|4), "ell.block", "coo.stages", "coo.ctas_per_sm", "beta0" (1: y = A*x).  0 = automatic. */
+/* Options (0 = automatic unless noted):
+ *   semantics   "beta0" 1: y = A*x instead of y += A*x.
+ *               "independent_launches" 1: the caller promises that the previous kernel in the stream
+ *               does not write this matrix's x (true for the reference protocol: x constant, y
+ *               accumulated); launches then skip griddepcontrol.wait and overlap at their boundaries.
+ *               "pdl" (default 1): programmatic dependent launch on/off.
+ *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular; "csr.lanes" 1|2|4|8
+ *               lanes per row; "csr.threads" 128|256; "csr.tile" 512|1024|2048; "csr.stages" 2|3;
+ *               "csr.ctas_per_sm"; "csr.spare_ctas" CTA slots per SM left free for a concurrent kernel.
+ *   ELL         "ell.rows_per_thread" 1|2|4, "ell.block" 32..256.
+ *   COO         "coo.threads" 64|128|256, "coo.stages" 2|3|4, "coo.ctas_per_sm".
+ *   host path   "host.zero_copy" (default 1; ELL): spmvb200_spmv_host lets the kernel read and write
+ *               pinned host y directly; 2 = y up by DMA in "host.chunks" row chunks, results stored by
+ *               the kernel; 0 = copies only ("host.chunks" > 1 pipelines them). */
 int spmvb200_set_option(spmvb200_matrix_t m, const char *key, int64_t value);
 int spmvb200_get_option(spmvb200_matrix_t m, const char *key, int64_t *value);
 /* Name of the kernel spmvb200_spmv launches for this matrix. */

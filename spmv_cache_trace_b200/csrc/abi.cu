@@ -952,6 +952,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;
     if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;
+    if (!strcmp(key, "coo.threads")) return &m->opt_coo_threads;
     if (!strcmp(key, "coo.ctas_per_sm")) return &m->opt_coo_ctas;
     if (!strcmp(key, "beta0")) return &m->opt_beta0;
     if (!strcmp(key, "host.chunks")) return &m->opt_host_chunks;

@@ -118,6 +118,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto
+    int64_t opt_coo_threads = 0;  // threads per CTA of the segmented kernel (64, 128, 256), 0 = auto
     int64_t opt_coo_stages = 0;
     int64_t opt_coo_ctas = 0;
     int64_t opt_host_zero_copy = 1;  // spmvb200_spmv_host: let the ELL kernel read/write pinned host y directly

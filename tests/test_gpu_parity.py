@@ -348,6 +348,10 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
         B = build(fmt, mm, **kw)
         y = B * x + y0
         assert_within(y, yref, bound + np.abs(yref), fmt)
+        for threads, stages in ((64, 2), (128, 3), (256, 4), (0, 0)):
+            B.set_option("coo.threads", threads)
+            B.set_option("coo.stages", stages)
+            assert_within(B * x + y0, yref, bound + np.abs(yref), f"{fmt} coo.threads={threads} coo.stages={stages}")
     H = hybrid_matrix.from_matrix_market(mm)
     OH = oracle.hyb(rows, cols, i, j, a)
     eh = H.export()
