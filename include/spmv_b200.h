@@ -265,7 +265,7 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               accumulated); launches then skip griddepcontrol.wait and overlap at their boundaries.
  *               "pdl" (default 1): programmatic dependent launch on/off.
  *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular; "csr.lanes" 1|2|4|8
- *               lanes per row; "csr.threads" 128|256; "csr.tile" 512|1024|2048; "csr.stages" 2|3;
+ *               lanes per row; "csr.threads" 32|64|128|256; "csr.tile" 256..2048; "csr.stages" 2|3;
  *               "csr.ctas_per_sm"; "csr.spare_ctas" CTA slots per SM left free for a concurrent kernel.
  *   ELL         "ell.rows_per_thread" 1|2|4, "ell.block" 32..256.
  *   COO         "coo.threads" 64|128|256, "coo.stages" 2|3|4, "coo.ctas_per_sm".

@@ -280,8 +280,7 @@ static CsrConfig csr_config(const Matrix * m)
     if (m->opt_csr_lanes) lanes = (int)m->opt_csr_lanes;
     c.lanes = lanes;
     // defaults from the sweeps in profiles/: short rows like 256-thread CTAs, shared rows 128
-    c.threads = (int)(m->opt_csr_threads == 128 || m->opt_csr_threads == 256 ? m->opt_csr_threads
-                                                                             : (lanes >= 2 ? 128 : 256));
+    c.threads = (int)(m->opt_csr_threads ? m->opt_csr_threads : (lanes >= 2 ? 128 : 256));
     c.tile = (int)(m->opt_csr_tile ? m->opt_csr_tile : (lanes == 0 ? 2048 : 1024));
     c.stages = (int)(m->opt_csr_stages ? m->opt_csr_stages : 2);
     return c;
@@ -371,7 +370,13 @@ static int launch_csr_stages(Matrix * m, const CsrConfig & c)
 template <typename OffT>
 static int launch_csr_t(Matrix * m, const CsrConfig & c)
 {
-    if (c.threads == 128) {
+    if (c.threads == 32) {
+        if (c.tile == 256) return launch_csr_stages<OffT, 32, 256>(m, c);
+        if (c.tile == 512) return launch_csr_stages<OffT, 32, 512>(m, c);
+    } else if (c.threads == 64) {
+        if (c.tile == 256) return launch_csr_stages<OffT, 64, 256>(m, c);
+        if (c.tile == 512) return launch_csr_stages<OffT, 64, 512>(m, c);
+    } else if (c.threads == 128) {
         if (c.tile == 512) return launch_csr_stages<OffT, 128, 512>(m, c);
         if (c.tile == 1024) return launch_csr_stages<OffT, 128, 1024>(m, c);
     } else if (c.threads == 256) {
