@@ -193,16 +193,18 @@ def measure_device(sp, name, steps, warmup, l2_bytes, peak, per_launch=True, max
         res["kernel_ms_mean"] = float(np.mean(per))
         res["kernel_ms_median"] = float(np.median(per))
         res["kernel_ms_min"] = float(np.min(per))
-    res["independent_launches"] = measure_independent(sp, mats, steps, warmup, B, peak)
+    res["ordered_launches"] = measure_ordered(sp, mats, steps, warmup, B, peak)
     return res, mats
 
 
-def measure_independent(sp, mats, steps, warmup, B, peak):
-    """The same K launches declared independent of each other ("independent_launches": the kernels skip
-    griddepcontrol.wait, so the drain of one launch overlaps the ramp of the next).  Valid here because
-    consecutive launches touch different copies; reported next to, never instead of, the ordered number."""
+def measure_ordered(sp, mats, steps, warmup, B, peak):
+    """The same K launches with full ordering forced ("independent_launches" = -1: every kernel executes
+    griddepcontrol.wait before it touches x or y).  By default the library orders two launches only when
+    one writes what the other reads (it tracks the x/y ranges in flight on its own streams); in the
+    reference protocol -- x constant, y accumulated with reductions -- that is never the case, so the
+    drain of one launch overlaps the ramp of the next.  Reported next to the default for comparison."""
     for m in mats:
-        m.set_option("independent_launches", 1)
+        m.set_option("independent_launches", -1)
     try:
         total_ms, _ = sp.time_rotating(mats, steps, warmup, False)
     finally:
@@ -316,7 +318,7 @@ def run_single_gpu(args):
     gpu_launches = sp.launch_count() - launches0
     _, per = sp.time_rotating(mats, args.steps, 0, True)  # same K steps again, one event pair per launch
     per = per if per is not None else np.array([total_ms / args.steps])
-    independent = measure_independent(sp, mats, args.steps, 3, B, peak)
+    ordered = measure_ordered(sp, mats, args.steps, 3, B, peak)
     t_step = total_ms * 1e-3 / args.steps
     value = B / t_step / 1e9
     k_ms = float(np.mean(per))
@@ -357,7 +359,7 @@ def run_single_gpu(args):
                 "call": "spmvb200_spmv_host (pinned host x, y -> device, kernel, y -> host)", "max_abs_y": ycheck},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
-        "independent_launches": independent,
+        "ordered_launches": ordered,
     }
     del xs, ys, mats, A
 

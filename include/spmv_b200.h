@@ -260,15 +260,23 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
                                 double *const *ys, int warmup, int steps, float *total_ms);
 /* Options (0 = automatic unless noted):
  *   semantics   "beta0" 1: y = A*x instead of y += A*x.
- *               "independent_launches" 1: the caller promises that the previous kernel in the stream
- *               does not write this matrix's x (true for the reference protocol: x constant, y
- *               accumulated); launches then skip griddepcontrol.wait and overlap at their boundaries.
+ *               "independent_launches": y is updated with reductions, so two launches need ordering only
+ *               when one writes what the other reads.  On the stream a matrix owns the library tracks
+ *               the x/y ranges of the kernels in flight and lets a launch start while the previous one
+ *               drains whenever that is provably safe (the reference protocol: x constant, y
+ *               accumulated); any other call on the matrix, overlapping ranges or "beta0" restore full
+ *               ordering.  On a caller-provided stream (spmvb200_set_stream) nothing is assumed unless
+ *               this option is 1 = the caller promises that no kernel in flight writes this matrix's x.
+ *               -1 = never overlap.
  *               "pdl" (default 1): programmatic dependent launch on/off.
  *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular; "csr.lanes" 1|2|4|8
  *               lanes per row; "csr.threads" 32|64|128|256; "csr.tile" 256..2048; "csr.stages" 2|3;
  *               "csr.ctas_per_sm"; "csr.spare_ctas" CTA slots per SM left free for a concurrent kernel.
  *   ELL         "ell.rows_per_thread" 1|2|4, "ell.block" 32..256.
- *   COO         "coo.threads" 64|128|256, "coo.stages" 2|3|4, "coo.ctas_per_sm".
+ *   COO         "coo.algo" 1 shared-memory staged tiles (sorted entries), 2 register-staged, 4 entries per
+ *               lane, one segmented warp scan per 128 entries (default, any entry order), 3 one reduction
+ *               per entry, 4 register-staged, striped lanes; "coo.items" 2|4|8 stripes per warp (algo 4);
+ *               "coo.threads" 64|128|256; "coo.stages" 2|3|4 and "coo.ctas_per_sm" (algo 1).
  *   host path   "host.zero_copy" (default 1; ELL): spmvb200_spmv_host lets the kernel read and write
  *               pinned host y directly; 2 = y up by DMA in "host.chunks" row chunks, results stored by
  *               the kernel; 0 = copies only ("host.chunks" > 1 pipelines them). */

@@ -9,6 +9,8 @@
 #include <atomic>
 #include <climits>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace spmvb200 {
@@ -180,7 +182,96 @@ static int finish(Guard & g, spmvb200_matrix_t * out)
     return 0;
 }
 
+// ---- what is in flight on the streams the library owns ---------------------------------------------------------
+// The SpMV kernels read the immutable matrix, gather x and add to y with reductions (RED), which commute.
+// Two consecutive launches therefore only need to be ordered when one writes what the other reads.
+// For streams created by the library (nothing else can enqueue work on them) the library knows every
+// kernel in flight: the record below keeps the bounding address ranges written (y) and read (x) by the
+// SpMV kernels launched since the last fully ordered point.  A launch whose x is not written and whose
+// y is not read by anything in flight skips griddepcontrol.wait, so its CTAs start while the previous
+// kernel drains (the reference protocol -- x constant, y accumulated, profile-kernel.cpp:159-161 --
+// is exactly this case).  Any other API call on the matrix invalidates the record; a launch that must
+// be ordered behind kernels that did not wait is issued without the PDL attribute, i.e. with ordinary
+// stream serialisation behind all of them.  User-provided streams (spmvb200_set_stream) are never
+// tracked: foreign work may precede the launch, so it always waits.
+struct StreamRec {
+    bool valid = false;  // everything enqueued since the last ordered point is an SpMV launch recorded here
+    uintptr_t wlo = 0, whi = 0, rlo = 0, rhi = 0;
+    int chain = 0;       // launches since the last ordered point that skipped griddepcontrol.wait
+};
+static std::mutex g_stream_mu;
+static std::unordered_map<cudaStream_t, StreamRec> g_streams;
+
+void stream_register(cudaStream_t s)
+{
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    g_streams[s] = StreamRec{};
+}
+void stream_forget(cudaStream_t s)
+{
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    g_streams.erase(s);
+}
+void stream_invalidate(cudaStream_t s)
+{
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    auto it = g_streams.find(s);
+    if (it != g_streams.end()) it->second.valid = false;
+}
+void stream_synced(cudaStream_t s)
+{
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    auto it = g_streams.find(s);
+    if (it != g_streams.end()) {
+        it->second = StreamRec{};
+        it->second.valid = true;
+    }
+}
+
+static inline bool overlaps(uintptr_t a0, uintptr_t a1, uintptr_t b0, uintptr_t b1) { return a0 < b1 && b0 < a1; }
+
+// Decide how the next kernel of `m` is launched (run_pdl, run_independent) and record it.
+void plan_run(Matrix * m, bool conservative)
+{
+    m->run_pdl = m->opt_pdl != 0;
+    m->run_independent = false;
+    const uintptr_t x0 = (uintptr_t)m->x, x1 = x0 + 8u * (uintptr_t)m->cols;
+    const uintptr_t y0 = (uintptr_t)m->y, y1 = y0 + 8u * (uintptr_t)m->rows;
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    auto it = g_streams.find(m->stream);
+    if (it == g_streams.end()) {  // not a library stream: the caller's promise is all there is
+        m->run_independent = m->opt_independent > 0 && !conservative;
+        return;
+    }
+    StreamRec & r = it->second;
+    const bool proven = r.valid && !overlaps(x0, x1, r.wlo, r.whi) && !overlaps(y0, y1, r.rlo, r.rhi);
+    if (!conservative && m->run_pdl && !m->opt_beta0 && (m->opt_independent > 0 || (m->opt_independent == 0 && proven))) {
+        m->run_independent = true;  // validity of the record is unchanged; its ranges grow
+        r.wlo = r.whi > r.wlo ? std::min(r.wlo, y0) : y0;
+        r.whi = std::max(r.whi, y1);
+        r.rlo = r.rhi > r.rlo ? std::min(r.rlo, x0) : x0;
+        r.rhi = std::max(r.rhi, x1);
+        r.chain++;
+        return;
+    }
+    // ordered launch: behind un-waited kernels only ordinary stream serialisation is transitive
+    if (r.chain > 0) m->run_pdl = false;
+    r = StreamRec{};
+    r.valid = !conservative;
+    r.wlo = y0; r.whi = y1; r.rlo = x0; r.rhi = x1;
+}
+
+// Entry check of every API call that is not an SpMV launch: whatever it enqueues is unknown to the record.
 static int check(spmvb200_matrix_t m)
+{
+    if (!m) return fail(SPMVB200_ERR_INVALID, "null matrix handle");
+    cudaError_t e = cudaSetDevice(m->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    stream_invalidate(m->stream);
+    return 0;
+}
+// Entry check of the launch paths.
+static int check_run(spmvb200_matrix_t m)
 {
     if (!m) return fail(SPMVB200_ERR_INVALID, "null matrix handle");
     cudaError_t e = cudaSetDevice(m->device);
@@ -714,7 +805,10 @@ int spmvb200_set_stream(spmvb200_matrix_t m, void * stream)
 {
     SPMV_TRY(check(m));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
-    if (m->own_stream) cudaStreamDestroy(m->stream);
+    if (m->own_stream) {
+        stream_forget(m->stream);
+        cudaStreamDestroy(m->stream);
+    }
     m->stream = (cudaStream_t)stream; m->own_stream = false;
     return 0;
 }
@@ -735,15 +829,18 @@ int spmvb200_host_free(void * p)
 static int launch(Matrix * m)
 {
     if (m->opt_beta0) SPMV_CUDA(cudaMemsetAsync(m->y, 0, sizeof(double) * (size_t)m->rows, m->stream));
+    plan_run(m, false);
     switch (m->format) {
     case SPMVB200_CSR: return launch_csr(m);
     case SPMVB200_ELL: return launch_ell(m, true);
     case SPMVB200_COO: return launch_coo(m);
     case SPMVB200_HYB:
-        // ELL pass, then the COO tail adds into the same y (hybrid-matrix.cpp:547-566)
+        // ELL pass, then the COO tail adds into the same y (hybrid-matrix.cpp:547-566); both only
+        // add to y, so the second kernel need not wait for the first
         SPMV_TRY(launch_ell(m, true));
+        if (m->coo_n > 0) plan_run(m, false);
         SPMV_TRY(launch_coo(m));
-        m->kernel_name = "ell_kernel+coo_segmented_kernel";
+        m->kernel_name = m->opt_coo_algo == 1 ? "ell_kernel+coo_segmented_kernel" : m->opt_coo_algo == 4 ? "ell_kernel+coo_warp_kernel" : "ell_kernel+coo_warp4_kernel";
         return 0;
     }
     return fail(SPMVB200_ERR_INVALID, "unknown format");
@@ -751,7 +848,7 @@ static int launch(Matrix * m)
 
 int spmvb200_spmv(spmvb200_matrix_t m)
 {
-    SPMV_TRY(check(m));
+    SPMV_TRY(check_run(m));
     return launch(m);
 }
 
@@ -759,6 +856,7 @@ int spmvb200_sync(spmvb200_matrix_t m)
 {
     SPMV_TRY(check(m));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    stream_synced(m->stream);
     return 0;
 }
 
@@ -801,6 +899,7 @@ static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chu
             m->host_y_in = m->y;
             m->host_y_out = y_dev_visible;
         }
+        plan_run(m, true);
         rc = launch_ell(m, true);
         m->host_y_in = nullptr;
         m->host_y_out = nullptr;
@@ -812,6 +911,7 @@ static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chu
     m->opt_beta0 = keep_beta0;
     if (rc) return rc;
     SPMV_CUDA(cudaStreamSynchronize(s));
+    stream_synced(s);
     return 0;
 }
 
@@ -833,12 +933,14 @@ int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
             m->host_y_out = (double *)ay.devicePointer;
             const int64_t keep = m->opt_beta0;
             m->opt_beta0 = 0;
+            plan_run(m, true);
             const int rc = launch_ell(m, true);
             m->opt_beta0 = keep;
             m->host_y_in = nullptr;
             m->host_y_out = nullptr;
             if (rc) return rc;
             SPMV_CUDA(cudaStreamSynchronize(s));
+            stream_synced(s);
             return 0;
         }
         cudaGetLastError();  // not a registered host pointer: fall through to the copying paths
@@ -850,6 +952,7 @@ int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
     SPMV_TRY(launch(m));
     SPMV_CUDA(cudaMemcpyAsync(y, m->y, sizeof(double) * (size_t)m->rows, cudaMemcpyDeviceToHost, s));
     SPMV_CUDA(cudaStreamSynchronize(s));
+    stream_synced(s);
     return 0;
 }
 
@@ -905,6 +1008,7 @@ int spmvb200_time_rotating(const spmvb200_matrix_t * ms, int n, int warmup, int 
         return 0;
     };
     rc = run();
+    if (rc == 0) stream_synced(s);
     for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
     return rc;
 }
@@ -954,6 +1058,8 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;
     if (!strcmp(key, "coo.threads")) return &m->opt_coo_threads;
     if (!strcmp(key, "coo.ctas_per_sm")) return &m->opt_coo_ctas;
+    if (!strcmp(key, "coo.algo")) return &m->opt_coo_algo;
+    if (!strcmp(key, "coo.items")) return &m->opt_coo_items;
     if (!strcmp(key, "beta0")) return &m->opt_beta0;
     if (!strcmp(key, "host.chunks")) return &m->opt_host_chunks;
     if (!strcmp(key, "host.zero_copy")) return &m->opt_host_zero_copy;

@@ -55,6 +55,7 @@ int matrix_new(Matrix ** out)
     e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     m->own_stream = true;
+    stream_register(m->stream);
     cudaEventCreate(&m->ev0);
     cudaEventCreate(&m->ev1);
     *out = m;
@@ -87,7 +88,10 @@ void matrix_free(Matrix * m)
     for (auto & e : m->ev_chunk) if (e) cudaEventDestroy(e);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
-    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    if (m->own_stream && m->stream) {
+        stream_forget(m->stream);
+        cudaStreamDestroy(m->stream);
+    }
     delete m;
 }
 

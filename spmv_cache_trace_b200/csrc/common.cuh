@@ -121,9 +121,15 @@ struct spmvb200_matrix_s {
     int64_t opt_coo_threads = 0;  // threads per CTA of the segmented kernel (64, 128, 256), 0 = auto
     int64_t opt_coo_stages = 0;
     int64_t opt_coo_ctas = 0;
+    int64_t opt_coo_algo = 0;     // 0 auto, 1 shared-memory staged (coo_segmented_kernel), 2 register-staged (coo_warp_kernel)
+    int64_t opt_coo_items = 0;    // stripes of 32 entries per warp of coo_warp_kernel (2, 4, 8), 0 = auto
     int64_t opt_host_zero_copy = 1;  // spmvb200_spmv_host: let the ELL kernel read/write pinned host y directly
     int64_t opt_host_chunks = 0;  // row chunks of the pipelined spmvb200_spmv_host (ELL), 0 = 8, 1 = off
     int64_t opt_beta0 = 0;        // 1: y = A*x (y is cleared first) instead of y += A*x
+    // per-launch decisions of plan_run() (abi.cu): launch attribute and whether the kernel may skip
+    // griddepcontrol.wait because nothing in flight on its stream writes its x or reads its y
+    bool run_pdl = true, run_independent = false;
+    bool aux_dirty = false;       // an auxiliary table was just (re)built on the stream: serialise the next launch
     const char * kernel_name = "";
 };
 
@@ -181,6 +187,26 @@ inline unsigned grid_for(int64_t n, int sm = 148)
 }
 
 int fill_device(double * p, int64_t n, double v, cudaStream_t s);
+
+// ---- in-flight tracking of library-owned streams (abi.cu) -----------------------------------
+void stream_register(cudaStream_t s);    // a stream created by the library
+void stream_forget(cudaStream_t s);
+void stream_invalidate(cudaStream_t s);  // something other than an SpMV launch was enqueued
+void stream_synced(cudaStream_t s);      // the stream was synchronised: nothing is in flight
+void plan_run(Matrix * m, bool conservative);
+
+// What the launchers pass on: {launch with the PDL attribute, kernel may skip griddepcontrol.wait}.
+// A launch that follows the (re)build of an auxiliary table on the same stream is fully serialised.
+struct RunMode {
+    bool pdl;
+    int independent;
+};
+inline RunMode run_mode(Matrix * m)
+{
+    RunMode r{m->run_pdl && !m->aux_dirty, (m->run_independent && !m->aux_dirty) ? 1 : 0};
+    m->aux_dirty = false;
+    return r;
+}
 
 // ---- launchers implemented in kernels.cu ---------------------------------------------------
 int launch_csr(Matrix * m);

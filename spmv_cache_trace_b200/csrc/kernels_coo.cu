@@ -111,6 +111,121 @@ coo_segmented_kernel(int64_t n, int64_t chunk, int independent, const int32_t * 
     }
 }
 
+// Row-sorted entries, register-staged: no shared memory, no CTA barrier.  A warp owns 32*U consecutive
+// entries; lane l loads entries l, l+32, ... (three coalesced streaming loads per stripe), so all 3*U
+// matrix loads and then all U gathers of x are in flight at once, and with nothing but registers in
+// use 48-64 warps are resident per SM.  This is what a gather-latency-bound matrix (power law: the
+// x-gathers miss L1 and half of them miss L2) needs: the staged kernel above keeps at most
+// 3 CTAs x 256 threads resident and alternates load, gather and reduce phases behind CTA barriers.
+// Each 32-entry stripe is reduced by a segmented warp scan keyed on the runs of equal row index
+// (Kogge-Stone with shuffles, cut short at the longest run of the stripe); the last lane of every
+// run adds its total to y with one fp64 reduction.  Correct for any entry order; efficient when equal
+// rows are adjacent.
+template <int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+coo_warp_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
+                const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int lane = threadIdx.x & 31;
+    const int64_t k0 = ((int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * (32 * U) + lane;
+    if (k0 - lane >= n) return;
+    const uint64_t pol = policy_evict_first();
+    int r[U], c[U];
+    double a[U];
+    // the arrays are padded with zeroed entries far beyond n: whole stripes can be loaded unguarded
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        r[u] = ldg_stream_i1(row + k0 + 32 * u, pol);
+        c[u] = ldg_stream_i1(col + k0 + 32 * u, pol);
+        a[u] = ldg_stream_d1(val + k0 + 32 * u, pol);
+    }
+    if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldg(x + c[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int rr = (k0 + 32 * u < n) ? r[u] : -1;
+        double s = __dmul_rn(a[u], v[u]);
+        const int rp = __shfl_up_sync(0xffffffffu, rr, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || rr != rp);
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // first lane of my run
+        const int dist = lane - start;
+        const int longest = __reduce_max_sync(0xffffffffu, dist);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            if (d <= longest) {  // warp-uniform
+                const double t = __shfl_up_sync(0xffffffffu, s, d);
+                if (dist >= d) s = __dadd_rn(s, t);
+            }
+        }
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (tail && rr >= 0) red_add_f64(y + rr, s);
+    }
+}
+
+// The same idea with a BLOCKED assignment: lane l owns the 4 consecutive entries 4l..4l+3 of the warp's
+// 128, fetched with one 128-bit load each for the row and column indices and one 256-bit load for
+// the values (3 load instructions instead of 12).  The lane sums its own runs of equal rows serially;
+// runs that lie strictly inside a lane go to y directly, and only the lane's first and last run take
+// part in ONE segmented scan across the warp per 128 entries (a quarter of the shuffles of the
+// striped kernel, whose l1tex/MIO pipe was 70 % busy with gathers + shuffles; profiles/).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
+                 const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int lane = threadIdx.x & 31;
+    const int64_t kw = ((int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * 128;
+    if (kw >= n) return;
+    const int64_t k0 = kw + 4 * lane;
+    const uint64_t pol = policy_evict_first();
+    const int4 r4 = ldg_stream_i4(row + k0, pol);
+    const int4 c4 = ldg_stream_i4(col + k0, pol);
+    double a[4];
+    ldg_stream_d4(val + k0, a);
+    if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const double x0 = __ldg(x + c4.x), x1 = __ldg(x + c4.y), x2 = __ldg(x + c4.z), x3 = __ldg(x + c4.w);
+    const int r[4] = {k0 < n ? r4.x : -1, k0 + 1 < n ? r4.y : -1, k0 + 2 < n ? r4.z : -1, k0 + 3 < n ? r4.w : -1};
+    const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
+    // runs inside the lane
+    int cur_row = r[0];
+    double cur = p[0], head = 0.0;
+    bool single = true;  // the lane holds one run only
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        if (r[j] == cur_row) {
+            cur = __dadd_rn(cur, p[j]);
+        } else {
+            if (single) { head = cur; single = false; }
+            else if (cur_row >= 0) red_add_f64(y + cur_row, cur);
+            cur_row = r[j];
+            cur = p[j];
+        }
+    }
+    // across lanes: my first run may continue the previous lane's last run
+    const int prev_last = __shfl_up_sync(0xffffffffu, r[3], 1);
+    const int next_first = __shfl_down_sync(0xffffffffu, r[0], 1);
+    const bool cont = lane > 0 && prev_last == r[0];
+    const bool next_cont = lane < 31 && next_first == r[3];
+    const unsigned heads = __ballot_sync(0xffffffffu, !(single && cont));
+    const int dist = lane - (31 - __clz(heads & (0xffffffffu >> (31 - lane))));
+    const int longest = __reduce_max_sync(0xffffffffu, dist);
+    double s = cur;  // sum of the last run, then of the chain of single-run lanes that ends here
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        if (d <= longest) {  // warp-uniform
+            const double t = __shfl_up_sync(0xffffffffu, s, d);
+            if (dist >= d) s = __dadd_rn(s, t);
+        }
+    }
+    const double prev_s = __shfl_up_sync(0xffffffffu, s, 1);
+    if (!single && r[0] >= 0) red_add_f64(y + r[0], cont ? __dadd_rn(prev_s, head) : head);
+    if (!next_cont && r[3] >= 0) red_add_f64(y + r[3], s);
+}
+
 // Entries in file order: one fp64 reduction per entry, two entries per thread and iteration
 // (64/128-bit loads; the arrays are padded so the vector loads stay in bounds).
 __global__ void __launch_bounds__(256)
@@ -144,8 +259,9 @@ static int launch_coo_seg(Matrix * m)
     const int ctas = m->opt_coo_ctas ? (int)std::min<int64_t>(m->opt_coo_ctas, occupancy) : occupancy;
     int64_t grid = std::min<int64_t>((int64_t)m->sm_count * ctas, std::max<int64_t>(1, (m->coo_n + 15) / 16));
     const int64_t chunk = round_up((m->coo_n + grid - 1) / grid, 16);
-    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, (unsigned)THREADS, smem, m->stream, m->opt_pdl != 0, m->coo_n, chunk,
-                            (int)(m->opt_independent != 0), (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
+    const RunMode rm = run_mode(m);
+    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, (unsigned)THREADS, smem, m->stream, rm.pdl, m->coo_n, chunk,
+                            rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
                             (const double *)m->coo_val, (const double *)m->x, m->y));
     count_launch();
     return 0;
@@ -162,18 +278,80 @@ static int launch_coo_stages(Matrix * m, int stages)
     return fail(SPMVB200_ERR_INVALID, "coo.stages must be 2, 3 or 4");
 }
 
+template <int U, int WARPS>
+static int launch_coo_warp_variant(Matrix * m)
+{
+    const int64_t per_cta = (int64_t)WARPS * 32 * U;
+    const int64_t grid = (m->coo_n + per_cta - 1) / per_cta;
+    if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "COO matrix too large for one launch");
+    const RunMode rm = run_mode(m);
+    SPMV_CUDA(launch_kernel(coo_warp_kernel<U, WARPS>, (unsigned)grid, (unsigned)(WARPS * 32), 0, m->stream, rm.pdl, m->coo_n,
+                            rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
+                            (const double *)m->coo_val, (const double *)m->x, m->y));
+    count_launch();
+    return 0;
+}
+
+template <int WARPS>
+static int launch_coo_warp4_variant(Matrix * m)
+{
+    const int64_t per_cta = (int64_t)WARPS * 128;
+    const int64_t grid = (m->coo_n + per_cta - 1) / per_cta;
+    if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "COO matrix too large for one launch");
+    const RunMode rm = run_mode(m);
+    SPMV_CUDA(launch_kernel(coo_warp4_kernel<WARPS>, (unsigned)grid, (unsigned)(WARPS * 32), 0, m->stream, rm.pdl, m->coo_n,
+                            rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
+                            (const double *)m->coo_val, (const double *)m->x, m->y));
+    count_launch();
+    return 0;
+}
+
+static int launch_coo_warp(Matrix * m)
+{
+    const int threads = (int)(m->opt_coo_threads ? m->opt_coo_threads : 128);  // sweep: profiles/r01_sweep_i_coo_warp4.log
+    if (m->opt_coo_algo != 4) {  // blocked lanes
+        if (threads == 64) return launch_coo_warp4_variant<2>(m);
+        if (threads == 128) return launch_coo_warp4_variant<4>(m);
+        if (threads == 256) return launch_coo_warp4_variant<8>(m);
+        return fail(SPMVB200_ERR_INVALID, "coo.threads must be 64, 128 or 256");
+    }
+    const int items = (int)(m->opt_coo_items ? m->opt_coo_items : 4);
+#define SPMV_COO_WARP(U)                                                  \
+    case U:                                                               \
+        if (threads == 64) return launch_coo_warp_variant<U, 2>(m);       \
+        if (threads == 128) return launch_coo_warp_variant<U, 4>(m);      \
+        if (threads == 256) return launch_coo_warp_variant<U, 8>(m);      \
+        break;
+    switch (items) {
+        SPMV_COO_WARP(2) SPMV_COO_WARP(4) SPMV_COO_WARP(8)
+    default: return fail(SPMVB200_ERR_INVALID, "coo.items must be 2, 4 or 8");
+    }
+#undef SPMV_COO_WARP
+    return fail(SPMVB200_ERR_INVALID, "coo.threads must be 64, 128 or 256");
+}
+
 int launch_coo(Matrix * m)
 {
     if (m->coo_n == 0 || m->rows == 0) return 0;
-    if (m->coo_mode == SPMVB200_COO_ATOMIC || !m->coo_sorted) {
+    // coo.algo: 0 automatic, 1 shared-memory staged tiles (sorted entries only), 2 register-staged warp
+    // stripes (any order), 3 one reduction per entry
+    // Automatic = 2 for both modes: on file-order entries the warp kernel still merges adjacent equal
+    // rows and keeps 4 gathers per lane in flight (R-MAT 2^24: 1.55 ms vs 5.07 ms for algo 3).
+    const bool unsorted = m->coo_mode == SPMVB200_COO_ATOMIC || !m->coo_sorted;
+    if (m->opt_coo_algo == 3 || (unsorted && m->opt_coo_algo == 1)) {
         m->kernel_name = "coo_atomic_kernel";
         const int64_t pairs = (m->coo_n + 1) / 2;
         int64_t grid = std::min<int64_t>((pairs + 255) / 256, (int64_t)m->sm_count * 8 * 4);
-        SPMV_CUDA(launch_kernel(coo_atomic_kernel, (unsigned)grid, 256u, 0, m->stream, m->opt_pdl != 0, m->coo_n,
-                                (int)(m->opt_independent != 0), (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
+        const RunMode rm = run_mode(m);
+        SPMV_CUDA(launch_kernel(coo_atomic_kernel, (unsigned)grid, 256u, 0, m->stream, rm.pdl, m->coo_n,
+                                rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
                                 (const double *)m->coo_val, (const double *)m->x, m->y));
         count_launch();
         return 0;
+    }
+    if (m->opt_coo_algo != 1) {
+        m->kernel_name = m->opt_coo_algo == 4 ? "coo_warp_kernel" : "coo_warp4_kernel";
+        return launch_coo_warp(m);
     }
     m->kernel_name = "coo_segmented_kernel";
     const int stages = (int)(m->opt_coo_stages ? m->opt_coo_stages : 2);

@@ -305,6 +305,7 @@ static int csr_build_table(Matrix * m, int tile, int grid)
     csr_tile_table_kernel<OffT><<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(
         m->rows, m->stored, m->csr_chunk, m->csr_tpc, tile, grid, (const OffT *)m->rp, table);
     SPMV_CUDA(cudaGetLastError());
+    m->aux_dirty = true;
     return 0;
 }
 
@@ -337,8 +338,9 @@ static int launch_csr_variant(Matrix * m)
     // persistent grid: one wave, but never more CTAs than there are 16-entry groups
     int64_t grid = std::min<int64_t>((int64_t)m->sm_count * ctas, std::max<int64_t>(1, (m->stored + 15) / 16));
     if (!m->tile_row || m->csr_tile != TILE || m->csr_grid != (int)grid) SPMV_TRY(csr_build_table<OffT>(m, TILE, (int)grid));
-    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, THREADS, smem, m->stream, m->opt_pdl != 0, m->stored, m->csr_chunk,
-                            m->csr_tpc, (int)(m->opt_independent != 0), (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
+    const RunMode rm = run_mode(m);
+    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, THREADS, smem, m->stream, rm.pdl, m->stored, m->csr_chunk,
+                            m->csr_tpc, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
                             (const int2 *)m->tile_row, (const double *)m->x, m->y));
     count_launch();
     return 0;

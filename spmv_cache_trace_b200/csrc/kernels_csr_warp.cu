@@ -166,6 +166,7 @@ static int build_span_table(Matrix * m)
     csr_span_rows_kernel<OffT><<<(unsigned)((nspans + 1 + 255) / 256), 256, 0, m->stream>>>(
         m->rows, nspans, kWarpSpan, (const OffT *)m->rp, m->span_row);
     SPMV_CUDA(cudaGetLastError());
+    m->aux_dirty = true;
     return 0;
 }
 
@@ -174,8 +175,9 @@ static int launch_warp_variant(Matrix * m)
 {
     const int64_t nspans = (m->stored + kWarpSpan - 1) / kWarpSpan;
     const unsigned grid = (unsigned)((nspans + WARPS - 1) / WARPS);
-    SPMV_CUDA(launch_kernel(csr_warp_kernel<OffT, G, WARPS>, grid, WARPS * 32u, 0, m->stream, m->opt_pdl != 0, m->stored,
-                            nspans, (int)(m->opt_independent != 0), (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
+    const RunMode rm = run_mode(m);
+    SPMV_CUDA(launch_kernel(csr_warp_kernel<OffT, G, WARPS>, grid, WARPS * 32u, 0, m->stream, rm.pdl, m->stored,
+                            nspans, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
                             (const int32_t *)m->span_row, (const double *)m->x, m->y));
     count_launch();
     return 0;

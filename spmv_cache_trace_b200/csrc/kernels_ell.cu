@@ -152,8 +152,9 @@ static int launch_ell_rw(Matrix * m, int block)
     const int64_t threads = (row1 - row0 + R - 1) / R;
     const unsigned grid = (unsigned)((threads + block - 1) / block);
     const int w = (int)m->ell_w;
-    const bool pdl = m->opt_pdl != 0;
-    const int indep = m->opt_independent != 0;
+    const RunMode rm = run_mode(m);
+    const bool pdl = rm.pdl;
+    const int indep = rm.independent;
     cudaError_t e;
 #define SPMV_ELL_CASE(WS)                                                                                      \
     case WS:                                                                                                   \

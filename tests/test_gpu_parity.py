@@ -348,10 +348,14 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
         B = build(fmt, mm, **kw)
         y = B * x + y0
         assert_within(y, yref, bound + np.abs(yref), fmt)
-        for threads, stages in ((64, 2), (128, 3), (256, 4), (0, 0)):
+        for threads, stages, algo, items in ((64, 2, 1, 0), (128, 3, 1, 0), (256, 4, 1, 0), (64, 0, 2, 2), (128, 0, 2, 4),
+                                             (256, 0, 2, 8), (0, 0, 3, 0), (0, 0, 0, 0)):
             B.set_option("coo.threads", threads)
             B.set_option("coo.stages", stages)
-            assert_within(B * x + y0, yref, bound + np.abs(yref), f"{fmt} coo.threads={threads} coo.stages={stages}")
+            B.set_option("coo.algo", algo)
+            B.set_option("coo.items", items)
+            assert_within(B * x + y0, yref, bound + np.abs(yref),
+                          f"{fmt} coo.threads={threads} coo.stages={stages} coo.algo={algo} coo.items={items}")
     H = hybrid_matrix.from_matrix_market(mm)
     OH = oracle.hyb(rows, cols, i, j, a)
     eh = H.export()
