@@ -231,6 +231,10 @@ int spmvb200_host_free(void *ptr);
 
 /* ---- the hot path ----------------------------------------------------------- */
 
+/* Build whatever launch metadata the selected kernel needs (CSR: span table / tile table) now instead
+ * of on the first spmvb200_spmv, and wait for it.  Ref: Kernel::prepare (kernels/kernel.hpp:28), which
+ * profile_kernel_run calls once before the timed runs (profile-kernel.cpp:227). */
+int spmvb200_prepare(spmvb200_matrix_t m);
 /* y += A*x on the device, asynchronous on the matrix's stream.
  * Ref: csr_matrix::spmv (matrix/csr-matrix-spmv.cpp:148-167),
  *      coo_matrix::spmv / spmv_atomic (matrix/coo-matrix.cpp:313-358),
@@ -269,9 +273,11 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               this option is 1 = the caller promises that no kernel in flight writes this matrix's x.
  *               -1 = never overlap.
  *               "pdl" (default 1): programmatic dependent launch on/off.
- *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular; "csr.lanes" 1|2|4|8
- *               lanes per row; "csr.threads" 32|64|128|256; "csr.tile" 256..2048; "csr.stages" 2|3;
- *               "csr.ctas_per_sm"; "csr.spare_ctas" CTA slots per SM left free for a concurrent kernel.
+ *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (default: split by
+ *               non-zeros, 4 entries per lane, rows from span metadata); "csr.threads" 128|256 (algo 3, 4),
+ *               32..256 (algo 1, 2); algo 1-3: "csr.lanes" 1|2|4|8 lanes per row; algo 1, 2: "csr.tile"
+ *               256..2048, "csr.stages" 2|3, "csr.ctas_per_sm", "csr.spare_ctas" CTA slots per SM left
+ *               free for a concurrent kernel.
  *   ELL         "ell.rows_per_thread" 1|2|4, "ell.block" 32..256.
  *   COO         "coo.algo" 1 shared-memory staged tiles (sorted entries), 2 register-staged, 4 entries per
  *               lane, one segmented warp scan per 128 entries (default, any entry order), 3 one reduction

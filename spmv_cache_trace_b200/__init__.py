@@ -302,6 +302,10 @@ class DeviceMatrix:
         _check(_abi.lib().spmvb200_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     # -- the hot path ------------------------------------------------------------
+    def prepare(self):
+        """Build the selected kernel's launch metadata now (Kernel::prepare, kernels/kernel.hpp:28)."""
+        _check(_abi.lib().spmvb200_prepare(self._h))
+
     def spmv(self):
         """y += A x on the device (asynchronous)."""
         _check(_abi.lib().spmvb200_spmv(self._h))

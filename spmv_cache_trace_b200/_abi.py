@@ -88,6 +88,7 @@ SIGNATURES = {
     "spmvb200_set_stream": (C.c_int, [vp, vp]),
     "spmvb200_host_alloc": (C.c_int, [C.c_size_t, vpp]),
     "spmvb200_host_free": (C.c_int, [vp]),
+    "spmvb200_prepare": (C.c_int, [vp]),
     "spmvb200_spmv": (C.c_int, [vp]),
     "spmvb200_sync": (C.c_int, [vp]),
     "spmvb200_spmv_host": (C.c_int, [vp, f64p, f64p]),

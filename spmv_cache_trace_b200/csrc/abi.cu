@@ -846,6 +846,20 @@ static int launch(Matrix * m)
     return fail(SPMVB200_ERR_INVALID, "unknown format");
 }
 
+int spmvb200_prepare(spmvb200_matrix_t m)
+{
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_CSR) return 0;  // only the CSR kernels keep launch metadata
+    m->dry_run = true;
+    const int rc = launch_csr(m);
+    m->dry_run = false;
+    if (rc) return rc;
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    m->aux_dirty = false;
+    stream_synced(m->stream);
+    return 0;
+}
+
 int spmvb200_spmv(spmvb200_matrix_t m)
 {
     SPMV_TRY(check_run(m));
@@ -985,6 +999,10 @@ int spmvb200_time_rotating(const spmvb200_matrix_t * ms, int n, int warmup, int 
         ms[k]->stream = s;
     }
     int rc = 0;
+    for (int k = 0; k < n; k++) {
+        SPMV_TRY(spmvb200_prepare(ms[k]));
+        ms[k]->stream = s;  // (prepare ran on the shared stream too)
+    }
     auto run = [&]() -> int {
         for (int w = 0; w < warmup; w++) SPMV_TRY(launch(ms[w % n]));
         SPMV_CUDA(cudaStreamSynchronize(s));

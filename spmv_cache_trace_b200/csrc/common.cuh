@@ -72,7 +72,10 @@ struct spmvb200_matrix_s {
     int csr_grid = 0;  // ... and the persistent grid size
     int64_t csr_chunk = 0;  // non-zeros per CTA
     int csr_tpc = 0;        // tiles per CTA
-    int32_t * span_row = nullptr;  // warp kernel: row holding the first entry of every 256-entry span
+    int32_t * span_row = nullptr;  // warp / flat kernels: row holding the first entry of every span_size-entry span
+    int span_size = 0;
+    int32_t * flat_meta = nullptr;  // flat kernel: {first row, -, -, -, 128-bit row-start mask} per 128-entry span
+    bool flat_has_empty = false;    // some row is empty: the mask cannot describe the row starts
     int64_t csr_maxlen = -1;       // longest row (computed on first use)
 
     // ELL (column-major)
@@ -130,6 +133,7 @@ struct spmvb200_matrix_s {
     // griddepcontrol.wait because nothing in flight on its stream writes its x or reads its y
     bool run_pdl = true, run_independent = false;
     bool aux_dirty = false;       // an auxiliary table was just (re)built on the stream: serialise the next launch
+    bool dry_run = false;         // spmvb200_prepare: build the launch metadata of the selected kernel, launch nothing
     const char * kernel_name = "";
 };
 

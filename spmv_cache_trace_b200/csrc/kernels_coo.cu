@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
+#include "segreduce.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -167,10 +168,10 @@ coo_warp_kernel(int64_t n, int independent, const int32_t * __restrict__ row, co
 
 // The same idea with a BLOCKED assignment: lane l owns the 4 consecutive entries 4l..4l+3 of the warp's
 // 128, fetched with one 128-bit load each for the row and column indices and one 256-bit load for
-// the values (3 load instructions instead of 12).  The lane sums its own runs of equal rows serially;
-// runs that lie strictly inside a lane go to y directly, and only the lane's first and last run take
-// part in ONE segmented scan across the warp per 128 entries (a quarter of the shuffles of the
-// striped kernel, whose l1tex/MIO pipe was 70 % busy with gathers + shuffles; profiles/).
+// the values (3 load instructions instead of 12).  The runs of equal rows are summed by
+// warp_segmented_add4 (segreduce.cuh): serially inside a lane, ONE segmented scan across the warp
+// per 128 entries -- a quarter of the shuffles of the striped kernel, whose l1tex/MIO pipe was 70 %
+// busy with gathers + shuffles (profiles/r01_ncu_c3_coo_warp.txt).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
@@ -190,40 +191,7 @@ coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, c
     const double x0 = __ldg(x + c4.x), x1 = __ldg(x + c4.y), x2 = __ldg(x + c4.z), x3 = __ldg(x + c4.w);
     const int r[4] = {k0 < n ? r4.x : -1, k0 + 1 < n ? r4.y : -1, k0 + 2 < n ? r4.z : -1, k0 + 3 < n ? r4.w : -1};
     const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
-    // runs inside the lane
-    int cur_row = r[0];
-    double cur = p[0], head = 0.0;
-    bool single = true;  // the lane holds one run only
-#pragma unroll
-    for (int j = 1; j < 4; ++j) {
-        if (r[j] == cur_row) {
-            cur = __dadd_rn(cur, p[j]);
-        } else {
-            if (single) { head = cur; single = false; }
-            else if (cur_row >= 0) red_add_f64(y + cur_row, cur);
-            cur_row = r[j];
-            cur = p[j];
-        }
-    }
-    // across lanes: my first run may continue the previous lane's last run
-    const int prev_last = __shfl_up_sync(0xffffffffu, r[3], 1);
-    const int next_first = __shfl_down_sync(0xffffffffu, r[0], 1);
-    const bool cont = lane > 0 && prev_last == r[0];
-    const bool next_cont = lane < 31 && next_first == r[3];
-    const unsigned heads = __ballot_sync(0xffffffffu, !(single && cont));
-    const int dist = lane - (31 - __clz(heads & (0xffffffffu >> (31 - lane))));
-    const int longest = __reduce_max_sync(0xffffffffu, dist);
-    double s = cur;  // sum of the last run, then of the chain of single-run lanes that ends here
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        if (d <= longest) {  // warp-uniform
-            const double t = __shfl_up_sync(0xffffffffu, s, d);
-            if (dist >= d) s = __dadd_rn(s, t);
-        }
-    }
-    const double prev_s = __shfl_up_sync(0xffffffffu, s, 1);
-    if (!single && r[0] >= 0) red_add_f64(y + r[0], cont ? __dadd_rn(prev_s, head) : head);
-    if (!next_cont && r[3] >= 0) red_add_f64(y + r[3], s);
+    warp_segmented_add4(lane, r, p, y);
 }
 
 // Entries in file order: one fp64 reduction per entry, two entries per thread and iteration

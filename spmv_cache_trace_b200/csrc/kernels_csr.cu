@@ -338,6 +338,7 @@ static int launch_csr_variant(Matrix * m)
     // persistent grid: one wave, but never more CTAs than there are 16-entry groups
     int64_t grid = std::min<int64_t>((int64_t)m->sm_count * ctas, std::max<int64_t>(1, (m->stored + 15) / 16));
     if (!m->tile_row || m->csr_tile != TILE || m->csr_grid != (int)grid) SPMV_TRY(csr_build_table<OffT>(m, TILE, (int)grid));
+    if (m->dry_run) return 0;
     const RunMode rm = run_mode(m);
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, THREADS, smem, m->stream, rm.pdl, m->stored, m->csr_chunk,
                             m->csr_tpc, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col, (const double *)m->val,
@@ -389,21 +390,20 @@ static int launch_csr_t(Matrix * m, const CsrConfig & c)
 }
 
 int launch_csr_warp(Matrix * m, int lanes);  // kernels_csr_warp.cu
+int launch_csr_flat(Matrix * m);             // kernels_csr_flat.cu
 int csr_max_row_length(Matrix * m);          // builders.cu
 
 int launch_csr(Matrix * m)
 {
     if (m->rows == 0 || m->stored == 0) return 0;
     const CsrConfig c = csr_config(m);
-    // csr.algo: 0 automatic, 1 stream/direct, 2 stream/product, 3 warp-granular register-staged.
-    // Automatic: the stream kernel when row lengths are regular (longest row within 4x the mean,
-    // e.g. PDE stencils); the warp kernel, whose scheduling is finer, for irregular matrices.
-    bool warp = m->opt_csr_algo == 3;
-    if (m->opt_csr_algo == 0 && c.lanes > 0) {
-        SPMV_TRY(csr_max_row_length(m));
-        const int64_t avg = (m->stored + m->rows - 1) / m->rows;
-        warp = m->csr_maxlen > 4 * std::max<int64_t>(avg, 4);
-    }
+    // csr.algo: 0 automatic, 1 stream/direct, 2 stream/product, 3 warp-granular register-staged,
+    // 4 flat (register-staged, split by non-zeros, rows from span metadata; kernels_csr_flat.cu).
+    // Automatic = flat: fastest on every matrix measured (profiles/r01_sweep_j_csr_flat.log: 2D 5-point
+    // 14.3 vs 16.2 us, 3D 7-point 35.0 vs 38.1 us, 27-point 256^3 1.01 vs 1.07 ms, R-MAT 2^24 1.18 vs
+    // 1.55 ms for the best of the others).
+    if (m->opt_csr_algo == 0 || m->opt_csr_algo == 4) return launch_csr_flat(m);
+    const bool warp = m->opt_csr_algo == 3;
     if (warp) return launch_csr_warp(m, c.lanes > 0 ? c.lanes : 8);
     m->kernel_name = c.lanes == 0 ? "csr_stream_kernel<product>" : "csr_stream_kernel<direct>";
     return m->off64 ? launch_csr_t<int64_t>(m, c) : launch_csr_t<uint32_t>(m, c);

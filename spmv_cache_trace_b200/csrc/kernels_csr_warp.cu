@@ -157,14 +157,21 @@ csr_warp_kernel(int64_t stored, int64_t nspans, int independent, const OffT * __
     }
 }
 
-template <typename OffT>
-static int build_span_table(Matrix * m)
+// span_row[w] = row holding entry w*span, for the warp-granular kernels (span 256 here, 128 in
+// kernels_csr_flat.cu); rebuilt when a kernel with a different span size is selected.
+int csr_build_span_table(Matrix * m, int span)
 {
-    if (m->span_row) return 0;
-    const int64_t nspans = (m->stored + kWarpSpan - 1) / kWarpSpan;
-    SPMV_TRY(dev_alloc(m, &m->span_row, nspans + 1));
-    csr_span_rows_kernel<OffT><<<(unsigned)((nspans + 1 + 255) / 256), 256, 0, m->stream>>>(
-        m->rows, nspans, kWarpSpan, (const OffT *)m->rp, m->span_row);
+    if (m->span_row && m->span_size == span) return 0;
+    if (m->span_row) {
+        cudaFree(m->span_row);
+        m->span_row = nullptr;
+    }
+    const int64_t nspans = (m->stored + span - 1) / span;
+    SPMV_TRY(dev_alloc((Matrix *)nullptr, &m->span_row, nspans + 1));
+    m->span_size = span;
+    const unsigned grid = (unsigned)((nspans + 1 + 255) / 256);
+    if (m->off64) csr_span_rows_kernel<int64_t><<<grid, 256, 0, m->stream>>>(m->rows, nspans, span, (const int64_t *)m->rp, m->span_row);
+    else csr_span_rows_kernel<uint32_t><<<grid, 256, 0, m->stream>>>(m->rows, nspans, span, (const uint32_t *)m->rp, m->span_row);
     SPMV_CUDA(cudaGetLastError());
     m->aux_dirty = true;
     return 0;
@@ -173,6 +180,7 @@ static int build_span_table(Matrix * m)
 template <typename OffT, int G, int WARPS>
 static int launch_warp_variant(Matrix * m)
 {
+    if (m->dry_run) return 0;
     const int64_t nspans = (m->stored + kWarpSpan - 1) / kWarpSpan;
     const unsigned grid = (unsigned)((nspans + WARPS - 1) / WARPS);
     const RunMode rm = run_mode(m);
@@ -197,7 +205,7 @@ static int launch_warp_warps(Matrix * m, int warps)
 template <typename OffT>
 static int launch_warp_t(Matrix * m, int lanes, int warps)
 {
-    SPMV_TRY(build_span_table<OffT>(m));
+    SPMV_TRY(csr_build_span_table(m, kWarpSpan));
     switch (lanes) {
     case 1: return launch_warp_warps<OffT, 1>(m, warps);
     case 2: return launch_warp_warps<OffT, 2>(m, warps);

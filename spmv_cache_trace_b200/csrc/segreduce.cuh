@@ -1,0 +1,55 @@
+// segreduce.cuh -- y[row] += sum of the products of a run of equal row indices, for a warp that
+// holds 128 consecutive entries, four per lane (lane l: entries 4l..4l+3).
+//
+// Each lane sums its own runs serially.  Runs that lie strictly inside a lane are added to y at
+// once; the lane's first and last run may continue in the neighbouring lanes, so the sums of the
+// last runs go through ONE segmented inclusive scan across the warp (Kogge-Stone with shuffles, cut
+// short at the longest chain of single-run lanes), after which every run that ends in a lane is
+// added to y by that lane with one fp64 reduction.  Rows < 0 mark entries past the end.
+// Used by coo_warp4_kernel (kernels_coo.cu) and csr_flat_kernel (kernels_csr_flat.cu).
+#pragma once
+
+#include "ptx.cuh"
+
+namespace spmvb200 {
+
+__device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4], const double (&p)[4],
+                                                    double * __restrict__ y)
+{
+    using ptx::red_add_f64;
+    int cur_row = r[0];
+    double cur = p[0], head = 0.0;
+    bool single = true;  // the lane holds one run only
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        if (r[j] == cur_row) {
+            cur = __dadd_rn(cur, p[j]);
+        } else {
+            if (single) { head = cur; single = false; }
+            else if (cur_row >= 0) red_add_f64(y + cur_row, cur);
+            cur_row = r[j];
+            cur = p[j];
+        }
+    }
+    // across lanes: my first run may continue the previous lane's last run
+    const int prev_last = __shfl_up_sync(0xffffffffu, r[3], 1);
+    const int next_first = __shfl_down_sync(0xffffffffu, r[0], 1);
+    const bool cont = lane > 0 && prev_last == r[0];
+    const bool next_cont = lane < 31 && next_first == r[3];
+    const unsigned heads = __ballot_sync(0xffffffffu, !(single && cont));
+    const int dist = lane - (31 - __clz(heads & (0xffffffffu >> (31 - lane))));
+    const int longest = __reduce_max_sync(0xffffffffu, dist);
+    double s = cur;  // sum of the last run, then of the chain of single-run lanes that ends here
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        if (d <= longest) {  // warp-uniform
+            const double t = __shfl_up_sync(0xffffffffu, s, d);
+            if (dist >= d) s = __dadd_rn(s, t);
+        }
+    }
+    const double prev_s = __shfl_up_sync(0xffffffffu, s, 1);
+    if (!single && r[0] >= 0) red_add_f64(y + r[0], cont ? __dadd_rn(prev_s, head) : head);
+    if (!next_cont && r[3] >= 0) red_add_f64(y + r[3], s);
+}
+
+}  // namespace spmvb200

@@ -147,6 +147,7 @@ def test_poisson2D(oracle, kats, poisson2d, fmt, kw):
     if fmt == "csr" and not kw:
         # one lane per row: only rows cut by a tile boundary may differ in the last bit; this small
         # matrix (2417 entries) is cut into 16-entry chunks, so at most one row per chunk
+        A.set_option("csr.algo", 1)
         A.set_option("csr.lanes", 1)
         assert (A * b != yref).sum() <= (2417 + 15) // 16
     if fmt == "ell":
@@ -332,7 +333,9 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
     assert np.array_equal(e["value"], O.value)
     for threads, tile, stages, lanes, algo in ((128, 512, 2, 1, 0), (128, 512, 3, 2, 0), (128, 1024, 3, 4, 0),
                                                (256, 1024, 2, 8, 0), (256, 2048, 3, 1, 0), (256, 2048, 2, 0, 2),
-                                               (128, 512, 2, 0, 2), (256, 1024, 3, 0, 2), (0, 0, 0, 0, 0)):
+                                               (128, 512, 2, 0, 2), (256, 1024, 3, 0, 2), (128, 0, 0, 1, 3),
+                                               (256, 0, 0, 2, 3), (64, 0, 0, 0, 4), (128, 0, 0, 0, 4), (256, 0, 0, 0, 4),
+                                               (0, 0, 0, 0, 0)):
         A.set_option("csr.threads", threads)
         A.set_option("csr.tile", tile)
         A.set_option("csr.stages", stages)
@@ -374,7 +377,9 @@ def test_forced_64bit_offsets(oracle):
         A = csr_matrix.from_matrix_market(matrix_market.from_entries(3000, 5000, i, j, a))
         assert A.info.offsets_64bit == 1
         assert np.array_equal(A.export()["row_ptr"], O.row_ptr)
-        assert_within(A * x, yref, oracle.csr_abs_rowsum(O, x), "csr int64 offsets")
+        for algo in (0, 1, 3, 4):
+            A.set_option("csr.algo", algo)
+            assert_within(A * x, yref, oracle.csr_abs_rowsum(O, x), f"csr int64 offsets, csr.algo={algo}")
         E = A.convert(sp.ELL)
         assert_within(E * x, yref, oracle.csr_abs_rowsum(O, x), "ell from int64 csr")
     finally:
@@ -470,6 +475,10 @@ def test_config1_poisson2d_1000x1000_full_size(oracle, fmt):
     if fmt in (sp.CSR, sp.ELL):
         # integer-valued data: every partial sum is exact, any order gives the same bits
         assert np.array_equal(y, yref)
+    if fmt == sp.CSR:  # every CSR kernel at full size
+        for algo in (1, 2, 3, 4):
+            A.set_option("csr.algo", algo)
+            assert np.array_equal(A * x, yref), f"csr.algo={algo}"
 
 
 def test_config2_poisson3d_128_ell_full_size(oracle):
@@ -491,11 +500,15 @@ def test_config2_poisson3d_128_ell_full_size(oracle):
         assert np.array_equal(A * x, yref)
     # CSR, one lane per row: every row that is not cut by a tile boundary is bit-identical too
     C = sp.generators.stencil(sp.STENCIL_3D7, n, n, n, fmt=sp.CSR)
+    C.set_option("csr.algo", 1)
     C.set_option("csr.lanes", 1)
     yc = C * x
     assert_within(yc, yref, oracle.csr_abs_rowsum(O, x), "config 2 csr")
     tiles = 148 * 8 * (14581760 // (148 * 8 * 1024) + 2)
     assert (yc != yref).sum() <= tiles
+    for algo in (3, 4, 0):
+        C.set_option("csr.algo", algo)
+        assert_within(C * x, yref, oracle.csr_abs_rowsum(O, x), f"config 2 csr.algo={algo}")
 
 
 def test_rmat_cross_format_agreement_and_linearity(oracle):
@@ -574,4 +587,4 @@ def test_kernels_really_launch():
     A.spmv()
     A.sync()
     assert sp.launch_count() == before + 1
-    assert A.kernel_name.startswith("csr_stream_kernel")
+    assert A.kernel_name == "csr_flat_kernel"
