@@ -313,6 +313,49 @@ int spmvb200_csr_row_block(spmvb200_matrix_t m, int64_t row_begin, int64_t row_e
 int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col_end,
                              int64_t *col_min, int64_t *col_max, int64_t *lo_end, int64_t *hi_begin);
 
+/* ---- the reference's cache model for the chosen partition (host side) -------- */
+
+/* The fully associative LRU model of the reference (cache-simulation/lru.cpp:31-54, driver
+ * cache-trace.cpp:92-161, interleaving replacement.cpp:41-95) run over the SpMV reference string
+ * (csr-matrix.cpp:97-143, ell-matrix.cpp:103-143, coo-matrix.cpp:144-185) with the two things the
+ * GPU path needs and the reference lacks: misses attributed to the array they hit, and an
+ * arbitrary contiguous partition.  Pure host code; no CUDA call. */
+typedef struct {
+    int64_t cache_bytes;    /* e.g. the L2 size reported by spmvb200_device_props                 */
+    int32_t line_bytes;     /* 64 = the reference's configs; 128 = L2 line; 32 = DRAM sector         */
+    int32_t parts;          /* "threads" of the reference model: GPUs of the row-partitioned mode   */
+    const int64_t *starts;  /* parts+1 row (COO: entry) starts; NULL = the reference rule ceil(n/P) */
+    int32_t shared;         /* 1: one cache, references of the parts interleaved round-robin
+                               (the reference's shared L3); 0: a private cache per part (an L2 per GPU) */
+    int32_t warmup;         /* 1: a warm-up pass before the counted one (cache-trace.cpp:128-140)  */
+    int32_t page_bytes;     /* > 0: x_j / y_i are owned per page by the reference's rule
+                               (aligned-allocator.hpp:156-211); 0: by the part that owns index j   */
+    int32_t stream_bypass;  /* 1: index/value streams miss but are not allocated (the kernels'
+                               evict-first L2 policy); 0: plain LRU for every reference             */
+} spmvb200_cache_config;
+
+typedef struct {
+    int64_t references;
+    int64_t misses_index;         /* row_ptr (CSR) / row_index (COO)                              */
+    int64_t misses_column_index;
+    int64_t misses_value;
+    int64_t misses_x_local, misses_x_remote; /* the x gather, by owner of x_j                      */
+    int64_t misses_y_local, misses_y_remote;
+    int64_t x_references, x_remote_references;
+} spmvb200_cache_misses;
+
+/* out[parts].  Host arrays in the reference's layouts (ELL: row-major). */
+int spmvb200_cache_trace_csr(int64_t rows, int64_t columns, const int64_t *row_ptr, const int32_t *column_index,
+                             const spmvb200_cache_config *cfg, spmvb200_cache_misses *out);
+int spmvb200_cache_trace_ell(int64_t rows, int64_t columns, int64_t row_length, const int32_t *column_index_row_major,
+                             const spmvb200_cache_config *cfg, spmvb200_cache_misses *out);
+int spmvb200_cache_trace_coo(int64_t rows, int64_t columns, int64_t num_entries, const int32_t *row_index,
+                             const int32_t *column_index, const spmvb200_cache_config *cfg, spmvb200_cache_misses *out);
+/* The same for a device matrix (CSR, ELL, COO; hybrid: its ELL part then its COO part, misses summed):
+ * the index arrays are copied back to the host first.  Ref: Kernel::memory_reference_string
+ * (kernels/kernel.hpp:33-36) + trace_cache_misses (cache-trace.cpp:163-187). */
+int spmvb200_cache_trace(spmvb200_matrix_t m, const spmvb200_cache_config *cfg, spmvb200_cache_misses *out);
+
 #ifdef __cplusplus
 }
 #endif

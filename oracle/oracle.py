@@ -489,6 +489,18 @@ class RefMatrix:
                                               _ptr(ns, _f64p)))
         return ns
 
+    def cache_trace(self, threads: int, cache_bytes: int, line_bytes: int = 64, warmup: bool = False,
+                    page_bytes: int = 4096):
+        """The reference's own cache trace of one cache shared by all threads (cache-trace.cpp:92-161):
+        misses[t, d] = misses of thread t on lines whose page belongs to thread/NUMA domain d."""
+        if not hasattr(self.ref.lib, "ref_cache_trace"):
+            raise RefError("libspmvref.so was built without the cache-simulation sources")
+        out = np.zeros((threads, threads), np.uint64)
+        self.ref._check(self.ref.lib.ref_cache_trace(self.h, C.c_int(threads), C.c_int64(cache_bytes), C.c_int(line_bytes),
+                                                     C.c_int(int(warmup)), C.c_int(page_bytes),
+                                                     out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out.astype(np.int64)
+
     def csr_rows_per_thread(self, t, T):
         return int(self.ref.lib.ref_csr_rows_per_thread(self.h, t, T))
 

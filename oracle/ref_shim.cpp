@@ -7,6 +7,8 @@
  * reference's public functions:
  *   matrix_market::fromStream / load_matrix / sort_matrix_row_major
  *   {csr,coo,ell,hybrid}_matrix::from_matrix_market, ::spmv, ::spmv_atomic
+ *   {csr,ell,coo}_matrix::Matrix::spmv[_atomic]_memory_reference_string,
+ *   replacement::LRU, replacement::trace_cache_misses
  * No reference source is copied into this repository.  Used (a) to pin
  * oracle/spmv_oracle.c, (b) to generate tests/golden/ref_vectors.npz, and
  * (c) as bench.py's CPU baseline ("kind": "reference").
@@ -17,6 +19,7 @@
 #include "matrix/hybrid-matrix.hpp"
 #include "matrix/matrix-error.hpp"
 #include "matrix/matrix-market.hpp"
+#include "cache-simulation/replacement.hpp"
 
 #include <omp.h>
 #include <sched.h>
@@ -297,6 +300,36 @@ int ref_time(void * h, int T, int pin, int reps, double * ns)
                 #pragma omp barrier
             }
         }
+    });
+}
+
+/* The reference's cache trace for one cache (cache-trace.cpp:92-161): reference strings of all T
+ * threads (numa domain of thread t = t), LRU of cache_bytes/line_bytes lines shared by them,
+ * optional warm-up pass; misses[t*T + d] = misses of thread t on lines owned by domain d.
+ * Formats: csr, ell, coo-atomic. */
+int ref_cache_trace(void * h, int T, int64_t cache_bytes, int line_bytes, int warmup, int page_size, uint64_t * misses)
+{
+    return guarded([&] {
+        auto * m = static_cast<RefMatrix *>(h);
+        int64_t rows, cols;
+        shape(m, &rows, &cols);
+        m->x.assign((size_t)cols, 1.0);
+        m->y.assign((size_t)rows, 0.0);
+        std::vector<int> domains(T);
+        for (int t = 0; t < T; t++) domains[t] = t;
+        std::vector<replacement::MemoryReferenceString> ws(T);
+        for (int t = 0; t < T; t++) {
+            if (m->format == "csr") ws[t] = m->csr.spmv_memory_reference_string(m->x, m->y, t, T, domains.data(), page_size);
+            else if (m->format == "ell") ws[t] = m->ell.spmv_memory_reference_string(m->x, m->y, t, T, domains.data(), page_size);
+            else if (m->format == "coo-atomic") ws[t] = m->coo.spmv_atomic_memory_reference_string(m->x, m->y, t, T, domains.data(), page_size);
+            else throw std::runtime_error("ref_cache_trace: format must be csr, ell or coo-atomic");
+        }
+        int64_t lines = (cache_bytes + line_bytes - 1) / line_bytes;
+        replacement::LRU lru(lines, line_bytes);
+        if (warmup) replacement::trace_cache_misses(lru, ws, T, false, 0);
+        auto r = replacement::trace_cache_misses(lru, ws, T, false, 0);
+        for (int t = 0; t < T; t++)
+            for (int d = 0; d < T; d++) misses[t * T + d] = r[t][d];
     });
 }
 

@@ -590,3 +590,65 @@ class partition:
         out = np.zeros(parts + 1, np.int64)
         _check(_abi.lib().spmvb200_partition_rows_nnz(A._h, parts, _p(out, i64p)))
         return out
+
+
+class cache_model:
+    """The reference's LRU cache model (cache-simulation/lru.cpp, cache-trace.cpp:92-161) over the SpMV
+    reference string, with per-array attribution and an arbitrary partition (include/spmv_b200.h).
+    Host side only.  Every function returns one dict per part."""
+
+    FIELDS = [n for n, _ in _abi.CacheMisses._fields_]
+
+    @staticmethod
+    def _config(cache_bytes, line_bytes, parts, starts, shared, warmup, page_bytes, stream_bypass):
+        keep = None
+        cfg = _abi.CacheConfig(int(cache_bytes), int(line_bytes), int(parts), None, int(bool(shared)),
+                               int(bool(warmup)), int(page_bytes), int(bool(stream_bypass)))
+        if starts is not None:
+            keep = np.ascontiguousarray(starts, dtype=np.int64)
+            if keep.size != parts + 1:
+                raise matrix_error("starts must have parts+1 entries")
+            cfg.starts = _p(keep, i64p)
+        return cfg, keep
+
+    @staticmethod
+    def _result(out):
+        return [{n: int(getattr(o, n)) for n in cache_model.FIELDS} for o in out]
+
+    @staticmethod
+    def csr(rows, columns, row_ptr, column_index, cache_bytes, line_bytes=64, parts=1, starts=None, shared=True,
+            warmup=False, page_bytes=0, stream_bypass=False):
+        rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        col = np.ascontiguousarray(column_index, dtype=np.int32)
+        cfg, keep = cache_model._config(cache_bytes, line_bytes, parts, starts, shared, warmup, page_bytes, stream_bypass)
+        out = (_abi.CacheMisses * parts)()
+        _check(_abi.lib().spmvb200_cache_trace_csr(rows, columns, _p(rp, i64p), _p(col, i32p), C.byref(cfg), out))
+        return cache_model._result(out)
+
+    @staticmethod
+    def ell(rows, columns, row_length, column_index_row_major, cache_bytes, line_bytes=64, parts=1, starts=None,
+            shared=True, warmup=False, page_bytes=0, stream_bypass=False):
+        col = np.ascontiguousarray(column_index_row_major, dtype=np.int32)
+        cfg, keep = cache_model._config(cache_bytes, line_bytes, parts, starts, shared, warmup, page_bytes, stream_bypass)
+        out = (_abi.CacheMisses * parts)()
+        _check(_abi.lib().spmvb200_cache_trace_ell(rows, columns, row_length, _p(col, i32p), C.byref(cfg), out))
+        return cache_model._result(out)
+
+    @staticmethod
+    def coo(rows, columns, row_index, column_index, cache_bytes, line_bytes=64, parts=1, starts=None, shared=True,
+            warmup=False, page_bytes=0, stream_bypass=False):
+        row = np.ascontiguousarray(row_index, dtype=np.int32)
+        col = np.ascontiguousarray(column_index, dtype=np.int32)
+        cfg, keep = cache_model._config(cache_bytes, line_bytes, parts, starts, shared, warmup, page_bytes, stream_bypass)
+        out = (_abi.CacheMisses * parts)()
+        _check(_abi.lib().spmvb200_cache_trace_coo(rows, columns, len(row), _p(row, i32p), _p(col, i32p), C.byref(cfg), out))
+        return cache_model._result(out)
+
+    @staticmethod
+    def matrix(A: "DeviceMatrix", cache_bytes, line_bytes=64, parts=1, starts=None, shared=True, warmup=False,
+               page_bytes=0, stream_bypass=False):
+        """The model for a device matrix (its index arrays are copied back to the host)."""
+        cfg, keep = cache_model._config(cache_bytes, line_bytes, parts, starts, shared, warmup, page_bytes, stream_bypass)
+        out = (_abi.CacheMisses * parts)()
+        _check(_abi.lib().spmvb200_cache_trace(A._h, C.byref(cfg), out))
+        return cache_model._result(out)

@@ -35,6 +35,25 @@ class Info(C.Structure):
     ]
 
 
+class CacheConfig(C.Structure):
+    """spmvb200_cache_config"""
+    _fields_ = [
+        ("cache_bytes", C.c_int64), ("line_bytes", C.c_int32), ("parts", C.c_int32),
+        ("starts", i64p), ("shared", C.c_int32), ("warmup", C.c_int32),
+        ("page_bytes", C.c_int32), ("stream_bypass", C.c_int32),
+    ]
+
+
+class CacheMisses(C.Structure):
+    """spmvb200_cache_misses"""
+    _fields_ = [(n, C.c_int64) for n in (
+        "references", "misses_index", "misses_column_index", "misses_value", "misses_x_local",
+        "misses_x_remote", "misses_y_local", "misses_y_remote", "x_references", "x_remote_references")]
+
+
+_ccp = C.POINTER(CacheConfig)
+_cmp = C.POINTER(CacheMisses)
+
 # name -> (restype, argtypes); the exported symbol set the tests check against the header
 SIGNATURES = {
     "spmvb200_last_error": (C.c_char_p, []),
@@ -104,6 +123,10 @@ SIGNATURES = {
     "spmvb200_partition_rows_nnz": (C.c_int, [vp, C.c_int32, i64p]),
     "spmvb200_csr_row_block": (C.c_int, [vp, C.c_int64, C.c_int64, vpp]),
     "spmvb200_csr_column_span": (C.c_int, [vp, C.c_int64, C.c_int64, i64p, i64p, i64p, i64p]),
+    "spmvb200_cache_trace_csr": (C.c_int, [C.c_int64, C.c_int64, i64p, i32p, _ccp, _cmp]),
+    "spmvb200_cache_trace_ell": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, i32p, _ccp, _cmp]),
+    "spmvb200_cache_trace_coo": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, i32p, i32p, _ccp, _cmp]),
+    "spmvb200_cache_trace": (C.c_int, [vp, _ccp, _cmp]),
 }
 
 _lib = None

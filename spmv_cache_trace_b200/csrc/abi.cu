@@ -1198,4 +1198,45 @@ int spmvb200_csr_row_block(spmvb200_matrix_t src, int64_t row_begin, int64_t row
     return finish(g, out);
 }
 
+// ---- cache model on a device matrix -------------------------------------------------------------------------------
+
+int spmvb200_cache_trace(spmvb200_matrix_t m, const spmvb200_cache_config * cfg, spmvb200_cache_misses * out)
+{
+    SPMV_TRY(check(m));
+    if (!cfg || !out || cfg->parts < 1) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    if (m->format == SPMVB200_CSR) {
+        std::vector<int64_t> rp((size_t)m->rows + 1);
+        std::vector<int32_t> col((size_t)std::max<int64_t>(m->stored, 1));
+        SPMV_TRY(spmvb200_csr_export(m, rp.data(), col.data(), nullptr));
+        return spmvb200_cache_trace_csr(m->rows, m->cols, rp.data(), col.data(), cfg, out);
+    }
+    if (m->format == SPMVB200_ELL) {
+        std::vector<int32_t> col((size_t)std::max<int64_t>(m->rows * m->ell_w, 1));
+        SPMV_TRY(spmvb200_ell_export(m, col.data(), nullptr));
+        return spmvb200_cache_trace_ell(m->rows, m->cols, m->ell_w, col.data(), cfg, out);
+    }
+    if (m->format == SPMVB200_COO) {
+        std::vector<int32_t> row((size_t)std::max<int64_t>(m->coo_n, 1)), col((size_t)std::max<int64_t>(m->coo_n, 1));
+        SPMV_TRY(spmvb200_coo_export(m, row.data(), col.data(), nullptr));
+        return spmvb200_cache_trace_coo(m->rows, m->cols, m->coo_n, row.data(), col.data(), cfg, out);
+    }
+    if (m->format == SPMVB200_HYB) {
+        std::vector<int32_t> ecol((size_t)std::max<int64_t>(m->rows * m->ell_w, 1));
+        std::vector<int32_t> row((size_t)std::max<int64_t>(m->coo_n, 1)), col((size_t)std::max<int64_t>(m->coo_n, 1));
+        SPMV_TRY(spmvb200_hyb_export(m, ecol.data(), nullptr, row.data(), col.data(), nullptr));
+        std::vector<spmvb200_cache_misses> tail((size_t)cfg->parts);
+        spmvb200_cache_config c2 = *cfg;
+        c2.starts = nullptr;  // the tail is cut by entries (hybrid-matrix.cpp:491-528)
+        SPMV_TRY(spmvb200_cache_trace_ell(m->rows, m->cols, m->ell_w, ecol.data(), cfg, out));
+        SPMV_TRY(spmvb200_cache_trace_coo(m->rows, m->cols, m->coo_n, row.data(), col.data(), &c2, tail.data()));
+        for (int p = 0; p < cfg->parts; p++) {
+            int64_t * a = reinterpret_cast<int64_t *>(&out[p]);
+            const int64_t * b = reinterpret_cast<const int64_t *>(&tail[(size_t)p]);
+            for (size_t k = 0; k < sizeof(spmvb200_cache_misses) / sizeof(int64_t); k++) a[k] += b[k];
+        }
+        return 0;
+    }
+    return fail(SPMVB200_ERR_INVALID, "unknown format");
+}
+
 }  // extern "C"

@@ -9,7 +9,11 @@
 // because the host clock around an asynchronous launch says little, the same N runs timed again
 // with CUDA events.  Output: one JSON document in the reference's shape ("kernel",
 // "execution_time" with print_sample's statistics, src/util/sample.hpp:137-165) plus "roofline".
-// The cache-trace mode (--profile 0 in the reference) stays with the reference binary.
+// The cache-trace mode (--profile 0 in the reference) stays with the reference binary; what the GPU
+// path adds is --x-gather PARTS: the reference's LRU model (spmvb200_cache_trace) run for the row
+// partition the multi-GPU mode would choose (balanced non-zeros for CSR, the reference rule otherwise),
+// one private cache of the size of this GPU's L2 per part, misses attributed per array -- the predicted
+// x-gather traffic to put next to ncu's dram__bytes ("x_gather" in the output).
 #include "cuda_spmv_kernels.hpp"
 
 #include <getopt.h>
@@ -57,23 +61,32 @@ static void print_sample(std::ostream & o, std::vector<double> v, const char * u
 int main(int argc, char ** argv)
 {
     std::string format, matrix_path;
-    int profile = 10, threads = 1;
+    int profile = 10, threads = 1, gather_parts = 0, line_bytes = 32;
+    long long cache_bytes = 0;
     bool verbose = false;
     static option longopts[] = {{"spmv-format", required_argument, nullptr, 'f'}, {"matrix", required_argument, nullptr, 'm'},
                                 {"profile", required_argument, nullptr, 'p'}, {"threads", required_argument, nullptr, 't'},
+                                {"x-gather", required_argument, nullptr, 'x'}, {"cache-bytes", required_argument, nullptr, 'c'},
+                                {"line-bytes", required_argument, nullptr, 'l'},
                                 {"verbose", no_argument, nullptr, 'v'}, {"help", no_argument, nullptr, 'h'},
                                 {nullptr, 0, nullptr, 0}};
     int c;
-    while ((c = getopt_long(argc, argv, "f:m:p:t:vh", longopts, nullptr)) != -1) {
+    while ((c = getopt_long(argc, argv, "f:m:p:t:x:c:l:vh", longopts, nullptr)) != -1) {
         switch (c) {
         case 'f': format = optarg; break;
         case 'm': matrix_path = optarg; break;
         case 'p': profile = std::atoi(optarg); break;
         case 't': threads = std::max(1, std::atoi(optarg)); break;
+        case 'x': gather_parts = std::max(1, std::atoi(optarg)); break;
+        case 'c': cache_bytes = std::atoll(optarg); break;
+        case 'l': line_bytes = std::max(1, std::atoi(optarg)); break;
         case 'v': verbose = true; break;
         default:
             std::cout << "Usage: spmv-b200 --spmv-format FMT --matrix PATH [--profile N] [--threads T] [--verbose]\n"
-                         "  FMT: cuda-csr, cuda-coo, cuda-coo-atomic, cuda-ell, cuda-hybrid\n";
+                         "                 [--x-gather PARTS [--cache-bytes B] [--line-bytes L]]\n"
+                         "  FMT: cuda-csr, cuda-coo, cuda-coo-atomic, cuda-ell, cuda-hybrid\n"
+                         "  --x-gather PARTS  cache-model prediction of the x-gather misses for a PARTS-way partition\n"
+                         "                    (default cache: this GPU's L2; default line: the 32 B DRAM sector)\n";
             return c == 'h' ? EXIT_SUCCESS : EXIT_FAILURE;
         }
     }
@@ -136,7 +149,42 @@ int main(int argc, char ** argv)
                   << ",\n\"gpu_kernel\": \"" << spmvb200_kernel_name(gpu->handle()) << "\""
                   << ",\n\"best_gbs\": " << (best > 0 ? bytes / best : 0.0)
                   << ",\n\"best_gflops\": " << (best > 0 ? 2.0 * (double)info.num_entries / best : 0.0)
-                  << ",\n\"fraction_of_8TBs\": " << (best > 0 ? bytes / best / 8000.0 : 0.0) << "\n}\n}\n";
+                  << ",\n\"fraction_of_8TBs\": " << (best > 0 ? bytes / best / 8000.0 : 0.0) << "\n}";
+        if (gather_parts > 0) {
+            int dev = 0, sms = 0, maj = 0, min = 0;
+            int64_t l2 = 0, mem = 0;
+            char name[128];
+            if (cache_bytes <= 0 && spmvb200_device_props(dev, name, sizeof name, &sms, &l2, &mem, &maj, &min) == 0) cache_bytes = l2;
+            std::vector<int64_t> starts((size_t)gather_parts + 1);
+            const bool by_nnz = info.format == SPMVB200_CSR;
+            int rc = by_nnz ? spmvb200_partition_rows_nnz(gpu->handle(), gather_parts, starts.data())
+                            : spmvb200_partition_rows_ref(info.format == SPMVB200_COO ? info.num_entries : info.rows, gather_parts, starts.data());
+            if (rc != 0) throw kernel_error(spmvb200_last_error());
+            spmvb200_cache_config cfg{};
+            cfg.cache_bytes = cache_bytes; cfg.line_bytes = line_bytes; cfg.parts = gather_parts;
+            cfg.starts = info.format == SPMVB200_HYB ? nullptr : starts.data();
+            cfg.shared = 0; cfg.warmup = 0; cfg.page_bytes = 0; cfg.stream_bypass = 1;
+            std::vector<spmvb200_cache_misses> miss((size_t)gather_parts);
+            if (spmvb200_cache_trace(gpu->handle(), &cfg, miss.data()) != 0) throw kernel_error(spmvb200_last_error());
+            std::cout << ",\n\"x_gather\": {\n\"model\": \"fully associative LRU (reference cache-simulation/lru.cpp), one private cache per part, "
+                         "matrix streams bypass the cache\",\n\"cache_bytes\": " << cache_bytes << ",\n\"line_bytes\": " << line_bytes
+                      << ",\n\"partition\": \"" << (by_nnz ? "balanced non-zeros" : "reference rule ceil(n/parts)") << "\",\n\"parts\": [";
+            for (int p = 0; p < gather_parts; p++) {
+                const spmvb200_cache_misses & q = miss[(size_t)p];
+                std::cout << (p ? ",\n" : "\n") << "{\"first\": " << starts[(size_t)p] << ", \"end\": " << starts[(size_t)p + 1]
+                          << ", \"references\": " << q.references << ", \"x_references\": " << q.x_references
+                          << ", \"x_remote_references\": " << q.x_remote_references
+                          << ", \"misses\": {\"index\": " << q.misses_index << ", \"column_index\": " << q.misses_column_index
+                          << ", \"value\": " << q.misses_value << ", \"x_local\": " << q.misses_x_local << ", \"x_remote\": "
+                          << q.misses_x_remote << ", \"y_local\": " << q.misses_y_local << ", \"y_remote\": " << q.misses_y_remote
+                          << "}, \"x_gather_miss_bytes\": " << (q.misses_x_local + q.misses_x_remote) * (long long)line_bytes
+                          << ", \"predicted_dram_bytes\": "
+                          << (q.misses_index + q.misses_column_index + q.misses_value + q.misses_x_local + q.misses_x_remote +
+                              q.misses_y_local + q.misses_y_remote) * (long long)line_bytes << "}";
+            }
+            std::cout << "\n]\n}";
+        }
+        std::cout << "\n}\n";
     } catch (kernel_error const & e) {
         std::cerr << kernel->name() << ": " << e.what() << '\n';
         return EXIT_FAILURE;

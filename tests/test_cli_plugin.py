@@ -57,3 +57,24 @@ def test_cli_profile_mode(fmt, name, mfmt):
     assert doc["host_execution_time"]["samples"] == 5
     assert doc["roofline"]["bytes"] == k["matrix_size"] + k["x_size"] + k["y_size"]
     assert doc["roofline"]["flops"] == 2 * 2417
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["cuda-csr", "cuda-ell", "cuda-coo", "cuda-hybrid"])
+def test_cli_x_gather_report(fmt):
+    """--x-gather: the cache-model prediction for a 2-way partition, tiny cache so that x is re-fetched."""
+    p = run("--spmv-format", fmt, "--matrix", MTX, "--profile", "2", "--x-gather", "2", "--cache-bytes", "512",
+            "--line-bytes", "32")
+    assert p.returncode == 0, p.stderr
+    g = json.loads(p.stdout)["x_gather"]
+    assert g["cache_bytes"] == 512 and g["line_bytes"] == 32 and len(g["parts"]) == 2
+    stored = {"cuda-csr": 2417, "cuda-coo": 2417, "cuda-ell": 367 * 9, "cuda-hybrid": 367 * 7 + 83}[fmt]
+    assert sum(q["x_references"] for q in g["parts"]) == stored
+    for q in g["parts"]:
+        m = q["misses"]
+        assert q["x_gather_miss_bytes"] == 32 * (m["x_local"] + m["x_remote"]) > 0
+        assert q["predicted_dram_bytes"] == 32 * sum(m.values())
+    if fmt == "cuda-csr":  # balanced non-zeros: the two parts differ by less than one row
+        a, b = (q["x_references"] for q in g["parts"])
+        assert abs(a - b) <= 9
+        assert g["partition"] == "balanced non-zeros"
