@@ -57,7 +57,8 @@ def ncu_traffic(key: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(key)
+            v = json.load(f).get(key)
+            return int(v["read"] + v["write"]) if isinstance(v, dict) else v
     except Exception:
         return None
 

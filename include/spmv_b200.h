@@ -110,8 +110,10 @@ int spmvb200_set_global_option(const char *key, int64_t value);
  * Symmetry is parsed but entries are NOT expanded, like the reference. */
 int spmvb200_mm_parse(const char *text, size_t len, spmvb200_mm_t *out);
 /* matrix_market::load_matrix (matrix-market.cpp:777-861): .mtx, .gz, .tar.gz
- * and .tgz (member <name>/<name>.mtx, :755-757).  A "__RCM" / "__GP<n>" path
- * suffix (reordering, :786-802) is rejected with SPMVB200_ERR_UNSUPPORTED. */
+ * and .tgz (member <name>/<name>.mtx, :755-757).  A "__RCM" path suffix loads
+ * the file without the suffix and applies the reverse Cuthill-McKee order
+ * (:786-802); "__GP<n>" is accepted and, like the reference built without
+ * METIS, permutes nothing. */
 int spmvb200_mm_load(const char *path, spmvb200_mm_t *out);
 /* matrix_market::Matrix(Header, Comments, Size, vector<CoordinateEntryReal>)
  * (matrix-market.hpp:81-84); i, j are 1-based. */
@@ -132,6 +134,13 @@ int spmvb200_mm_row_lengths(spmvb200_mm_t mm, int32_t *lengths /* rows */);
  * in place and stable. */
 int spmvb200_mm_sort_row_major(spmvb200_mm_t mm);
 int spmvb200_mm_sort_column_major(spmvb200_mm_t mm);
+/* find_new_order_RCM (matrix/matrix-market-reorder.cpp:60-170): new_order[old index] = new index,
+ * `rows` entries; square real coordinate matrices only. */
+int spmvb200_mm_order_rcm(spmvb200_mm_t mm, int32_t *new_order);
+/* find_new_order_GP without METIS (matrix-market-reorder.cpp:172-180): the identity. */
+int spmvb200_mm_order_gp(spmvb200_mm_t mm, int32_t nparts, int32_t *new_order);
+/* Matrix::permute (matrix-market.cpp:309-333): i, j <- new_order[i-1]+1, new_order[j-1]+1. */
+int spmvb200_mm_permute(spmvb200_mm_t mm, const int32_t *new_order);
 void spmvb200_mm_free(spmvb200_mm_t mm);
 
 /* ---- device builders from Matrix Market entries ---------------------------- */

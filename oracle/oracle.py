@@ -444,6 +444,12 @@ class RefMatrix:
     def max_row_length(self):
         return int(self.ref.lib.ref_mm_max_row_length(self.h))
 
+    def order_rcm(self):
+        """find_new_order_RCM of the reference itself (new_order[old] = new)."""
+        out = np.zeros(max(self.info()["rows"], 1), np.int32)
+        self.ref._check(self.ref.lib.ref_mm_order_rcm(self.h, _ptr(out, _i32p)))
+        return out[: self.info()["rows"]]
+
     def sort_row_major(self):
         self.ref._check(self.ref.lib.ref_mm_sort_row_major(self.h))
         return self

@@ -19,6 +19,7 @@
 #include "matrix/hybrid-matrix.hpp"
 #include "matrix/matrix-error.hpp"
 #include "matrix/matrix-market.hpp"
+#include "matrix/matrix-market-reorder.hpp"
 #include "cache-simulation/replacement.hpp"
 
 #include <omp.h>
@@ -300,6 +301,17 @@ int ref_time(void * h, int T, int pin, int reps, double * ns)
                 #pragma omp barrier
             }
         }
+    });
+}
+
+/* find_new_order_RCM of the reference (matrix-market-reorder.cpp:60-170); out has `rows` entries.
+ * (The reference prints progress lines to stdout.) */
+int ref_mm_order_rcm(void * h, int32_t * out)
+{
+    return guarded([&] {
+        auto * m = static_cast<RefMatrix *>(h);
+        std::vector<int> order = find_new_order_RCM(*m->mm);
+        std::copy(order.begin(), order.end(), out);
     });
 }
 

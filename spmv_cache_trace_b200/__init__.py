@@ -152,6 +152,13 @@ class MatrixMarket:
         _check(_abi.lib().spmvb200_mm_row_lengths(self._h, _p(out, i32p)))
         return out[: self.rows]
 
+    def permute(self, new_order):
+        """Matrix::permute (matrix-market.cpp:309-333), in place: i, j <- new_order[i-1]+1, new_order[j-1]+1."""
+        order = _i32(new_order)
+        if order.size != self.rows:
+            raise matrix_error("The dimension of the matrix doesn't match")
+        _check(_abi.lib().spmvb200_mm_permute(self._h, _p(order, i32p)))
+
 
 class matrix_market:
     """namespace matrix_market"""
@@ -182,6 +189,20 @@ class matrix_market:
         _check(_abi.lib().spmvb200_mm_from_entries(rows, columns, len(i), _p(i, i32p), _p(j, i32p), _p(a, f64p),
                                                    C.byref(h)))
         return MatrixMarket(h)
+
+    @staticmethod
+    def find_new_order_RCM(m: MatrixMarket):
+        """matrix/matrix-market-reorder.cpp:60-170: new_order[old index] = new index."""
+        out = np.zeros(max(m.rows, 1), np.int32)
+        _check(_abi.lib().spmvb200_mm_order_rcm(m._h, _p(out, i32p)))
+        return out[: m.rows]
+
+    @staticmethod
+    def find_new_order_GP(m: MatrixMarket, nparts: int):
+        """matrix-market-reorder.cpp:172-180 (the reference without METIS): the identity."""
+        out = np.zeros(max(m.rows, 1), np.int32)
+        _check(_abi.lib().spmvb200_mm_order_gp(m._h, int(nparts), _p(out, i32p)))
+        return out[: m.rows]
 
     @staticmethod
     def _copy(m: MatrixMarket) -> MatrixMarket:

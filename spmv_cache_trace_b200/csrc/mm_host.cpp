@@ -250,12 +250,8 @@ int mm_parse_text(const char * text, size_t len, spmvb200_mm_s ** out)
     return 0;
 }
 
-int mm_load_path(const char * path_c, spmvb200_mm_s ** out)
+static int load_plain(const std::string & path, spmvb200_mm_s ** out)
 {
-    std::string path(path_c);
-    // "__RCM" / "__GP<n>" suffixes select a reordering in the reference (matrix-market.cpp:786-802)
-    if (path.rfind("__RCM") != std::string::npos || path.rfind("__GP") != std::string::npos)
-        return fail(SPMVB200_ERR_UNSUPPORTED, path + ": matrix reordering (__RCM / __GP) is not part of the SpMV path");
     std::string raw;
     int rc = read_file(path, raw);
     if (rc) return rc;
@@ -278,6 +274,35 @@ int mm_load_path(const char * path_c, spmvb200_mm_s ** out)
         return mm_parse_text(text.data(), text.size(), out);
     }
     return mm_parse_text(raw.data(), raw.size(), out);
+}
+
+int mm_load_path(const char * path_c, spmvb200_mm_s ** out)
+{
+    std::string path(path_c);
+    // "__RCM" / "__GP<n>" suffixes select a reordering (matrix-market.cpp:786-802): the suffix is cut off,
+    // the file is loaded, then the order is computed and applied (RCM first, then GP).
+    bool rcm = false, gp = false;
+    size_t pos = path.rfind("__RCM");
+    if (pos != std::string::npos) {
+        rcm = true;
+        path.erase(pos);
+    }
+    pos = path.rfind("__GP");
+    if (pos != std::string::npos) {
+        gp = true;  // without METIS the reference's graph-partitioning order is the identity
+        path.erase(pos);
+    }
+    (void)gp;
+    int rc = load_plain(path, out);
+    if (rc || !rcm) return rc;
+    std::vector<int32_t> order((size_t)(*out)->rows);
+    rc = mm_order_rcm(*out, order.data());
+    if (rc == 0) rc = mm_permute(*out, order.data());
+    if (rc) {
+        delete *out;
+        *out = nullptr;
+    }
+    return rc;
 }
 
 int mm_from_entries(int32_t rows, int32_t columns, int32_t n, const int32_t * i, const int32_t * j,

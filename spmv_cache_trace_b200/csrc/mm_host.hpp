@@ -26,5 +26,8 @@ int mm_from_entries(int32_t rows, int32_t columns, int32_t n, const int32_t * i,
                     const double * a, spmvb200_mm_s ** out);
 int mm_row_lengths(const spmvb200_mm_s * mm, int32_t * lengths);
 int mm_sort(spmvb200_mm_s * mm, bool row_major);
+// reorder_host.cpp
+int mm_order_rcm(const spmvb200_mm_s * mm, int32_t * new_order);
+int mm_permute(spmvb200_mm_s * mm, const int32_t * new_order);
 
 }  // namespace spmvb200
