@@ -347,7 +347,7 @@ def bench_main(args) -> int:
             "gflops": r["gflops"], "frac_of_8TBs_nominal_per_gpu": r["gbs"] / world / NOMINAL_HBM_GBS,
             "roofline": {"bound": "hbm", "achieved": per_rank_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": per_rank_bytes / t / 1e9 / peak, "traffic": None,
-                         "kernel": "csr_stream_kernel (per rank; step time includes the exchange)",
+                         "kernel": "csr_flat_kernel (per rank; step time includes the exchange)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_rank_bytes)},
             "e2e": {"value": B / (r["e2e_ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N, "ms_per_step": r["e2e_ms_per_step"],
