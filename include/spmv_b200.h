@@ -99,7 +99,13 @@ int spmvb200_device_props(int device, char *name, size_t name_cap, int *sm_count
 /* Total number of kernels this library has launched in this process. */
 int64_t spmvb200_launch_count(void);
 /* Process-wide switches.  "force_offsets64" = 1 makes every CSR built afterwards keep int64 row
- * offsets on the device (normally only when stored_entries >= 2^32) so that path can be tested. */
+ * offsets on the device (normally only when stored_entries >= 2^32) so that path can be tested.
+ * "coo.col_block_log2": the builders of SEGMENTED COO matrices and of the hybrid tail may store the
+ * row-sorted entries partitioned by column block (blocks of 2^k columns, rows ascending inside a block)
+ * so that a block's slice of x stays in L2; 0 (default) = automatic (only when x is larger than 1.5 L2
+ * and the extra sweeps over y cost less than the gather misses), -1 = never, k > 0 = always, with 2^k
+ * columns.  Exports restore the row-major order.  spmvb200_get_option(m, "coo.col_block_log2") tells
+ * what was applied to a matrix. */
 int spmvb200_set_global_option(const char *key, int64_t value);
 
 /* ---- host side: Matrix Market --------------------------------------------- */

@@ -18,6 +18,7 @@ namespace spmvb200 {
 static thread_local std::string g_error;
 static std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_off64{0};
+std::atomic<int64_t> g_coo_col_block_log2{0};
 
 void set_error(const std::string & msg) { g_error = msg; }
 int fail(int code, const std::string & msg)
@@ -293,6 +294,7 @@ int spmvb200_set_global_option(const char * key, int64_t value)
 {
     if (!key) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (!strcmp(key, "force_offsets64")) { g_force_off64 = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "coo.col_block_log2")) { g_coo_col_block_log2 = value; return 0; }
     return fail(SPMVB200_ERR_INVALID, std::string("unknown global option ") + key);
 }
 
@@ -677,16 +679,27 @@ int spmvb200_csr_export(spmvb200_matrix_t m, int64_t * row_ptr, int32_t * column
     return 0;
 }
 
-static int export_coo_arrays(Matrix * m, int32_t * row, int32_t * col, double * val)
+// device_order = false: the row-major order of the reference (a column-blocked matrix is sorted back first)
+static int export_coo_arrays(Matrix * m, int32_t * row, int32_t * col, double * val, bool device_order = false)
 {
     cudaStream_t s = m->stream;
     const size_t n = (size_t)m->coo_n;
     if (n) {
-        if (row) SPMV_CUDA(cudaMemcpyAsync(row, m->coo_row, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
-        if (col) SPMV_CUDA(cudaMemcpyAsync(col, m->coo_col, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
-        if (val) SPMV_CUDA(cudaMemcpyAsync(val, m->coo_val, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        const int32_t * dr = m->coo_row;
+        const int32_t * dc = m->coo_col;
+        const double * dv = m->coo_val;
+        Scratch<int32_t> r2, c2;
+        Scratch<double> v2;
+        if (m->coo_col_shift > 0 && !device_order) {
+            SPMV_TRY(r2.alloc(m->coo_n)); SPMV_TRY(c2.alloc(m->coo_n)); SPMV_TRY(v2.alloc(m->coo_n));
+            SPMV_TRY(coo_row_major_copy(m, r2.p, c2.p, v2.p));
+            dr = r2.p; dc = c2.p; dv = v2.p;
+        }
+        if (row) SPMV_CUDA(cudaMemcpyAsync(row, dr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+        if (col) SPMV_CUDA(cudaMemcpyAsync(col, dc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+        if (val) SPMV_CUDA(cudaMemcpyAsync(val, dv, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
     }
-    SPMV_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 
@@ -1096,6 +1109,10 @@ int spmvb200_set_option(spmvb200_matrix_t m, const char * key, int64_t value)
 int spmvb200_get_option(spmvb200_matrix_t m, const char * key, int64_t * value)
 {
     if (!m || !key || !value) return fail(SPMVB200_ERR_INVALID, "null argument");
+    if (!strcmp(key, "coo.col_block_log2")) {  // read-only: the column-block size the builder applied (0 = none)
+        *value = m->coo_col_shift;
+        return 0;
+    }
     int64_t * slot = option_slot(m, key);
     if (!slot) return fail(SPMVB200_ERR_INVALID, std::string("unknown option ") + key);
     *value = *slot;
@@ -1217,13 +1234,14 @@ int spmvb200_cache_trace(spmvb200_matrix_t m, const spmvb200_cache_config * cfg,
     }
     if (m->format == SPMVB200_COO) {
         std::vector<int32_t> row((size_t)std::max<int64_t>(m->coo_n, 1)), col((size_t)std::max<int64_t>(m->coo_n, 1));
-        SPMV_TRY(spmvb200_coo_export(m, row.data(), col.data(), nullptr));
+        SPMV_TRY(export_coo_arrays(m, row.data(), col.data(), nullptr, true));  // the order the kernel walks
         return spmvb200_cache_trace_coo(m->rows, m->cols, m->coo_n, row.data(), col.data(), cfg, out);
     }
     if (m->format == SPMVB200_HYB) {
         std::vector<int32_t> ecol((size_t)std::max<int64_t>(m->rows * m->ell_w, 1));
         std::vector<int32_t> row((size_t)std::max<int64_t>(m->coo_n, 1)), col((size_t)std::max<int64_t>(m->coo_n, 1));
-        SPMV_TRY(spmvb200_hyb_export(m, ecol.data(), nullptr, row.data(), col.data(), nullptr));
+        SPMV_TRY(export_ell_arrays(m, ecol.data(), nullptr));
+        SPMV_TRY(export_coo_arrays(m, row.data(), col.data(), nullptr, true));  // the order the kernel walks
         std::vector<spmvb200_cache_misses> tail((size_t)cfg->parts);
         spmvb200_cache_config c2 = *cfg;
         c2.starts = nullptr;  // the tail is cut by entries (hybrid-matrix.cpp:491-528)

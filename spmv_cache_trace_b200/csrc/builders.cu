@@ -471,7 +471,7 @@ static int hyb_from_csr_t(const Matrix * src, int skip, bool check_int32, Matrix
         SPMV_CUDA(cudaGetLastError());
     }
     SPMV_CUDA(cudaStreamSynchronize(s));
-    return 0;
+    return coo_column_blocks(dst);
 }
 
 int hyb_from_csr(const Matrix * src, int skip, bool check_int32, Matrix * dst)
@@ -525,6 +525,121 @@ __global__ void gather_kernel(int64_t n, const uint32_t * idx, const int32_t * c
     }
 }
 
+// ---- column-blocked order for matrices whose x does not fit in L2 -----------------------------------
+// With x several times larger than L2 the gathers of a row-sorted sweep miss (R-MAT 2^26: the COO kernel
+// read 64 GB for 33 GB of entries, profiles/r01_ncu_c4_hyb_warp4.txt).  The order of COO entries is
+// free, so the row-sorted entries are stably partitioned by column block (blocks of 2^shift columns,
+// at most L2/2 bytes of x each): inside a block the rows still ascend, so runs of equal rows stay
+// adjacent for the segmented reduce, the block's slice of x stays in L2 for the whole pass, and the
+// price is one sweep over y per block; the reorder is done only when that is a win (R-MAT 2^26 hybrid:
+// 12.9 -> 9.0 ms with 16 blocks of 2^22 columns, profiles/r01_sweep_k_coo_column_blocks.log).  Only applied when the row-sorted order has
+// ascending columns inside each row, so that a stable sort by row restores it exactly for export.
+extern std::atomic<int64_t> g_coo_col_block_log2;  // global option "coo.col_block_log2": -1 never, 0 auto, k block of 2^k columns
+
+__global__ void rowcol_sorted_kernel(int64_t n, const int32_t * row, const int32_t * col, int * unsorted)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        if (row[k] < row[k - 1] || (row[k] == row[k - 1] && col[k] < col[k - 1])) *unsorted = 1;
+}
+
+__global__ void block_key_kernel(int64_t n, const int32_t * col, int shift, unsigned char * key, uint32_t * idx)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        key[k] = (unsigned char)(col[k] >> shift);
+        idx[k] = (uint32_t)k;
+    }
+}
+
+__global__ void gather3_kernel(int64_t n, const uint32_t * idx, const int32_t * row, const int32_t * col, const double * val,
+                               int32_t * row2, int32_t * col2, double * val2)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = idx[k];
+        row2[k] = row[s];
+        col2[k] = col[s];
+        val2[k] = val[s];
+    }
+}
+
+int coo_column_blocks(Matrix * m)
+{
+    const int64_t opt = g_coo_col_block_log2.load();
+    const int64_t n = m->coo_n;
+    m->coo_col_shift = 0;
+    if (opt < 0 || n < 2 || n >= ((int64_t)1 << 32) || !m->coo_sorted) return 0;
+    int l2 = 0;
+    SPMV_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m->device));
+    int shift = (int)opt;
+    if (opt == 0) {
+        if (l2 <= 0 || 8 * m->cols <= (int64_t)l2 + l2 / 2) return 0;  // x fits (or nearly): nothing to gain
+        shift = 0;
+        while (((int64_t)16 << shift) <= l2 / 2) shift++;  // largest block with 8 * 2^shift <= L2/2
+    }
+    const int64_t nblocks = (m->cols + ((int64_t)1 << shift) - 1) >> shift;
+    if (nblocks < 2 || nblocks > 256) return 0;
+    // automatic: worth it when the gather misses saved (about 12 B per entry measured on R-MAT 2^26) outweigh
+    // the extra sweeps over y (a 32 B sector read + written per 4 rows, about half the rows touched per block)
+    if (opt == 0 && n * 12 <= nblocks * m->rows * 8) return 0;
+    cudaStream_t s = m->stream;
+    Scratch<int> flag;
+    SPMV_TRY(flag.alloc(1));
+    SPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+    rowcol_sorted_kernel<<<grid_for(n), 256, 0, s>>>(n, m->coo_row, m->coo_col, flag.p);
+    SPMV_CUDA(cudaGetLastError());
+    int unsorted = 0;
+    SPMV_CUDA(cudaMemcpyAsync(&unsorted, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    if (unsorted) return 0;
+    {
+        Scratch<unsigned char> key, key2, tmp;
+        Scratch<uint32_t> idx, idx2;
+        SPMV_TRY(key.alloc(n)); SPMV_TRY(key2.alloc(n)); SPMV_TRY(idx.alloc(n)); SPMV_TRY(idx2.alloc(n));
+        block_key_kernel<<<grid_for(n), 256, 0, s>>>(n, m->coo_col, shift, key.p, idx.p);
+        SPMV_CUDA(cudaGetLastError());
+        size_t tb = 0;
+        const int end_bit = bits_for(nblocks);
+        SPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, idx2.p, n, 0, end_bit, s));
+        SPMV_TRY(tmp.alloc((int64_t)tb));
+        SPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, idx2.p, n, 0, end_bit, s));
+        int32_t *row2 = nullptr, *col2 = nullptr;
+        double * val2 = nullptr;
+        SPMV_TRY(alloc_streamed(m, &row2, n));
+        SPMV_TRY(alloc_streamed(m, &col2, n));
+        SPMV_TRY(alloc_streamed(m, &val2, n));
+        gather3_kernel<<<grid_for(n), 256, 0, s>>>(n, idx2.p, m->coo_row, m->coo_col, m->coo_val, row2, col2, val2);
+        SPMV_CUDA(cudaGetLastError());
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        const int64_t cap = round_up(n, 4096) + kPadEntries;
+        cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
+        m->device_bytes -= cap * 16;
+        m->coo_row = row2; m->coo_col = col2; m->coo_val = val2;
+    }
+    m->coo_col_shift = shift;
+    return 0;
+}
+
+// Copies of the COO arrays back in row-major order (undoes coo_column_blocks): stable sort by row.
+int coo_row_major_copy(Matrix * m, int32_t * row2, int32_t * col2, double * val2)
+{
+    const int64_t n = m->coo_n;
+    cudaStream_t s = m->stream;
+    Scratch<uint32_t> idx, idx2;
+    Scratch<int32_t> key2;
+    Scratch<unsigned char> tmp;
+    SPMV_TRY(idx.alloc(n)); SPMV_TRY(idx2.alloc(n)); SPMV_TRY(key2.alloc(n));
+    iota_kernel<<<grid_for(n), 256, 0, s>>>(n, idx.p);
+    SPMV_CUDA(cudaGetLastError());
+    size_t tb = 0;
+    const int end_bit = bits_for(m->rows);
+    SPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, m->coo_row, key2.p, idx.p, idx2.p, n, 0, end_bit, s));
+    SPMV_TRY(tmp.alloc((int64_t)tb));
+    SPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, m->coo_row, key2.p, idx.p, idx2.p, n, 0, end_bit, s));
+    gather3_kernel<<<grid_for(n), 256, 0, s>>>(n, idx2.p, m->coo_row, m->coo_col, m->coo_val, row2, col2, val2);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int coo_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t n, int32_t * row, int32_t * col, double * val,
               int mode, bool already_sorted)
 {
@@ -572,6 +687,7 @@ int coo_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t n, int32_t * row, 
         m->coo_sorted = true;
     }
     SPMV_CUDA(cudaStreamSynchronize(s));
+    if (mode == SPMVB200_COO_SEGMENTED) SPMV_TRY(coo_column_blocks(m));
     return 0;
 }
 

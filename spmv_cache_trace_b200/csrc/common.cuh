@@ -89,6 +89,7 @@ struct spmvb200_matrix_s {
     double * coo_val = nullptr;
     int64_t coo_n = 0;
     bool coo_sorted = false;
+    int coo_col_shift = 0;  // > 0: entries are partitioned by column block of 2^shift columns, row-sorted inside a block
 
     // optional row range for the next launches (ELL): [range_begin, range_end), range_end <= 0 = all rows
     int64_t range_begin = 0, range_end = 0;
@@ -230,6 +231,8 @@ int coo_adopt(Matrix * m, int64_t rows, int64_t cols, int64_t n, int32_t * row, 
 int ell_from_csr(const Matrix * src, int skip_padding, bool check_int32, Matrix * dst);
 int hyb_from_csr(const Matrix * src, int skip_padding, bool check_int32, Matrix * dst);
 int coo_from_csr(const Matrix * src, int mode, Matrix * dst);
+int coo_column_blocks(Matrix * m);
+int coo_row_major_copy(Matrix * m, int32_t * row2, int32_t * col2, double * val2);
 int csr_from_entries_host(int64_t rows, int64_t cols, int64_t n, const int32_t * i, const int32_t * j,
                           const double * a, int32_t row_alignment, Matrix * dst);
 

@@ -366,6 +366,48 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
     assert np.array_equal(eh["ell_column_index"], OH.ell_column_index) and np.array_equal(eh["coo_value"], OH.coo_value)
 
 
+def test_column_blocked_coo_layout(oracle):
+    """The column-blocked order of SEGMENTED COO / the hybrid tail (for x larger than L2), forced at a small
+    block size: same products, exports restore the reference's row-major order bit for bit."""
+    rng = np.random.default_rng(21)
+    rows, cols = 3000, 5000
+    i, j, a = ragged_matrix(rng, rows, cols, long_rows=(5, 1500), long_len=3000, short_max=14, empty_every=11)
+    if 1 not in i:
+        i = np.concatenate([[1], i]).astype(np.int32); j = np.concatenate([[1], j]).astype(np.int32); a = np.concatenate([[0.5], a])
+    x = rng.uniform(-1, 1, cols)
+    O = oracle.csr(rows, cols, i, j, a)
+    yref = oracle.csr_spmv(O, x)
+    bound = oracle.csr_abs_rowsum(O, x)
+    mm = matrix_market.sort_matrix_row_major(matrix_market.from_entries(rows, cols, i, j, a))
+    plain_c = coo_matrix.from_matrix_market(mm, COO_SEGMENTED)
+    plain_h = hybrid_matrix.from_matrix_market(mm)
+    assert plain_c.get_option("coo.col_block_log2") == 0 and plain_h.get_option("coo.col_block_log2") == 0
+    sp.set_global_option("coo.col_block_log2", 9)  # 512-column blocks: 10 blocks
+    try:
+        C2 = coo_matrix.from_matrix_market(mm, COO_SEGMENTED)
+        H2 = hybrid_matrix.from_matrix_market(mm)
+        A2 = coo_matrix.from_matrix_market(mm, COO_ATOMIC)  # file order is never touched
+        U2 = coo_matrix.from_matrix_market(matrix_market.from_entries(rows, cols, i[::-1], j[::-1], a[::-1]), COO_SEGMENTED)
+    finally:
+        sp.set_global_option("coo.col_block_log2", 0)
+    assert C2.get_option("coo.col_block_log2") == 9 and H2.get_option("coo.col_block_log2") == 9
+    assert A2.get_option("coo.col_block_log2") == 0
+    assert U2.get_option("coo.col_block_log2") == 0  # columns descend inside the rows: not restorable, so not blocked
+    for name, B, P in (("coo", C2, plain_c), ("hybrid", H2, plain_h)):
+        for algo in (0, 1, 3, 4):
+            B.set_option("coo.algo", algo)
+            assert_within(B * x, yref, bound, f"column-blocked {name} coo.algo={algo}")
+        e, p = B.export(), P.export()
+        for k in e:
+            assert np.array_equal(e[k], p[k]), (name, k)
+    assert_within(U2 * x, yref, bound, "unsorted segmented")
+    # the cache model sees the order the kernel walks: blocked entries gather from one block at a time
+    small = 64 * 1024
+    m_plain = sp.cache_model.matrix(plain_c, small, 32, stream_bypass=True)[0]
+    m_block = sp.cache_model.matrix(C2, small, 32, stream_bypass=True)[0]
+    assert m_block["x_references"] == m_plain["x_references"]
+
+
 def test_forced_64bit_offsets(oracle):
     rng = np.random.default_rng(5)
     i, j, a = ragged_matrix(rng, 3000, 5000, long_rows=(10,), long_len=4000, short_max=12)

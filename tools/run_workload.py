@@ -40,8 +40,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--copies", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--gopt", action="append", default=[], help="global option key=value, set before the matrices are built")
     ap.add_argument("--sweep", action="append", default=[], help="key=v1,v2,... (cartesian product of all sweeps)")
     args = ap.parse_args()
+    for kv in args.gopt:
+        sp.set_global_option(kv.split("=")[0], int(kv.split("=")[1]))
     make = factory(args.workload)
     A = make()
     B = A.algorithmic_bytes()

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_xgather_model.json"))
     ap.add_argument("--workloads", default="c1_csr,c1_coo,c2_ell,c3s_coo,c3_coo,c5s_csr")
     ap.add_argument("--line", type=int, default=32)
+    ap.add_argument("--layout-experiment", action="store_true")
     args = ap.parse_args()
     l2 = sp.device_props(0)["l2_bytes"]
     try:
@@ -75,6 +76,27 @@ def main():
             }
             print(json.dumps(doc["partition_c5s_8"]), flush=True)
         del A
+    if args.layout_experiment:
+        # Config 4 at 1/16 scale (R-MAT 2^22 x 32, hybrid) with 1/16 of the L2: the row-sorted COO tail against the
+        # column-blocked one.  The model walks the entries in the order the kernel does.
+        cache = l2 // 16
+        exp = {"matrix": "R-MAT 2^22 x 32, hybrid (config 4 at 1/16 scale)", "cache_bytes": int(cache), "line_bytes": args.line,
+               "x_bytes": 8 << 22, "layouts": []}
+        for label, k in (("row-sorted tail", -1), ("column blocks of 2^18 (x block = cache/4)", 18),
+                         ("column blocks of 2^19 (x block = cache/2)", 19)):
+            sp.set_global_option("coo.col_block_log2", k)
+            try:
+                H = sp.generators.rmat(22, 32, 0x5EED0004, fmt=sp.HYB)
+            finally:
+                sp.set_global_option("coo.col_block_log2", 0)
+            r = sp.cache_model.matrix(H, cache, args.line, parts=1, shared=False, stream_bypass=True)[0]
+            exp["layouts"].append({"layout": label, "applied_log2": H.get_option("coo.col_block_log2"),
+                                   "x_gather_miss_bytes": (r["misses_x_local"] + r["misses_x_remote"]) * args.line,
+                                   "y_miss_bytes": (r["misses_y_local"] + r["misses_y_remote"]) * args.line,
+                                   "stream_bytes": (r["misses_index"] + r["misses_column_index"] + r["misses_value"]) * args.line})
+            print(json.dumps(exp["layouts"][-1]), flush=True)
+            del H
+        doc["layout_experiment"] = exp
     with open(args.out, "w") as f:
         json.dump(doc, f, indent=1)
 
