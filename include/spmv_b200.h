@@ -288,8 +288,10 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               this option is 1 = the caller promises that no kernel in flight writes this matrix's x.
  *               -1 = never overlap.
  *               "pdl" (default 1): programmatic dependent launch on/off.
- *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (default: split by
- *               non-zeros, 4 entries per lane, rows from span metadata); "csr.threads" 128|256 (algo 3, 4),
+ *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (split by non-zeros,
+ *               4 entries per lane, rows from span metadata), 5 sliced (lane per row on a slot-major copy of
+ *               the entries; "csr.batch" 2|4|8 slots in flight); 0 = automatic: sliced when the mean row has
+ *               >= 10 entries and the longest row <= 2x the mean, else flat; "csr.threads" 128|256 (algo 3, 4),
  *               32..256 (algo 1, 2); algo 1-3: "csr.lanes" 1|2|4|8 lanes per row; algo 1, 2: "csr.tile"
  *               256..2048, "csr.stages" 2|3, "csr.ctas_per_sm", "csr.spare_ctas" CTA slots per SM left
  *               free for a concurrent kernel.

@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "libspmvb200.so")
 CLI = os.path.join(HERE, "bin", "spmv-b200")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-CUDA_SOURCES = ["abi.cu", "kernels_csr.cu", "kernels_csr_warp.cu", "kernels_csr_flat.cu", "kernels_ell.cu", "kernels_coo.cu", "builders.cu", "generators.cu"]
+CUDA_SOURCES = ["abi.cu", "kernels_csr.cu", "kernels_csr_warp.cu", "kernels_csr_flat.cu", "kernels_csr_sliced.cu", "kernels_ell.cu", "kernels_coo.cu", "builders.cu", "generators.cu"]
 CXX_SOURCES = ["mm_host.cpp", "cache_model.cpp", "reorder_host.cpp"]
 HEADERS = ["common.cuh", "ptx.cuh", "launch.cuh", "segreduce.cuh", "mm_host.hpp", os.path.join(INCLUDE, "spmv_b200.h")]
 

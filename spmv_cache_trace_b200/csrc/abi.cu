@@ -1084,6 +1084,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.lanes")) return &m->opt_csr_lanes;
     if (!strcmp(key, "csr.ctas_per_sm")) return &m->opt_csr_ctas;
     if (!strcmp(key, "csr.spare_ctas")) return &m->opt_csr_spare;
+    if (!strcmp(key, "csr.batch")) return &m->opt_csr_batch;
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;
     if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;

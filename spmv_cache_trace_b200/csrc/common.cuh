@@ -76,6 +76,9 @@ struct spmvb200_matrix_s {
     int span_size = 0;
     int32_t * flat_meta = nullptr;  // flat kernel: {first row, -, -, -, 128-bit row-start mask} per 128-entry span
     bool flat_has_empty = false;    // some row is empty: the mask cannot describe the row starts
+    int32_t * slice_col = nullptr;  // sliced kernel: column_index / value with every 32-row slice stored slot-major
+    double * slice_val = nullptr;
+    bool slice_unavailable = false;  // the copy could not be allocated: automatic selection stays with the flat kernel
     int64_t csr_maxlen = -1;       // longest row (computed on first use)
 
     // ELL (column-major)
@@ -119,6 +122,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_lanes = 0;    // lanes per row in direct mode (1, 2, 4, 8), 0 = auto
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
+    int64_t opt_csr_batch = 0;    // sliced kernel: slots in flight per lane (2, 4, 8), 0 = auto
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto

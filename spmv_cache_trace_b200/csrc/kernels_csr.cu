@@ -391,6 +391,7 @@ static int launch_csr_t(Matrix * m, const CsrConfig & c)
 
 int launch_csr_warp(Matrix * m, int lanes);  // kernels_csr_warp.cu
 int launch_csr_flat(Matrix * m);             // kernels_csr_flat.cu
+int launch_csr_sliced(Matrix * m);           // kernels_csr_sliced.cu
 int csr_max_row_length(Matrix * m);          // builders.cu
 
 int launch_csr(Matrix * m)
@@ -402,6 +403,22 @@ int launch_csr(Matrix * m)
     // Automatic = flat: fastest on every matrix measured (profiles/r01_sweep_j_csr_flat.log: 2D 5-point
     // 14.3 vs 16.2 us, 3D 7-point 35.0 vs 38.1 us, 27-point 256^3 1.01 vs 1.07 ms, R-MAT 2^24 1.18 vs
     // 1.55 ms for the best of the others).
+    // 5 sliced (lane per row on a slot-major copy; kernels_csr_sliced.cu): automatic for long regular rows
+    // (mean >= 10 entries, longest row <= 2x the mean), where the flat kernel's gathers saturate the L1.
+    if (m->opt_csr_algo == 5) return launch_csr_sliced(m);
+    if (m->opt_csr_algo == 0) {
+        const int64_t avg = m->stored / std::max<int64_t>(m->rows, 1);
+        if (avg >= 10) {
+            SPMV_TRY(csr_max_row_length(m));
+            if (m->csr_maxlen <= 2 * avg && !m->slice_unavailable) {
+                const int rc = launch_csr_sliced(m);
+                if (rc == 0 || m->slice_col) return rc;
+                // no room for the second copy of the entries: the flat kernel needs only 0.25 B per entry
+                m->slice_unavailable = true;
+                cudaGetLastError();
+            }
+        }
+    }
     if (m->opt_csr_algo == 0 || m->opt_csr_algo == 4) return launch_csr_flat(m);
     const bool warp = m->opt_csr_algo == 3;
     if (warp) return launch_csr_warp(m, c.lanes > 0 ? c.lanes : 8);

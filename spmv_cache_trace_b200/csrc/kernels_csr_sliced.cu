@@ -1,0 +1,143 @@
+// kernels_csr_sliced.cu -- CSR SpMV with a lane-per-row mapping on a slice-interleaved copy:  y += A*x.
+//
+// Same job as csr_flat_kernel (reference matrix/csr-matrix-spmv.cpp:21-33, 63-76) for matrices whose rows
+// are long and regular (wide stencils).  There the flat kernel is bound by the L1, not by HBM: a lane's
+// four consecutive entries of a 27-wide row gather x from ~17 sectors per instruction (l1tex 99 % busy,
+// profiles/r01_ncu_c5s_csr_flat.txt), whereas the ELL kernel, whose 32 lanes hold 32 consecutive ROWS of
+// one slot, touches 8 full sectors and runs the same matrix at 6.76 TB/s against 5.67 TB/s.
+//
+// This kernel gives CSR that mapping without ELL's padding.  The builder keeps a second copy of
+// column_index / value in which the entries of every slice of 32 consecutive rows are stored SLOT-MAJOR:
+// first the first entries of all rows of the slice that have one (ascending row), then the second
+// entries, and so on.  A slice holds exactly the entries it holds in plain CSR, so row_ptr[32 s] is also
+// the slice's offset in the copy, the copy has `stored` entries, and no byte of padding exists.  Lane i
+// of a warp owns row 32 s + i; for slot l the lanes whose row is longer than l read consecutive
+// addresses (position = slice offset + entries of earlier slots + rank of the lane among the active
+// ones, from one ballot and two popcounts), gather x from consecutive rows -- adjacent columns for a
+// banded matrix -- and add the product to their row's sum strictly left to right with separate
+// multiply/add roundings: bit-identical to the reference's loop for every row.
+//
+// Chosen automatically when the mean row length is at least 10 and the longest row at most twice the
+// mean (lanes idle while the longest row of their slice finishes); "csr.algo" = 5 forces it.
+#include "common.cuh"
+#include "launch.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <climits>
+
+namespace spmvb200 {
+
+using namespace ptx;
+
+// One warp per slice: copy the slice's entries from row-major to slot-major order.
+template <typename OffT>
+__global__ void csr_slice_fill_kernel(int64_t rows, const OffT * __restrict__ rp, const int32_t * __restrict__ col,
+                                      const double * __restrict__ val, int32_t * __restrict__ scol, double * __restrict__ sval)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // row (blockDim is a multiple of 32)
+    if (i - lane >= rows) return;
+    const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
+    const int len = (int)min(hi - lo, (int64_t)INT_MAX);
+    int64_t pos = __shfl_sync(0xffffffffu, lo, 0);
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    for (int l = 0; l < maxlen; ++l) {
+        const bool active = len > l;
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const int64_t p = pos + __popc(mask & ((1u << lane) - 1u));
+            scol[p] = col[lo + l];
+            sval[p] = val[lo + l];
+        }
+        pos += __popc(mask);
+    }
+}
+
+// U = slots whose matrix loads are in flight together
+template <typename OffT, int U>
+__global__ void __launch_bounds__(128, U <= 4 ? 16 : 8)
+csr_sliced_kernel(int64_t rows, int independent, const OffT * __restrict__ rp, const int32_t * __restrict__ scol,
+                  const double * __restrict__ sval, const double * __restrict__ x, double * __restrict__ y)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i - lane >= rows) return;  // whole warp past the end
+    const uint64_t pol = policy_evict_first();
+    const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
+    const int len = (int)min(hi - lo, (int64_t)INT_MAX);
+    int64_t pos = __shfl_sync(0xffffffffu, lo, 0);  // offset of the slice = row_ptr of its first row
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    const unsigned below = (1u << lane) - 1u;
+    double z = 0.0;
+    bool waited = independent != 0;
+    for (int l0 = 0; l0 < maxlen; l0 += U) {
+        int c[U];
+        double a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // warp-uniform trip count: every lane takes part in the ballots
+            const bool active = len > l0 + u;
+            const unsigned mask = __ballot_sync(0xffffffffu, active);
+            const int64_t p = pos + __popc(mask & below);
+            c[u] = active ? ldg_stream_i1(scol + p, pol) : 0;
+            a[u] = active ? ldg_stream_d1(sval + p, pol) : 0.0;
+            pos += __popc(mask);
+        }
+        if (!waited) {  // the matrix is immutable; x and y may come from the previous launch
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            waited = true;
+        }
+        double xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = len > l0 + u ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (len > l0 + u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
+    }
+    if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (len > 0) red_add_f64(y + i, z);
+}
+
+static int csr_build_sliced(Matrix * m)
+{
+    if (m->slice_col && m->slice_val) return 0;
+    int rc = alloc_streamed(m, &m->slice_col, m->stored);
+    if (rc == 0) rc = alloc_streamed(m, &m->slice_val, m->stored);
+    if (rc) {  // leave nothing half-built behind
+        if (m->slice_col) cudaFree(m->slice_col);
+        m->slice_col = nullptr;
+        m->slice_val = nullptr;
+        return rc;
+    }
+    const unsigned grid = (unsigned)((m->rows + 127) / 128);
+    if (m->off64) csr_slice_fill_kernel<int64_t><<<grid, 128, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, m->col, m->val, m->slice_col, m->slice_val);
+    else csr_slice_fill_kernel<uint32_t><<<grid, 128, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, m->col, m->val, m->slice_col, m->slice_val);
+    SPMV_CUDA(cudaGetLastError());
+    m->aux_dirty = true;
+    return 0;
+}
+
+int launch_csr_sliced(Matrix * m)
+{
+    SPMV_TRY(csr_build_sliced(m));
+    m->kernel_name = "csr_sliced_kernel";
+    if (m->dry_run) return 0;
+    const int64_t grid = (m->rows + 127) / 128;
+    if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
+    const RunMode rm = run_mode(m);
+    const int batch = (int)(m->opt_csr_batch ? m->opt_csr_batch : 4);
+#define SPMV_SLICED(OFF, UU)                                                                                              \
+    SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU>, (unsigned)grid, 128u, 0, m->stream, rm.pdl, m->rows, rm.independent, \
+                            (const OFF *)m->rp, (const int32_t *)m->slice_col, (const double *)m->slice_val,            \
+                            (const double *)m->x, m->y))
+    if (batch == 4) { if (m->off64) SPMV_SLICED(int64_t, 4); else SPMV_SLICED(uint32_t, 4); }
+    else if (batch == 8) { if (m->off64) SPMV_SLICED(int64_t, 8); else SPMV_SLICED(uint32_t, 8); }
+    else if (batch == 2) { if (m->off64) SPMV_SLICED(int64_t, 2); else SPMV_SLICED(uint32_t, 2); }
+    else return fail(SPMVB200_ERR_INVALID, "csr.batch must be 2, 4 or 8");
+#undef SPMV_SLICED
+    count_launch();
+    return 0;
+}
+
+}  // namespace spmvb200

@@ -335,7 +335,7 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
                                                (256, 1024, 2, 8, 0), (256, 2048, 3, 1, 0), (256, 2048, 2, 0, 2),
                                                (128, 512, 2, 0, 2), (256, 1024, 3, 0, 2), (128, 0, 0, 1, 3),
                                                (256, 0, 0, 2, 3), (64, 0, 0, 0, 4), (128, 0, 0, 0, 4), (256, 0, 0, 0, 4),
-                                               (0, 0, 0, 0, 0)):
+                                               (0, 0, 0, 0, 5), (0, 0, 0, 0, 0)):
         A.set_option("csr.threads", threads)
         A.set_option("csr.tile", tile)
         A.set_option("csr.stages", stages)
@@ -419,7 +419,7 @@ def test_forced_64bit_offsets(oracle):
         A = csr_matrix.from_matrix_market(matrix_market.from_entries(3000, 5000, i, j, a))
         assert A.info.offsets_64bit == 1
         assert np.array_equal(A.export()["row_ptr"], O.row_ptr)
-        for algo in (0, 1, 3, 4):
+        for algo in (0, 1, 3, 4, 5):
             A.set_option("csr.algo", algo)
             assert_within(A * x, yref, oracle.csr_abs_rowsum(O, x), f"csr int64 offsets, csr.algo={algo}")
         E = A.convert(sp.ELL)
@@ -518,7 +518,7 @@ def test_config1_poisson2d_1000x1000_full_size(oracle, fmt):
         # integer-valued data: every partial sum is exact, any order gives the same bits
         assert np.array_equal(y, yref)
     if fmt == sp.CSR:  # every CSR kernel at full size
-        for algo in (1, 2, 3, 4):
+        for algo in (1, 2, 3, 4, 5):
             A.set_option("csr.algo", algo)
             assert np.array_equal(A * x, yref), f"csr.algo={algo}"
 
@@ -551,6 +551,11 @@ def test_config2_poisson3d_128_ell_full_size(oracle):
     for algo in (3, 4, 0):
         C.set_option("csr.algo", algo)
         assert_within(C * x, yref, oracle.csr_abs_rowsum(O, x), f"config 2 csr.algo={algo}")
+    # the sliced kernel sums every row strictly left to right: bit-identical for every row
+    C.set_option("csr.algo", 5)
+    for batch in (2, 4, 8):
+        C.set_option("csr.batch", batch)
+        assert np.array_equal(C * x, yref), f"sliced, csr.batch={batch}"
 
 
 def test_rmat_cross_format_agreement_and_linearity(oracle):
