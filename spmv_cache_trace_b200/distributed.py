@@ -289,7 +289,8 @@ def bench_main(args) -> int:
         results[mode] = {"ms_per_step": t * 1e3, "gbs": B / t / 1e9, "gflops": 2.0 * nnz / t / 1e9,
                          "recv_bytes_per_step_per_rank": eng.plan.recv_bytes, "plan": eng.plan.mode,
                          "row_blocks": [(b, e2, r) for _, b, e2, r in eng.blocks],
-                         "gpu_launches": int(sp.launch_count() - launches0), "x_norm": xnorm}
+                         "gpu_launches": int(sp.launch_count() - launches0), "x_norm": xnorm,
+                         "kernel": max(eng.blocks, key=lambda t: t[2] - t[1])[0].kernel_name}
         # end to end: this rank's slice of x from pinned host memory each step, its slice of y back
         hx = torch.empty(e - s, dtype=torch.float64).pin_memory()
         hy = torch.empty(e - s, dtype=torch.float64).pin_memory()
@@ -347,7 +348,7 @@ def bench_main(args) -> int:
             "gflops": r["gflops"], "frac_of_8TBs_nominal_per_gpu": r["gbs"] / world / NOMINAL_HBM_GBS,
             "roofline": {"bound": "hbm", "achieved": per_rank_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": per_rank_bytes / t / 1e9 / peak, "traffic": None,
-                         "kernel": "csr_flat_kernel (per rank; step time includes the exchange)",
+                         "kernel": r.get("kernel", "csr kernel") + " (per rank; step time includes the exchange)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_rank_bytes)},
             "e2e": {"value": B / (r["e2e_ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N, "ms_per_step": r["e2e_ms_per_step"],
