@@ -290,7 +290,9 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               "pdl" (default 1): programmatic dependent launch on/off.
  *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (split by non-zeros,
  *               4 entries per lane, rows from span metadata), 5 sliced (lane per row on a slot-major copy of
- *               the entries; "csr.batch" 2|4|8 slots in flight); 0 = automatic: sliced when the mean row has
+ *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" 1 = free the row-major
+ *               column_index/value once that copy exists -- they are rebuilt on demand by export, convert,
+ *               row_block, column_span and the other kernels); 0 = automatic: sliced when the mean row has
  *               >= 10 entries and the longest row <= 2x the mean, else flat; "csr.threads" 128|256 (algo 3, 4),
  *               32..256 (algo 1, 2); algo 1-3: "csr.lanes" 1|2|4|8 lanes per row; algo 1, 2: "csr.tile"
  *               256..2048, "csr.stages" 2|3, "csr.ctas_per_sm", "csr.spare_ctas" CTA slots per SM left
@@ -304,6 +306,8 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               pinned host y directly; 2 = y up by DMA in "host.chunks" row chunks, results stored by
  *               the kernel; 0 = copies only ("host.chunks" > 1 pipelines them). */
 int spmvb200_set_option(spmvb200_matrix_t m, const char *key, int64_t value);
+/* Also answers the read-only keys "coo.col_block_log2" (what the builder applied) and
+ * "last_launch.overlapped" / "last_launch.pdl" (how the library ordered the last kernel of this matrix). */
 int spmvb200_get_option(spmvb200_matrix_t m, const char *key, int64_t *value);
 /* Name of the kernel spmvb200_spmv launches for this matrix. */
 const char *spmvb200_kernel_name(spmvb200_matrix_t m);

@@ -600,6 +600,7 @@ int spmvb200_convert(spmvb200_matrix_t src, int32_t format, int32_t arg, spmvb20
     if (!out) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (src->format != SPMVB200_CSR || src->row_alignment != 1)
         return fail(SPMVB200_ERR_UNSUPPORTED, "conversion source must be an unpadded CSR matrix");
+    SPMV_TRY(csr_ensure_row_major(src));
     SPMV_CUDA(cudaStreamSynchronize(src->stream));
     return convert_from_csr(src, format, arg, false, out);
 }
@@ -661,6 +662,7 @@ int spmvb200_csr_export(spmvb200_matrix_t m, int64_t * row_ptr, int32_t * column
 {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_CSR) return fail(SPMVB200_ERR_INVALID, "not a CSR matrix");
+    if (column_index || value) SPMV_TRY(csr_ensure_row_major(m));
     cudaStream_t s = m->stream;
     if (row_ptr) {
         if (m->off64) {
@@ -1085,6 +1087,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.ctas_per_sm")) return &m->opt_csr_ctas;
     if (!strcmp(key, "csr.spare_ctas")) return &m->opt_csr_spare;
     if (!strcmp(key, "csr.batch")) return &m->opt_csr_batch;
+    if (!strcmp(key, "csr.drop_row_major")) return &m->opt_csr_drop;
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;
     if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;
@@ -1112,6 +1115,14 @@ int spmvb200_get_option(spmvb200_matrix_t m, const char * key, int64_t * value)
     if (!m || !key || !value) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (!strcmp(key, "coo.col_block_log2")) {  // read-only: the column-block size the builder applied (0 = none)
         *value = m->coo_col_shift;
+        return 0;
+    }
+    if (!strcmp(key, "last_launch.overlapped")) {  // read-only: the last kernel was allowed to skip griddepcontrol.wait
+        *value = m->run_independent ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(key, "last_launch.pdl")) {  // read-only: ... was launched with the PDL attribute
+        *value = m->run_pdl ? 1 : 0;
         return 0;
     }
     int64_t * slot = option_slot(m, key);
@@ -1158,6 +1169,7 @@ int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col
 {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_CSR) return fail(SPMVB200_ERR_INVALID, "not a CSR matrix");
+    SPMV_TRY(csr_ensure_row_major(m));
     Scratch<long long> d;
     SPMV_TRY(d.alloc(4));
     long long h[4] = {LLONG_MAX, -1, 0, (long long)m->rows};
@@ -1181,6 +1193,7 @@ int spmvb200_csr_row_block(spmvb200_matrix_t src, int64_t row_begin, int64_t row
     SPMV_TRY(check(src));
     if (!out || src->format != SPMVB200_CSR || row_begin < 0 || row_end > src->rows || row_begin > row_end)
         return fail(SPMVB200_ERR_INVALID, "bad argument");
+    SPMV_TRY(csr_ensure_row_major(src));
     cudaStream_t s0 = src->stream;
     SPMV_CUDA(cudaStreamSynchronize(s0));
     int64_t first = 0, last = 0;

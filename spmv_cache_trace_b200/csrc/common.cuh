@@ -123,6 +123,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
     int64_t opt_csr_batch = 0;    // sliced kernel: slots in flight per lane (2, 4, 8), 0 = auto
+    int64_t opt_csr_drop = 0;     // sliced kernel: 1 = free the row-major column_index/value once the slot-major copy exists
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto
@@ -222,6 +223,9 @@ int launch_csr(Matrix * m);
 int launch_ell(Matrix * m, bool accumulate_into_y);
 int launch_coo(Matrix * m);
 int csr_build_tiles(Matrix * m);  // (re)build tile_row for the configured tile size
+// The row-major column_index / value of a CSR matrix may have been dropped in favour of the slot-major copy
+// ("csr.drop_row_major"); everything that reads them calls this first (rebuilds them from the copy).
+int csr_ensure_row_major(Matrix * m);
 
 // ---- builders.cu -----------------------------------------------------------------------------
 int matrix_new(Matrix ** out);

@@ -419,6 +419,7 @@ int launch_csr(Matrix * m)
             }
         }
     }
+    SPMV_TRY(csr_ensure_row_major(m));  // every other kernel walks the row-major arrays
     if (m->opt_csr_algo == 0 || m->opt_csr_algo == 4) return launch_csr_flat(m);
     const bool warp = m->opt_csr_algo == 3;
     if (warp) return launch_csr_warp(m, c.lanes > 0 ? c.lanes : 8);

@@ -55,6 +55,50 @@ __global__ void csr_slice_fill_kernel(int64_t rows, const OffT * __restrict__ rp
 }
 
 // U = slots whose matrix loads are in flight together
+// The inverse of csr_slice_fill_kernel.
+template <typename OffT>
+__global__ void csr_slice_unfill_kernel(int64_t rows, const OffT * __restrict__ rp, const int32_t * __restrict__ scol,
+                                        const double * __restrict__ sval, int32_t * __restrict__ col, double * __restrict__ val)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i - lane >= rows) return;
+    const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
+    const int len = (int)min(hi - lo, (int64_t)INT_MAX);
+    int64_t pos = __shfl_sync(0xffffffffu, lo, 0);
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    for (int l = 0; l < maxlen; ++l) {
+        const bool active = len > l;
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const int64_t p = pos + __popc(mask & ((1u << lane) - 1u));
+            col[lo + l] = scol[p];
+            val[lo + l] = sval[p];
+        }
+        pos += __popc(mask);
+    }
+}
+
+int csr_ensure_row_major(Matrix * m)
+{
+    if (m->format != SPMVB200_CSR || (m->col && m->val)) return 0;
+    if (!m->slice_col || !m->slice_val) return fail(SPMVB200_ERR_INVALID, "CSR matrix holds neither copy of its entries");
+    int rc = alloc_streamed(m, &m->col, m->stored);
+    if (rc == 0) rc = alloc_streamed(m, &m->val, m->stored);
+    if (rc) {
+        if (m->col) cudaFree(m->col);
+        m->col = nullptr;
+        m->val = nullptr;
+        return rc;
+    }
+    const unsigned grid = (unsigned)((m->rows + 127) / 128);
+    if (m->off64) csr_slice_unfill_kernel<int64_t><<<grid, 128, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, m->slice_col, m->slice_val, m->col, m->val);
+    else csr_slice_unfill_kernel<uint32_t><<<grid, 128, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, m->slice_col, m->slice_val, m->col, m->val);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
 template <typename OffT, int U>
 __global__ void __launch_bounds__(128, U <= 4 ? 16 : 8)
 csr_sliced_kernel(int64_t rows, int independent, const OffT * __restrict__ rp, const int32_t * __restrict__ scol,
@@ -99,9 +143,22 @@ csr_sliced_kernel(int64_t rows, int independent, const OffT * __restrict__ rp, c
     if (len > 0) red_add_f64(y + i, z);
 }
 
+static int csr_drop_row_major(Matrix * m)
+{
+    if (!m->opt_csr_drop || !m->col || !m->slice_col) return 0;
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));  // the fill kernel reads them
+    const int64_t cap = round_up(m->stored, 4096) + kPadEntries;
+    cudaFree(m->col);
+    cudaFree(m->val);
+    m->col = nullptr;
+    m->val = nullptr;
+    m->device_bytes -= cap * 12;
+    return 0;
+}
+
 static int csr_build_sliced(Matrix * m)
 {
-    if (m->slice_col && m->slice_val) return 0;
+    if (m->slice_col && m->slice_val) return csr_drop_row_major(m);
     int rc = alloc_streamed(m, &m->slice_col, m->stored);
     if (rc == 0) rc = alloc_streamed(m, &m->slice_val, m->stored);
     if (rc) {  // leave nothing half-built behind
@@ -115,7 +172,7 @@ static int csr_build_sliced(Matrix * m)
     else csr_slice_fill_kernel<uint32_t><<<grid, 128, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, m->col, m->val, m->slice_col, m->slice_val);
     SPMV_CUDA(cudaGetLastError());
     m->aux_dirty = true;
-    return 0;
+    return csr_drop_row_major(m);
 }
 
 int launch_csr_sliced(Matrix * m)

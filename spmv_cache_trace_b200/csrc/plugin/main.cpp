@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -30,6 +31,42 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+// Number of entries of "thread_affinities" in a reference trace-config file (src/trace-config.cpp:263-343):
+// the only thing a GPU kernel takes from it (one OpenMP thread per entry enters prepare()/run()).
+// Returns 0 when the file cannot be read or has no such array.
+static int trace_config_threads(std::string const & path)
+{
+    FILE * f = std::fopen(path.c_str(), "rb");
+    if (!f) return 0;
+    std::string text;
+    char buf[4096];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    std::fclose(f);
+    size_t pos = text.find("\"thread_affinities\"");
+    if (pos == std::string::npos) return 0;
+    pos = text.find('[', pos);
+    if (pos == std::string::npos) return 0;
+    int depth = 0, count = 0;
+    bool in_string = false;
+    for (size_t k = pos; k < text.size(); k++) {
+        const char ch = text[k];
+        if (in_string) {
+            if (ch == '\\') k++;
+            else if (ch == '"') in_string = false;
+            continue;
+        }
+        if (ch == '"') in_string = true;
+        else if (ch == '[' || ch == '{') {
+            if (ch == '{' && depth == 1) count++;
+            depth++;
+        } else if (ch == ']' || ch == '}') {
+            if (--depth == 0) break;
+        }
+    }
+    return count;
+}
 
 static void print_sample(std::ostream & o, std::vector<double> v, const char * unit)
 {
@@ -66,8 +103,9 @@ int main(int argc, char ** argv)
     bool verbose = false;
     static option longopts[] = {{"spmv-format", required_argument, nullptr, 'f'}, {"matrix", required_argument, nullptr, 'm'},
                                 {"profile", required_argument, nullptr, 'p'}, {"threads", required_argument, nullptr, 't'},
-                                {"x-gather", required_argument, nullptr, 'x'}, {"cache-bytes", required_argument, nullptr, 'c'},
-                                {"line-bytes", required_argument, nullptr, 'l'},
+                                {"x-gather", required_argument, nullptr, 'x'}, {"cache-bytes", required_argument, nullptr, 1001},
+                                {"line-bytes", required_argument, nullptr, 'l'}, {"trace-config", required_argument, nullptr, 'c'},
+                                {"warmup", no_argument, nullptr, 1002}, {"flush-caches", no_argument, nullptr, 1003},
                                 {"verbose", no_argument, nullptr, 'v'}, {"help", no_argument, nullptr, 'h'},
                                 {nullptr, 0, nullptr, 0}};
     int c;
@@ -78,11 +116,22 @@ int main(int argc, char ** argv)
         case 'p': profile = std::atoi(optarg); break;
         case 't': threads = std::max(1, std::atoi(optarg)); break;
         case 'x': gather_parts = std::max(1, std::atoi(optarg)); break;
-        case 'c': cache_bytes = std::atoll(optarg); break;
+        case 1001: cache_bytes = std::atoll(optarg); break;
+        case 'c': {  // the reference's mandatory -c/--trace-config (main.cpp:152-153): only its thread count matters here
+            const int t = trace_config_threads(optarg);
+            if (t <= 0) {
+                std::cerr << "spmv-b200: " << optarg << ": no thread_affinities found\n";
+                return EXIT_FAILURE;
+            }
+            threads = t;
+            break;
+        }
+        case 1002: case 1003: break;  // --warmup / --flush-caches of the reference: a warm-up run is always done, and
+                                      // cache flushing is a CPU notion (the L2-cold protocol lives in bench.py)
         case 'l': line_bytes = std::max(1, std::atoi(optarg)); break;
         case 'v': verbose = true; break;
         default:
-            std::cout << "Usage: spmv-b200 --spmv-format FMT --matrix PATH [--profile N] [--threads T] [--verbose]\n"
+            std::cout << "Usage: spmv-b200 --spmv-format FMT --matrix PATH [--profile N] [--threads T | -c TRACE_CONFIG] [--verbose]\n"
                          "                 [--x-gather PARTS [--cache-bytes B] [--line-bytes L]]\n"
                          "  FMT: cuda-csr, cuda-coo, cuda-coo-atomic, cuda-ell, cuda-hybrid\n"
                          "  --x-gather PARTS  cache-model prediction of the x-gather misses for a PARTS-way partition\n"

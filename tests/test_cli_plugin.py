@@ -30,6 +30,14 @@ def test_cli_usage_and_errors():
     assert p.stderr.startswith("cuda-ell-spmv: /no/such/file.mtx: ")
 
 
+def test_cli_accepts_the_reference_trace_config(tmp_path):
+    """-c/--trace-config is mandatory in the reference CLI (main.cpp:152-153); here only its thread count matters."""
+    bad = tmp_path / "cfg.json"
+    bad.write_text('{"trace-config": {"caches": {}, "numa_domains": []}}')
+    p = run("--spmv-format", "cuda-csr", "--matrix", MTX, "-c", str(bad))
+    assert p.returncode != 0 and "no thread_affinities" in p.stderr
+
+
 def test_cli_bad_matrix_market(tmp_path):
     bad = tmp_path / "bad.mtx"
     bad.write_text("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n")
@@ -57,6 +65,22 @@ def test_cli_profile_mode(fmt, name, mfmt):
     assert doc["host_execution_time"]["samples"] == 5
     assert doc["roofline"]["bytes"] == k["matrix_size"] + k["x_size"] + k["y_size"]
     assert doc["roofline"]["flops"] == 2 * 2417
+
+
+@pytest.mark.gpu
+def test_cli_with_readme_trace_config(tmp_path):
+    cfg = tmp_path / "trace-config.json"  # the README's two-thread hierarchy (README.md:53-66)
+    cfg.write_text("""{"trace-config": {"caches": {
+      "L1-0": {"size": 32768, "line_size": 64, "parent": "L2-0"}, "L1-1": {"size": 32768, "line_size": 64, "parent": "L2-1"},
+      "L2-0": {"size": 262144, "line_size": 64, "parent": "L3"}, "L2-1": {"size": 262144, "line_size": 64, "parent": "L3"},
+      "L3": {"size": 20971520, "line_size": 64, "parent": null}},
+      "numa_domains": ["a [string] with {braces}"],
+      "thread_affinities": [{"thread": 0, "cpu": 0, "cache": "L1-0", "numa_domain": 0},
+                            {"thread": 1, "cpu": 1, "cache": "L1-1", "numa_domain": 1}]}}""")
+    p = run("--spmv-format", "cuda-ell", "-m", MTX, "-c", str(cfg), "-p", "3", "--warmup", "--flush-caches")
+    assert p.returncode == 0, p.stderr
+    doc = json.loads(p.stdout)
+    assert doc["execution_time"]["samples"] == 3 and doc["kernel"]["name"] == "cuda-ell-spmv"
 
 
 @pytest.mark.gpu

@@ -628,6 +628,74 @@ def test_row_partition_concatenates_to_the_full_product(oracle, P):
         assert csr_matrix.spmv_nonzeros_per_thread(A, t, P) == oracle.csr_nonzeros_per_thread(O.row_ptr, N, t, P)
 
 
+def test_sliced_csr_can_drop_and_rebuild_the_row_major_copy(oracle):
+    n = 40
+    i, j, a = stencil_entries(2, n, n, n)  # 27-point: the sliced kernel is the automatic choice
+    N = n ** 3
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, N)
+    O = oracle.csr(N, N, i, j, a)
+    yref = oracle.csr_spmv(O, x)
+    A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+    full = A.info.device_bytes
+    A.set_option("csr.drop_row_major", 1)
+    y = A * x
+    assert A.kernel_name == "csr_sliced_kernel"
+    assert np.array_equal(y, yref)  # strictly left-to-right sums: bit-identical
+    after = A.info.device_bytes
+    assert after < full + 12 * A.num_entries // 2  # one copy of the entries, not two
+    # everything that needs the row-major arrays rebuilds them first
+    e = A.export()
+    assert np.array_equal(e["row_ptr"], O.row_ptr) and np.array_equal(e["column_index"], O.column_index)
+    assert np.array_equal(e["value"], O.value)
+    assert np.array_equal(A * x, yref)  # drops them again
+    B = A.row_block(N // 3, 2 * N // 3)
+    assert np.array_equal(B * x, yref[N // 3: 2 * N // 3])
+    assert np.array_equal(A.convert(sp.ELL) * x, yref)
+    A.set_option("csr.algo", 4)
+    assert_within(A * x, yref, oracle.csr_abs_rowsum(O, x), "flat after drop")
+
+
+def test_launch_ordering_follows_the_data_hazards(oracle):
+    """The library skips griddepcontrol.wait only when nothing in flight on its stream writes the launch's x or
+    reads its y; every other API call, beta0, overlapping ranges and forced ordering bring the wait back."""
+    n = 96
+    i, j, a = stencil_entries(0, n, n)
+    N = n * n
+    x = 1.0 + (np.arange(N) % 5) / 4.0
+    O = oracle.csr(N, N, i, j, a)
+    y1 = oracle.csr_spmv(O, x)
+    for fmt in (sp.CSR, sp.ELL, sp.COO, sp.HYB):
+        A = sp.generators.stencil(sp.STENCIL_2D5, n, n, 1, fmt=fmt)
+        A.prepare()
+        A.set_x(x)
+        A.fill_y(0.0)  # an asynchronous fill kernel precedes the launch
+        A.spmv()
+        assert A.get_option("last_launch.overlapped") == 0  # first launch after other calls: ordered (this 5-point
+        #                                                     hybrid has no COO tail, so it is one ELL kernel)
+        for _ in range(4):
+            A.spmv()
+            assert A.get_option("last_launch.overlapped") == 1  # x constant, y accumulated: independent
+        assert np.array_equal(A.get_y(), 5 * y1)  # integer-valued data: exact
+        A.spmv()
+        assert A.get_option("last_launch.overlapped") == 0  # get_y went in between
+        A.set_option("independent_launches", -1)
+        A.spmv(); A.spmv()
+        assert A.get_option("last_launch.overlapped") == 0  # ordering forced
+        A.set_option("independent_launches", 0)
+        A.set_option("beta0", 1)
+        A.spmv(); A.spmv()
+        assert A.get_option("last_launch.overlapped") == 0  # y is cleared first: ordered
+        assert np.array_equal(A.get_y(), y1)
+        A.set_option("beta0", 0)
+    # x bound to the matrix's own y: every launch reads what the previous one wrote
+    A = sp.generators.stencil(sp.STENCIL_2D5, n, n, 1)
+    A.fill_y(1.0)
+    A.bind_x(A.y_device())
+    A.spmv(); A.spmv()
+    assert A.get_option("last_launch.overlapped") == 0
+
+
 def test_kernels_really_launch():
     before = sp.launch_count()
     A = sp.generators.stencil(sp.STENCIL_2D5, 64, 64, 1)
