@@ -292,7 +292,10 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               4 entries per lane, rows from span metadata), 5 sliced (lane per row on a slot-major copy of
  *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" 1 = free the row-major
  *               column_index/value once that copy exists -- they are rebuilt on demand by export, convert,
- *               row_block, column_span and the other kernels); 0 = automatic: sliced when the mean row has
+ *               row_block, column_span and the other kernels); "csr.probe" 1 = regular traffic
+ *               (y_i += sum a_k, values streamed, no gather), 2 = irregular traffic (y_i += sum x[j_k], the
+ *               gather alone): spmv_regular_traffic / spmv_irregular_traffic of the reference
+ *               (csr-matrix-spmv.cpp:35-61, 119-146); "csr.algo" 0 = automatic: sliced when the mean row has
  *               >= 10 entries and the longest row <= 2x the mean, else flat; "csr.threads" 128|256 (algo 3, 4),
  *               32..256 (algo 1, 2); algo 1-3: "csr.lanes" 1|2|4|8 lanes per row; algo 1, 2: "csr.tile"
  *               256..2048, "csr.stages" 2|3, "csr.ctas_per_sm", "csr.spare_ctas" CTA slots per SM left

@@ -459,6 +459,24 @@ class csr_matrix:
     spmv = staticmethod(_spmv)
 
     @staticmethod
+    def spmv_regular_traffic(A: DeviceMatrix, x, y):
+        """y_i += sum_k a_k: the matrix values streamed, no gather (csr-matrix.hpp:132, csr-matrix-spmv.cpp:35-47, 119-131)."""
+        A.set_option("csr.probe", 1)
+        try:
+            return _spmv(A, x, y)
+        finally:
+            A.set_option("csr.probe", 0)
+
+    @staticmethod
+    def spmv_irregular_traffic(A: DeviceMatrix, x, y):
+        """y_i += sum_k x[j_k]: the gather alone (csr-matrix.hpp:137, csr-matrix-spmv.cpp:49-61, 133-146)."""
+        A.set_option("csr.probe", 2)
+        try:
+            return _spmv(A, x, y)
+        finally:
+            A.set_option("csr.probe", 0)
+
+    @staticmethod
     def spmv_rows_per_thread(A: DeviceMatrix, thread: int, num_threads: int) -> int:
         s = partition.rows_ref(A.rows, num_threads)
         return int(s[thread + 1] - s[thread])

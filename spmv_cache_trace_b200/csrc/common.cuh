@@ -123,6 +123,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
     int64_t opt_csr_batch = 0;    // sliced kernel: slots in flight per lane (2, 4, 8), 0 = auto
+    int64_t opt_csr_probe = 0;    // 1 regular traffic (values only), 2 irregular traffic (x gather only): csr-matrix-spmv.cpp:35-61
     int64_t opt_csr_drop = 0;     // sliced kernel: 1 = free the row-major column_index/value once the slot-major copy exists
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto

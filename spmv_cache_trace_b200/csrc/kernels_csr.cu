@@ -405,6 +405,10 @@ int launch_csr(Matrix * m)
     // 1.55 ms for the best of the others).
     // 5 sliced (lane per row on a slot-major copy; kernels_csr_sliced.cu): automatic for long regular rows
     // (mean >= 10 entries, longest row <= 2x the mean), where the flat kernel's gathers saturate the L1.
+    if (m->opt_csr_probe != 0) {  // the traffic probes live in the flat kernel
+        SPMV_TRY(csr_ensure_row_major(m));
+        return launch_csr_flat(m);
+    }
     if (m->opt_csr_algo == 5) return launch_csr_sliced(m);
     if (m->opt_csr_algo == 0) {
         const int64_t avg = m->stored / std::max<int64_t>(m->rows, 1);

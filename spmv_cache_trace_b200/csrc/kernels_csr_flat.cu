@@ -92,7 +92,11 @@ static int csr_build_flat_meta(Matrix * m)
     return 0;
 }
 
-template <typename OffT, int WARPS, bool MASK>
+// PROBE: 0 = y += A*x; 1 = "regular traffic": y_i += sum_k a_k, the matrix values streamed, no gather
+// (csr_spmv_inner_loop_regular_traffic, csr-matrix-spmv.cpp:35-47); 2 = "irregular traffic": y_i += sum_k
+// x[j_k], the gather alone without the values (:49-61).  The reference keeps the two as diagnostics; here
+// they split a kernel's time into its streaming and its gather part.
+template <typename OffT, int WARPS, bool MASK, int PROBE>
 __global__ void __launch_bounds__(WARPS * 32)
 csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, const OffT * __restrict__ rp,
                 const int32_t * __restrict__ col, const double * __restrict__ val,
@@ -111,9 +115,10 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
     const uint64_t pol = policy_evict_first();
 
     // the span in flight (arrays are padded past `stored` with (0, 0.0))
-    const int4 c4 = ldg_stream_i4(col + k0, pol);
-    double a[4];
-    ldg_stream_d4(val + k0, a);
+    int4 c4 = make_int4(0, 0, 0, 0);
+    if (PROBE != 1) c4 = ldg_stream_i4(col + k0, pol);
+    double a[4] = {1.0, 1.0, 1.0, 1.0};
+    if (PROBE != 2) ldg_stream_d4(val + k0, a);
     int r[4];
     if (MASK) {
         const int r_lo = __ldg(meta + 8 * w);
@@ -162,7 +167,8 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
 
     // Everything above reads only the immutable matrix; x and y may come from the previous launch.
     if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
-    const double x0 = __ldg(x + c4.x), x1 = __ldg(x + c4.y), x2 = __ldg(x + c4.z), x3 = __ldg(x + c4.w);
+    double x0 = 1.0, x1 = 1.0, x2 = 1.0, x3 = 1.0;
+    if (PROBE != 1) { x0 = __ldg(x + c4.x); x1 = __ldg(x + c4.y); x2 = __ldg(x + c4.z); x3 = __ldg(x + c4.w); }
     const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
     warp_segmented_add4(lane, r, p, y);
 }
@@ -176,7 +182,13 @@ static int launch_flat_variant(Matrix * m)
     const int64_t grid = (nspans + WARPS - 1) / WARPS;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     const RunMode rm = run_mode(m);
-    auto kernel = m->flat_has_empty ? csr_flat_kernel<OffT, WARPS, false> : csr_flat_kernel<OffT, WARPS, true>;
+    auto kernel = m->flat_has_empty ? csr_flat_kernel<OffT, WARPS, false, 0> : csr_flat_kernel<OffT, WARPS, true, 0>;
+    if (WARPS == 4 && m->opt_csr_probe == 1)
+        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, false, 1> : csr_flat_kernel<OffT, 4, true, 1>;
+    else if (WARPS == 4 && m->opt_csr_probe == 2)
+        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, false, 2> : csr_flat_kernel<OffT, 4, true, 2>;
+    else if (m->opt_csr_probe != 0)
+        return fail(SPMVB200_ERR_INVALID, "csr.probe must be 0, 1 or 2 (and csr.threads 128)");
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, WARPS * 32u, 0, m->stream, rm.pdl, m->rows,
                             m->stored, nspans, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col,
                             (const double *)m->val, (const int32_t *)m->flat_meta, (const double *)m->x, m->y));
@@ -187,7 +199,8 @@ static int launch_flat_variant(Matrix * m)
 int launch_csr_flat(Matrix * m)
 {
     const int threads = (int)(m->opt_csr_threads ? m->opt_csr_threads : 128);
-    m->kernel_name = "csr_flat_kernel";
+    m->kernel_name = m->opt_csr_probe == 1 ? "csr_flat_kernel<regular traffic>"
+                     : m->opt_csr_probe == 2 ? "csr_flat_kernel<irregular traffic>" : "csr_flat_kernel";
     switch (threads) {
     case 64: return m->off64 ? launch_flat_variant<int64_t, 2>(m) : launch_flat_variant<uint32_t, 2>(m);
     case 128: return m->off64 ? launch_flat_variant<int64_t, 4>(m) : launch_flat_variant<uint32_t, 4>(m);

@@ -628,6 +628,32 @@ def test_row_partition_concatenates_to_the_full_product(oracle, P):
         assert csr_matrix.spmv_nonzeros_per_thread(A, t, P) == oracle.csr_nonzeros_per_thread(O.row_ptr, N, t, P)
 
 
+@pytest.mark.parametrize("empty_every", [0, 5])
+def test_csr_traffic_probes(oracle, empty_every):
+    """spmv_regular_traffic / spmv_irregular_traffic (csr-matrix-spmv.cpp:35-61): values only / gather only."""
+    rng = np.random.default_rng(17)
+    rows, cols = 4000, 3000
+    i, j, a = ragged_matrix(rng, rows, cols, long_rows=(3, 2000), long_len=700, short_max=11, empty_every=empty_every)
+    if empty_every == 0:  # make sure no row is empty (the mask path of the flat kernel)
+        missing = np.setdiff1d(np.arange(1, rows + 1), i)
+        i = np.concatenate([i, missing]).astype(np.int32); j = np.concatenate([j, np.ones(len(missing))]).astype(np.int32)
+        a = np.concatenate([a, rng.uniform(-1, 1, len(missing))])
+    x = rng.uniform(-1, 1, cols)
+    y0 = rng.uniform(-1, 1, rows)
+    O = oracle.csr(rows, cols, i, j, a)
+    rp, cj, av = np.asarray(O.row_ptr, np.int64), np.asarray(O.column_index), np.asarray(O.value)
+    seg = lambda v: np.add.reduceat(np.concatenate([v, [0.0]]), rp[:-1])* (np.diff(rp) > 0)
+    absum = lambda v: np.add.reduceat(np.concatenate([np.abs(v), [0.0]]), rp[:-1]) * (np.diff(rp) > 0)
+    A = csr_matrix.from_matrix_market(matrix_market.from_entries(rows, cols, i, j, a))
+    yr = csr_matrix.spmv_regular_traffic(A, x, y0.copy())
+    assert A.get_option("csr.probe") == 0
+    assert_within(yr, y0 + seg(av), absum(av) + np.abs(y0), "regular traffic")
+    yi = csr_matrix.spmv_irregular_traffic(A, x, y0.copy())
+    assert_within(yi, y0 + seg(x[cj]), absum(x[cj]) + np.abs(y0), "irregular traffic")
+    # and the full product is untouched by the probes
+    assert_within(csr_matrix.spmv(A, x, y0.copy()), oracle.csr_spmv(O, x, y0), oracle.csr_abs_rowsum(O, x) + np.abs(y0), "spmv")
+
+
 def test_sliced_csr_can_drop_and_rebuild_the_row_major_copy(oracle):
     n = 40
     i, j, a = stencil_entries(2, n, n, n)  # 27-point: the sliced kernel is the automatic choice
