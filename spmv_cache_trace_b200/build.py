@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or not _newer(o, [s] + headers):
-            jobs.append([cxx, "-O2", "-std=c++17", "-fPIC", "-Wall", "-I", INCLUDE, "-c", s, "-o", o])
+            jobs.append([cxx, "-O2", "-std=c++17", "-fPIC", "-pthread", "-Wall", "-I", INCLUDE, "-c", s, "-o", o])
     outputs = []
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:

@@ -10,7 +10,8 @@
 //   * a .tar.gz/.tgz archive is searched for the member "<name>/<name>.mtx".
 // The implementation is a single pass over an in-memory buffer (the whole file is read, and
 // inflated with zlib when compressed) instead of iostream extraction, which is what makes the
-// reference's loader take seconds on an 80 MB file.
+// reference's loader take seconds on an 80 MB file; files with one record per line (all of
+// SuiteSparse) are parsed by several threads.
 #include "mm_host.hpp"
 
 #include "../../include/spmv_b200.h"
@@ -21,9 +22,11 @@
 #include <cerrno>
 #include <charconv>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 
 namespace spmvb200 {
 
@@ -93,6 +96,116 @@ bool take_f64(Cursor & c, double & v)
     return true;
 }
 
+// Parallel fast path for the common layout -- exactly one record per line.  The text after the size line
+// is cut into chunks at line boundaries, every chunk is parsed by its own thread into private arrays, and
+// the pieces are concatenated.  Any line that is not one complete record (records spanning or sharing
+// lines, blank lines, junk) makes the whole fast path stand down, and the sequential tokenizer below --
+// which defines the behaviour and the error messages -- runs instead.  Returns true when it filled m.
+inline void skip_blank(Cursor & c)  // spaces and tabs, never a line end
+{
+    while (c.p < c.end && (*c.p == ' ' || *c.p == '\t')) ++c.p;
+}
+
+inline bool blank_i32(Cursor & c, int32_t & v)
+{
+    skip_blank(c);
+    auto r = std::from_chars(c.p, c.end, v, 10);
+    if (r.ec != std::errc() || r.ptr == c.p) return false;
+    c.p = r.ptr;
+    return true;
+}
+
+inline bool blank_f64(Cursor & c, double & v)
+{
+    skip_blank(c);
+    auto r = std::from_chars(c.p, c.end, v, std::chars_format::general);
+    if (r.ec != std::errc() || r.ptr == c.p) return false;  // also "+1.0", overflow, denormals: left to the sequential reader
+    c.p = r.ptr;
+    return true;
+}
+
+// Parses the lines of `c` into i[0..], j[0..], a[0..]; returns the number of records, or -1 when a line is
+// not exactly one record or more than `room` records turn up.
+int64_t parse_lines(Cursor c, int field, int32_t rows, int32_t columns, int32_t * pi, int32_t * pj, double * pa, int64_t room)
+{
+    int64_t k = 0;
+    while (!c.at_end()) {
+        int32_t i = 0, j = 0;
+        double a = 1.0;
+        bool ok = blank_i32(c, i) && blank_i32(c, j);
+        if (ok) {
+            switch (field) {
+            case 0: ok = blank_f64(c, a); break;
+            case 1: { double im; ok = blank_f64(c, a) && blank_f64(c, im); break; }
+            case 2: { int32_t v = 0; ok = blank_i32(c, v); a = (double)v; break; }
+            default: break;
+            }
+        }
+        if (ok) {
+            skip_blank(c);
+            if (c.p < c.end && *c.p == '\r') ++c.p;
+            ok = c.at_end() || *c.p == '\n';
+        }
+        if (!ok || k >= room || i < 1 || i > rows || j < 1 || j > columns) return -1;
+        if (!c.at_end()) ++c.p;  // the line end
+        pi[k] = i; pj[k] = j; pa[k] = a;
+        ++k;
+    }
+    return k;
+}
+
+bool parse_entries_parallel(Cursor c, spmvb200_mm_s * m)
+{
+    const size_t n = (size_t)m->num_entries;
+    const size_t bytes = (size_t)(c.end - c.p);
+    unsigned T = std::min<unsigned>(std::thread::hardware_concurrency(), 32u);
+    if (const char * env = getenv("SPMVB200_PARSE_THREADS")) T = (unsigned)std::max(1, atoi(env));
+    T = (unsigned)std::min<size_t>(T, bytes / ((size_t)4 << 20));  // at least 4 MB of text per thread
+    if (n < ((size_t)1 << 16) || T < 2) return false;
+    std::vector<Cursor> chunk(T);
+    const char * b = c.p;
+    for (unsigned t = 0; t < T; t++) {
+        const char * e = t + 1 == T ? c.end : c.p + bytes / T * (t + 1);
+        if (e < b) e = b;
+        while (e < c.end && e > c.p && e[-1] != '\n') ++e;  // extend to the end of the line
+        chunk[t] = Cursor{b, e};
+        b = e;
+    }
+    // pass 1: lines per chunk (memchr speed), so that every thread knows where its records go
+    std::vector<int64_t> lines(T, 0), got(T, 0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; t++)
+        th.emplace_back([&, t] {
+            int64_t cnt = 0;
+            const char * p = chunk[t].p;
+            while (p < chunk[t].end) {
+                const char * q = (const char *)memchr(p, '\n', (size_t)(chunk[t].end - p));
+                ++cnt;
+                if (!q) break;
+                p = q + 1;
+            }
+            lines[t] = cnt;
+        });
+    for (auto & x : th) x.join();
+    size_t total = 0;
+    for (auto v : lines) total += (size_t)v;
+    if (total != n) return false;  // blank lines, too few or too many records: the sequential reader decides
+    m->i.resize(n); m->j.resize(n); m->a.resize(n);
+    // pass 2: parse straight into place
+    th.clear();
+    size_t off = 0;
+    for (unsigned t = 0; t < T; t++) {
+        th.emplace_back([&, t, off] {
+            got[t] = parse_lines(chunk[t], m->field, m->rows, m->columns, m->i.data() + off, m->j.data() + off, m->a.data() + off, lines[t]);
+        });
+        off += (size_t)lines[t];
+    }
+    for (auto & x : th) x.join();
+    for (unsigned t = 0; t < T; t++)
+        if (got[t] != lines[t]) return false;
+    return true;
+}
+
 int parse(Cursor c, spmvb200_mm_s * m)
 {
     if (c.at_end()) return fail(SPMVB200_ERR_PARSE, "Failed to parse header: Expected \"%%MatrixMarket\", got \"\"");
@@ -137,6 +250,7 @@ int parse(Cursor c, spmvb200_mm_s * m)
     if (m->rows < 0 || m->columns < 0 || m->num_entries < 0) return fail(SPMVB200_ERR_PARSE, "Failed to parse size");
 
     const size_t n = (size_t)m->num_entries;
+    if (parse_entries_parallel(c, m)) return 0;
     m->i.resize(n); m->j.resize(n); m->a.resize(n);
     for (size_t k = 0; k < n; k++) {
         bool ok = take_i32(c, m->i[k]) && take_i32(c, m->j[k]);

@@ -144,3 +144,56 @@ def test_compute_fails_loudly_without_gpu():
     assert e.value.status == 5  # SPMVB200_ERR_CUDA
     with pytest.raises(matrix_error):
         sp.generators.stencil(sp.STENCIL_2D5, 8, 8)
+
+
+def _big_text(n, seed=0, fmt="%d %d %.17g"):
+    rng = np.random.default_rng(seed)
+    rows, cols = 700000, 650000
+    i = rng.integers(1, rows + 1, n).astype(np.int32)
+    j = rng.integers(1, cols + 1, n).astype(np.int32)
+    a = rng.uniform(-1e3, 1e3, n)
+    lines = [fmt % (ii, jj, aa) for ii, jj, aa in zip(i.tolist(), j.tolist(), a.tolist())]
+    head = "%%MatrixMarket matrix coordinate real general\n% a comment\n" + f"{rows} {cols} {n}\n"
+    return head, lines, i, j, a
+
+
+def test_parallel_parse_matches_the_sequential_reader():
+    """Files with one record per line are parsed by several threads (>= 4 MB of text per thread); anything
+    irregular falls back to the sequential tokenizer, with the same results and the same errors."""
+    import spmv_cache_trace_b200 as sp
+    head, lines, i, j, a = _big_text(400000)
+    text = head + "\n".join(lines) + "\n"
+    assert len(text) > 9 << 20
+    mm = sp.matrix_market.fromStream(text)
+    assert np.array_equal(mm.row_indices(), i) and np.array_equal(mm.column_indices(), j)
+    assert np.array_equal(mm.values_real(), a)  # %.17g round-trips
+    os.environ["SPMVB200_PARSE_THREADS"] = "1"  # the sequential reader on the same text
+    try:
+        m1 = sp.matrix_market.fromStream(text)
+    finally:
+        del os.environ["SPMVB200_PARSE_THREADS"]
+    assert np.array_equal(m1.row_indices(), i) and np.array_equal(m1.values_real(), a)
+    # no trailing newline, CRLF line ends, tabs
+    m2 = sp.matrix_market.fromStream(head + "\r\n".join(l.replace(" ", "\t", 1) for l in lines))
+    assert np.array_equal(m2.column_indices(), j) and np.array_equal(m2.values_real(), a)
+    # irregular layouts: two records on one line / a record split over two lines / a blank line
+    two = lines[:]
+    two[1000] = two[1000] + " " + two.pop(1001)
+    m3 = sp.matrix_market.fromStream(head + "\n".join(two) + "\n")
+    assert np.array_equal(m3.row_indices(), i) and np.array_equal(m3.values_real(), a)
+    split = lines[:]
+    first, rest = split[2000].split(" ", 1)
+    split[2000] = first + "\n" + rest
+    m4 = sp.matrix_market.fromStream(head + "\n".join(split) + "\n")
+    assert np.array_equal(m4.column_indices(), j)
+    blank = lines[:]
+    blank.insert(3000, "")
+    m5 = sp.matrix_market.fromStream(head + "\n".join(blank) + "\n")
+    assert np.array_equal(m5.row_indices(), i)
+    # errors read like the sequential reader's: one record short, an index outside the matrix
+    with pytest.raises(sp.matrix_error, match="Expected 400000 entries, got 399999 entries"):
+        sp.matrix_market.fromStream(head + "\n".join(lines[:-1]) + "\n")
+    bad = lines[:]
+    bad[123456] = "700001 1 1.0"
+    with pytest.raises(sp.matrix_error, match="index outside the matrix in entry 123457"):
+        sp.matrix_market.fromStream(head + "\n".join(bad) + "\n")
