@@ -257,6 +257,10 @@ int spmvb200_prepare(spmvb200_matrix_t m);
  *      hybrid_matrix::spmv (matrix/hybrid-matrix.cpp:535-567),
  * i.e. the bodies of Kernel::run (kernels/csr-spmv.cpp:64-67 etc.). */
 int spmvb200_spmv(spmvb200_matrix_t m);
+/* y += alpha*A*x from now on (default 1.0, which is exact and the reference's semantics).  With the
+ * "beta0" option: y = alpha*A*x, which kernels that own whole rows (ELL, sliced CSR) write with plain
+ * stores -- no clearing pass, no read of y.  Supported by the default kernels of every format. */
+int spmvb200_set_alpha(spmvb200_matrix_t m, double alpha);
 /* Wait for the matrix's stream. */
 int spmvb200_sync(spmvb200_matrix_t m);
 /* Host-buffer form: copies x (columns) and y (rows) to the device, runs

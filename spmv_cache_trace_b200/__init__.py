@@ -323,6 +323,10 @@ class DeviceMatrix:
         _check(_abi.lib().spmvb200_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     # -- the hot path ------------------------------------------------------------
+    def set_alpha(self, alpha: float):
+        """y += alpha*A*x from now on (1.0 = the reference's semantics, exact)."""
+        _check(_abi.lib().spmvb200_set_alpha(self._h, float(alpha)))
+
     def prepare(self):
         """Build the selected kernel's launch metadata now (Kernel::prepare, kernels/kernel.hpp:28)."""
         _check(_abi.lib().spmvb200_prepare(self._h))

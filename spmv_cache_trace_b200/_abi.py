@@ -108,6 +108,7 @@ SIGNATURES = {
     "spmvb200_host_alloc": (C.c_int, [C.c_size_t, vpp]),
     "spmvb200_host_free": (C.c_int, [vp]),
     "spmvb200_prepare": (C.c_int, [vp]),
+    "spmvb200_set_alpha": (C.c_int, [vp, C.c_double]),
     "spmvb200_spmv": (C.c_int, [vp]),
     "spmvb200_sync": (C.c_int, [vp]),
     "spmvb200_spmv_host": (C.c_int, [vp, f64p, f64p]),

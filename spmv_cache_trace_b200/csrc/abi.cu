@@ -198,6 +198,7 @@ static int finish(Guard & g, spmvb200_matrix_t * out)
 struct StreamRec {
     bool valid = false;  // everything enqueued since the last ordered point is an SpMV launch recorded here
     uintptr_t wlo = 0, whi = 0, rlo = 0, rhi = 0;
+    uintptr_t slo = 0, shi = 0;  // range written with plain stores (a "beta0" launch): reductions must not overtake it
     int chain = 0;       // launches since the last ordered point that skipped griddepcontrol.wait
 };
 static std::mutex g_stream_mu;
@@ -245,8 +246,10 @@ void plan_run(Matrix * m, bool conservative)
         return;
     }
     StreamRec & r = it->second;
-    const bool proven = r.valid && !overlaps(x0, x1, r.wlo, r.whi) && !overlaps(y0, y1, r.rlo, r.rhi);
-    if (!conservative && m->run_pdl && !m->opt_beta0 && (m->opt_independent > 0 || (m->opt_independent == 0 && proven))) {
+    const bool proven = r.valid && !overlaps(x0, x1, r.wlo, r.whi) && !overlaps(y0, y1, r.rlo, r.rhi) &&
+                        !overlaps(y0, y1, r.slo, r.shi);
+    if (!conservative && m->run_pdl && !m->opt_beta0 && !m->run_beta0 &&
+        (m->opt_independent > 0 || (m->opt_independent == 0 && proven))) {
         m->run_independent = true;  // validity of the record is unchanged; its ranges grow
         r.wlo = r.whi > r.wlo ? std::min(r.wlo, y0) : y0;
         r.whi = std::max(r.whi, y1);
@@ -260,6 +263,7 @@ void plan_run(Matrix * m, bool conservative)
     r = StreamRec{};
     r.valid = !conservative;
     r.wlo = y0; r.whi = y1; r.rlo = x0; r.rhi = x1;
+    if (m->run_beta0 || m->opt_beta0) { r.slo = y0; r.shi = y1; }
 }
 
 // Entry check of every API call that is not an SpMV launch: whatever it enqueues is unknown to the record.
@@ -841,10 +845,8 @@ int spmvb200_host_free(void * p)
 
 // ---- run ----------------------------------------------------------------------------------------------------------
 
-static int launch(Matrix * m)
+static int launch_format(Matrix * m)
 {
-    if (m->opt_beta0) SPMV_CUDA(cudaMemsetAsync(m->y, 0, sizeof(double) * (size_t)m->rows, m->stream));
-    plan_run(m, false);
     switch (m->format) {
     case SPMVB200_CSR: return launch_csr(m);
     case SPMVB200_ELL: return launch_ell(m, true);
@@ -859,6 +861,24 @@ static int launch(Matrix * m)
         return 0;
     }
     return fail(SPMVB200_ERR_INVALID, "unknown format");
+}
+
+// One y (+)= alpha*A*x.  "beta0" (y = ...): kernels in which one thread owns a whole row (ELL, sliced CSR) store
+// their result; the others clear y first (clear_y_for_beta0) and add with reductions as always.
+static int launch(Matrix * m)
+{
+    m->run_beta0 = m->opt_beta0 != 0;
+    plan_run(m, false);
+    const int rc = launch_format(m);
+    m->run_beta0 = false;
+    return rc;
+}
+
+int spmvb200_set_alpha(spmvb200_matrix_t m, double alpha)
+{
+    if (!m) return fail(SPMVB200_ERR_INVALID, "null matrix handle");
+    m->alpha = alpha;
+    return 0;
 }
 
 int spmvb200_prepare(spmvb200_matrix_t m)

@@ -139,6 +139,8 @@ struct spmvb200_matrix_s {
     // per-launch decisions of plan_run() (abi.cu): launch attribute and whether the kernel may skip
     // griddepcontrol.wait because nothing in flight on its stream writes its x or reads its y
     bool run_pdl = true, run_independent = false;
+    bool run_beta0 = false;       // this launch computes y = alpha*A*x: kernels that own whole rows store, the others clear y first
+    double alpha = 1.0;           // y += alpha*A*x (spmvb200_set_alpha); 1.0 is exact, the reference's semantics
     bool aux_dirty = false;       // an auxiliary table was just (re)built on the stream: serialise the next launch
     bool dry_run = false;         // spmvb200_prepare: build the launch metadata of the selected kernel, launch nothing
     const char * kernel_name = "";
@@ -212,6 +214,20 @@ struct RunMode {
     bool pdl;
     int independent;
 };
+// Kernels that add partial row sums with reductions need y cleared first when the launch is y = alpha*A*x.
+inline int clear_y_for_beta0(Matrix * m)
+{
+    if (!m->run_beta0) return 0;
+    m->run_beta0 = false;
+    cudaError_t e = cudaMemsetAsync(m->y, 0, sizeof(double) * (size_t)m->rows, m->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__);
+    return 0;
+}
+inline int need_unit_alpha(const Matrix * m, const char * kernel)
+{
+    if (m->alpha == 1.0) return 0;
+    return fail(SPMVB200_ERR_UNSUPPORTED, std::string(kernel) + " does not scale its result: use the default kernels with spmvb200_set_alpha");
+}
 inline RunMode run_mode(Matrix * m)
 {
     RunMode r{m->run_pdl && !m->aux_dirty, (m->run_independent && !m->aux_dirty) ? 1 : 0};

@@ -175,7 +175,7 @@ coo_warp_kernel(int64_t n, int independent, const int32_t * __restrict__ row, co
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
-                 const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y)
+                 const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y, double alpha)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
@@ -191,7 +191,7 @@ coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, c
     const double x0 = __ldg(x + c4.x), x1 = __ldg(x + c4.y), x2 = __ldg(x + c4.z), x3 = __ldg(x + c4.w);
     const int r[4] = {k0 < n ? r4.x : -1, k0 + 1 < n ? r4.y : -1, k0 + 2 < n ? r4.z : -1, k0 + 3 < n ? r4.w : -1};
     const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
-    warp_segmented_add4(lane, r, p, y);
+    warp_segmented_add4(lane, r, p, y, alpha);
 }
 
 // Entries in file order: one fp64 reduction per entry, two entries per thread and iteration
@@ -269,7 +269,7 @@ static int launch_coo_warp4_variant(Matrix * m)
     const RunMode rm = run_mode(m);
     SPMV_CUDA(launch_kernel(coo_warp4_kernel<WARPS>, (unsigned)grid, (unsigned)(WARPS * 32), 0, m->stream, rm.pdl, m->coo_n,
                             rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
-                            (const double *)m->coo_val, (const double *)m->x, m->y));
+                            (const double *)m->coo_val, (const double *)m->x, m->y, m->alpha));
     count_launch();
     return 0;
 }
@@ -300,7 +300,10 @@ static int launch_coo_warp(Matrix * m)
 
 int launch_coo(Matrix * m)
 {
-    if (m->coo_n == 0 || m->rows == 0) return 0;
+    if (m->rows == 0) return 0;
+    SPMV_TRY(clear_y_for_beta0(m));  // every COO kernel adds partial sums
+    if (m->coo_n == 0) return 0;
+    if (m->opt_coo_algo == 1 || m->opt_coo_algo == 3 || m->opt_coo_algo == 4) SPMV_TRY(need_unit_alpha(m, "this COO kernel"));
     // coo.algo: 0 automatic, 1 shared-memory staged tiles (sorted entries only), 2 register-staged warp
     // stripes (any order), 3 one reduction per entry
     // Automatic = 2 for both modes: on file-order entries the warp kernel still merges adjacent equal

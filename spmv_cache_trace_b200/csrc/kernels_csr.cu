@@ -425,6 +425,8 @@ int launch_csr(Matrix * m)
     }
     SPMV_TRY(csr_ensure_row_major(m));  // every other kernel walks the row-major arrays
     if (m->opt_csr_algo == 0 || m->opt_csr_algo == 4) return launch_csr_flat(m);
+    SPMV_TRY(need_unit_alpha(m, "this CSR kernel"));
+    if (!m->dry_run) SPMV_TRY(clear_y_for_beta0(m));
     const bool warp = m->opt_csr_algo == 3;
     if (warp) return launch_csr_warp(m, c.lanes > 0 ? c.lanes : 8);
     m->kernel_name = c.lanes == 0 ? "csr_stream_kernel<product>" : "csr_stream_kernel<direct>";

@@ -100,7 +100,7 @@ template <typename OffT, int WARPS, bool MASK, int PROBE>
 __global__ void __launch_bounds__(WARPS * 32)
 csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, const OffT * __restrict__ rp,
                 const int32_t * __restrict__ col, const double * __restrict__ val,
-                const int32_t * __restrict__ meta, const double * __restrict__ x, double * __restrict__ y)
+                const int32_t * __restrict__ meta, const double * __restrict__ x, double * __restrict__ y, double alpha)
 {
     __shared__ __align__(16) int32_t smark[MASK ? 1 : WARPS][kFlatSpan];
 
@@ -170,7 +170,7 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
     double x0 = 1.0, x1 = 1.0, x2 = 1.0, x3 = 1.0;
     if (PROBE != 1) { x0 = __ldg(x + c4.x); x1 = __ldg(x + c4.y); x2 = __ldg(x + c4.z); x3 = __ldg(x + c4.w); }
     const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
-    warp_segmented_add4(lane, r, p, y);
+    warp_segmented_add4(lane, r, p, y, alpha);
 }
 
 template <typename OffT, int WARPS>
@@ -181,6 +181,7 @@ static int launch_flat_variant(Matrix * m)
     const int64_t nspans = (m->stored + kFlatSpan - 1) / kFlatSpan;
     const int64_t grid = (nspans + WARPS - 1) / WARPS;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
+    SPMV_TRY(clear_y_for_beta0(m));
     const RunMode rm = run_mode(m);
     auto kernel = m->flat_has_empty ? csr_flat_kernel<OffT, WARPS, false, 0> : csr_flat_kernel<OffT, WARPS, true, 0>;
     if (WARPS == 4 && m->opt_csr_probe == 1)
@@ -191,7 +192,7 @@ static int launch_flat_variant(Matrix * m)
         return fail(SPMVB200_ERR_INVALID, "csr.probe must be 0, 1 or 2 (and csr.threads 128)");
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, WARPS * 32u, 0, m->stream, rm.pdl, m->rows,
                             m->stored, nspans, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col,
-                            (const double *)m->val, (const int32_t *)m->flat_meta, (const double *)m->x, m->y));
+                            (const double *)m->val, (const int32_t *)m->flat_meta, (const double *)m->x, m->y, m->alpha));
     count_launch();
     return 0;
 }

@@ -101,8 +101,9 @@ int csr_ensure_row_major(Matrix * m)
 
 template <typename OffT, int U>
 __global__ void __launch_bounds__(128, U <= 4 ? 16 : 8)
-csr_sliced_kernel(int64_t rows, int independent, const OffT * __restrict__ rp, const int32_t * __restrict__ scol,
-                  const double * __restrict__ sval, const double * __restrict__ x, double * __restrict__ y)
+csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
+                  const int32_t * __restrict__ scol, const double * __restrict__ sval, const double * __restrict__ x,
+                  double * __restrict__ y)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
@@ -140,7 +141,9 @@ csr_sliced_kernel(int64_t rows, int independent, const OffT * __restrict__ rp, c
             if (len > l0 + u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
     }
     if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (len > 0) red_add_f64(y + i, z);
+    // a lane owns its whole row: y = alpha*A*x is a plain store (no clearing pass, no read of y)
+    if (store) { if (i < rows) y[i] = __dmul_rn(alpha, z); }
+    else if (len > 0) red_add_f64(y + i, __dmul_rn(alpha, z));
 }
 
 static int csr_drop_row_major(Matrix * m)
@@ -183,10 +186,12 @@ int launch_csr_sliced(Matrix * m)
     const int64_t grid = (m->rows + 127) / 128;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     const RunMode rm = run_mode(m);
+    const int store = m->run_beta0 ? 1 : 0;
+    m->run_beta0 = false;
     const int batch = (int)(m->opt_csr_batch ? m->opt_csr_batch : 4);
 #define SPMV_SLICED(OFF, UU)                                                                                              \
     SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU>, (unsigned)grid, 128u, 0, m->stream, rm.pdl, m->rows, rm.independent, \
-                            (const OFF *)m->rp, (const int32_t *)m->slice_col, (const double *)m->slice_val,            \
+                            store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col, (const double *)m->slice_val,            \
                             (const double *)m->x, m->y))
     if (batch == 4) { if (m->off64) SPMV_SLICED(int64_t, 4); else SPMV_SLICED(uint32_t, 4); }
     else if (batch == 8) { if (m->off64) SPMV_SLICED(int64_t, 8); else SPMV_SLICED(uint32_t, 8); }

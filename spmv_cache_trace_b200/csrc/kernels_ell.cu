@@ -54,7 +54,8 @@ struct EllLoad<4> {
 // so all of a thread's matrix loads are issued before the first gather returns.
 template <int R, int W_STATIC, bool SKIP>
 __global__ void __launch_bounds__(256)
-ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int independent, const int32_t * __restrict__ col,
+ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int independent, int store, double alpha,
+           const int32_t * __restrict__ col,
            const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y,
            const double * __restrict__ y_in_host, double * __restrict__ y_out_host)
 {
@@ -123,6 +124,8 @@ ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int indepen
             }
         }
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r) z[r] = __dmul_rn(alpha, z[r]);  // alpha = 1.0 is exact
     if (y_out_host) {
 #pragma unroll
         for (int r = 0; r < R; ++r) z[r] = __dadd_rn(yo[r], z[r]);
@@ -136,6 +139,12 @@ ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int indepen
             for (int r = 0; r < R; ++r)
                 if (i0 + r < rows) __stcs(y_out_host + i0 + r, z[r]);
         }
+        return;
+    }
+    if (store) {  // y = alpha*A*x: a thread owns its rows
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (i0 + r < rows) y[i0 + r] = z[r];
         return;
     }
 #pragma unroll
@@ -155,18 +164,20 @@ static int launch_ell_rw(Matrix * m, int block)
     const RunMode rm = run_mode(m);
     const bool pdl = rm.pdl;
     const int indep = rm.independent;
+    const int store = (m->run_beta0 && !m->host_y_out) ? 1 : 0;
+    m->run_beta0 = false;
     cudaError_t e;
 #define SPMV_ELL_CASE(WS)                                                                                      \
     case WS:                                                                                                   \
         e = launch_kernel(ell_kernel<R, WS, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, row0, row1,    \
-                          m->ell_pitch, w, indep, (const int32_t *)m->ell_col, (const double *)m->ell_val,            \
+                          m->ell_pitch, w, indep, store, m->alpha, (const int32_t *)m->ell_col, (const double *)m->ell_val,            \
                           (const double *)m->x, m->y, (const double *)m->host_y_in, m->host_y_out);              \
         break;
     switch (w) {
         SPMV_ELL_CASE(1) SPMV_ELL_CASE(2) SPMV_ELL_CASE(3) SPMV_ELL_CASE(4) SPMV_ELL_CASE(5)
         SPMV_ELL_CASE(6) SPMV_ELL_CASE(7) SPMV_ELL_CASE(8) SPMV_ELL_CASE(9)
     default:
-        e = launch_kernel(ell_kernel<R, 0, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, row0, row1, m->ell_pitch, w, indep,
+        e = launch_kernel(ell_kernel<R, 0, SKIP>, grid, (unsigned)block, 0, m->stream, pdl, row0, row1, m->ell_pitch, w, indep, store, m->alpha,
                           (const int32_t *)m->ell_col, (const double *)m->ell_val, (const double *)m->x, m->y,
                           (const double *)m->host_y_in, m->host_y_out);
     }
@@ -178,7 +189,8 @@ static int launch_ell_rw(Matrix * m, int block)
 
 int launch_ell(Matrix * m, bool)
 {
-    if (m->rows == 0 || m->ell_w == 0) return 0;
+    if (m->rows == 0) return 0;
+    if (m->ell_w == 0) return clear_y_for_beta0(m);  // nothing to add; y = alpha*A*x still has to clear y
     int R = (int)(m->opt_ell_rows ? m->opt_ell_rows : 2);
     int block = (int)(m->opt_ell_block ? m->opt_ell_block : 128);
     if (block < 32 || block > 256 || block % 32) return fail(SPMVB200_ERR_INVALID, "ell.block must be 32..256");

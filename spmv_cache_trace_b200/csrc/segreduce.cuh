@@ -13,8 +13,9 @@
 
 namespace spmvb200 {
 
+// alpha scales every sum on its way out (alpha = 1.0 is exact).
 __device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4], const double (&p)[4],
-                                                    double * __restrict__ y)
+                                                    double * __restrict__ y, double alpha = 1.0)
 {
     using ptx::red_add_f64;
     int cur_row = r[0];
@@ -26,7 +27,7 @@ __device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4],
             cur = __dadd_rn(cur, p[j]);
         } else {
             if (single) { head = cur; single = false; }
-            else if (cur_row >= 0) red_add_f64(y + cur_row, cur);
+            else if (cur_row >= 0) red_add_f64(y + cur_row, __dmul_rn(alpha, cur));
             cur_row = r[j];
             cur = p[j];
         }
@@ -48,8 +49,8 @@ __device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4],
         }
     }
     const double prev_s = __shfl_up_sync(0xffffffffu, s, 1);
-    if (!single && r[0] >= 0) red_add_f64(y + r[0], cont ? __dadd_rn(prev_s, head) : head);
-    if (!next_cont && r[3] >= 0) red_add_f64(y + r[3], s);
+    if (!single && r[0] >= 0) red_add_f64(y + r[0], __dmul_rn(alpha, cont ? __dadd_rn(prev_s, head) : head));
+    if (!next_cont && r[3] >= 0) red_add_f64(y + r[3], __dmul_rn(alpha, s));
 }
 
 }  // namespace spmvb200

@@ -167,6 +167,7 @@ class DistributedSpMV:
         for b, e, remote in blocks:
             A = local if (b, e) == (0, self.rows) else local.row_block(b, e)
             A.set_stream(self.compute.cuda_stream)
+            A.set_option("beta0", 1)
             if not remote and self.P > 1:
                 # The interior kernel is persistent and would fill every SM; keep CTA slots free so
                 # the NCCL kernel of the concurrent exchange is not locked out until it drains.
@@ -199,7 +200,10 @@ class DistributedSpMV:
             exchange(self.dist, cur, self.starts, self.rank, self.plan)
             ready.record(self.comm)
         with torch.cuda.stream(self.compute):
-            nxt[self.s:self.e].zero_()  # the kernels accumulate: y += A x
+            # y = alpha*A*x ("beta0" + spmvb200_set_alpha): the sliced CSR kernel owns whole rows and stores them, so
+            # there is no clearing pass over x_{k+1}, no read of it by reductions and no separate scaling kernel
+            # (8-GPU step 1.02 -> see DESIGN.md section 8); kernels that add partial sums clear their rows first.
+            alpha = scale if scale else 1.0
             waited = False
             # interior block first (no remote x), then the boundary blocks after the exchange
             for A, b, e, remote in sorted(self.blocks, key=lambda t: t[3]):
@@ -208,11 +212,10 @@ class DistributedSpMV:
                     waited = True
                 A.bind_x(cur.data_ptr())
                 A.bind_y(nxt.data_ptr() + 8 * (self.s + b))
+                A.set_alpha(alpha)
                 A.spmv()
             if not waited:
                 self.compute.wait_event(ready)
-            if scale:
-                nxt[self.s:self.e].mul_(scale)
         self.k += 1
 
     def synchronize(self):

@@ -654,6 +654,63 @@ def test_csr_traffic_probes(oracle, empty_every):
     assert_within(csr_matrix.spmv(A, x, y0.copy()), oracle.csr_spmv(O, x, y0), oracle.csr_abs_rowsum(O, x) + np.abs(y0), "spmv")
 
 
+def test_alpha_and_beta0_store_mode(oracle):
+    """y (+)= alpha*A*x: alpha = 1 is exact; with beta0 the row-owning kernels (ELL, sliced CSR) store, the others
+    clear y first; a later accumulating launch is ordered behind the stores."""
+    n = 24
+    i, j, a = stencil_entries(2, n, n, n)  # 27-point: CSR picks the sliced kernel
+    N = n ** 3
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1, 1, N)
+    y0 = rng.uniform(-1, 1, N)
+    O = oracle.csr(N, N, i, j, a)
+    ax = oracle.csr_spmv(O, x)
+    bound = oracle.csr_abs_rowsum(O, x)
+    alpha = 1.0 / 52.0
+    for fmt in (sp.CSR, sp.ELL, sp.COO, sp.HYB):
+        A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=fmt)
+        A.set_x(x)
+        A.set_alpha(alpha)
+        A.set_y(y0)
+        A.spmv()
+        assert_within(A.get_y(), y0 + alpha * ax, alpha * bound + np.abs(y0), f"alpha, fmt {fmt}")
+        A.set_option("beta0", 1)
+        A.set_y(np.full(N, 1e30))  # garbage that y = alpha*A*x must overwrite
+        A.spmv()
+        assert_within(A.get_y(), alpha * ax, alpha * bound, f"alpha + beta0, fmt {fmt}")
+        A.set_y(np.full(N, 1e30))
+        A.spmv()               # stores ...
+        A.set_option("beta0", 0)
+        A.spmv()               # ... then accumulates on top: must not overtake the stores
+        assert A.get_option("last_launch.overlapped") == 0
+        A.spmv()
+        assert A.get_option("last_launch.overlapped") == 1
+        assert_within(A.get_y(), 3 * alpha * ax, 3 * alpha * bound, f"store then accumulate, fmt {fmt}")
+        A.set_alpha(1.0)
+        A.set_option("beta0", 1)
+        A.spmv()
+        ref = ax if fmt in (sp.CSR, sp.ELL) else None
+        if ref is not None:
+            assert np.array_equal(A.get_y(), ax), f"alpha = 1 is exact, fmt {fmt}"
+    # kernels that do not scale refuse alpha != 1 instead of ignoring it
+    A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+    A.set_alpha(2.0)
+    A.set_option("csr.algo", 1)
+    with pytest.raises(sp.matrix_error):
+        A.spmv()
+    A.set_option("csr.algo", 4)
+    A.set_x(x); A.fill_y(0.0); A.spmv()
+    assert_within(A.get_y(), 2 * ax, 2 * bound, "flat with alpha")
+    # hybrid whose ELL part is empty (W = 0): beta0 still clears y before the COO pass
+    mm = matrix_market.from_entries(6, 6, [1, 1, 1, 1, 2], [1, 2, 3, 4, 2], [1.0, 2.0, 3.0, 4.0, 5.0])
+    H = hybrid_matrix.from_matrix_market(mm)
+    assert H.ell_row_length == 0
+    H.set_option("beta0", 1)
+    H.set_y(np.full(6, 7.0))
+    H.set_x(np.ones(6)); H.spmv()
+    assert np.array_equal(H.get_y(), [10.0, 5.0, 0, 0, 0, 0])
+
+
 def test_sliced_csr_can_drop_and_rebuild_the_row_major_copy(oracle):
     n = 40
     i, j, a = stencil_entries(2, n, n, n)  # 27-point: the sliced kernel is the automatic choice
