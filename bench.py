@@ -16,6 +16,8 @@ N = 1   headline workload = BASELINE configs[1]: ELLPACK SpMV on the 3D 7-point 
 N > 1   BASELINE configs[4]: row-partitioned CSR SpMV on the 27-point stencil of a 512^3 grid
         (134 217 728 rows, 3 609 741 304 nnz), strong scaling, a step = one SpMV plus the exchange of
         x between ranks over NCCL; see spmv_cache_trace_b200/distributed.py.
+        `--workload c4_hyb` (N = 2): BASELINE configs[3], the hybrid ELL+COO matrix (R-MAT 2^26 x 32)
+        cut into row blocks of equal non-zeros, x all-gathered between iterations.
 --impl reference   the reference's own OpenMP kernels (oracle/_ref, compiled from the unmodified
         reference sources) on this box's host cores, same workload, same metric.
 

@@ -330,6 +330,11 @@ int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t *sta
 /* New matrix holding rows [row_begin, row_end) of a CSR matrix (global columns). */
 int spmvb200_csr_row_block(spmvb200_matrix_t m, int64_t row_begin, int64_t row_end,
                            spmvb200_matrix_t *out);
+/* Two new CSR matrices with the rows of `m`: the entries whose column lies in [col_begin, col_end) and all the
+ * others (A = inside + outside).  The row-partitioned mode uses it for matrices that are not banded: the part of a
+ * rank's rows that references only the rank's own slice of x runs while the exchange of x is in flight. */
+int spmvb200_csr_column_split(spmvb200_matrix_t m, int64_t col_begin, int64_t col_end, spmvb200_matrix_t *inside,
+                              spmvb200_matrix_t *outside);
 /* What a rank of the row-partitioned mode needs from the others.  For a CSR matrix whose rows own
  * columns [col_begin, col_end) of x (the analogue of the reference tagging every x[j] with the
  * thread that owns its page, matrix/csr-matrix.cpp:132-136):

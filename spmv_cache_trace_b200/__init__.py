@@ -402,6 +402,12 @@ class DeviceMatrix:
         _check(_abi.lib().spmvb200_convert(self._h, fmt, arg, C.byref(h)))
         return DeviceMatrix(h)
 
+    def column_split(self, col_begin: int, col_end: int):
+        """(inside, outside): the entries with column in [col_begin, col_end) and all the others, as two CSR matrices."""
+        a, b = C.c_void_p(), C.c_void_p()
+        _check(_abi.lib().spmvb200_csr_column_split(self._h, int(col_begin), int(col_end), C.byref(a), C.byref(b)))
+        return DeviceMatrix(a), DeviceMatrix(b)
+
     def column_span(self, col_begin: int, col_end: int) -> dict:
         """Columns this (CSR) row block references and its rows that need no remote x (see spmv_b200.h)."""
         v = [C.c_int64() for _ in range(4)]

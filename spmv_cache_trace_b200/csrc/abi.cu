@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "mm_host.hpp"
 
+#include <cub/cub.cuh>
+
 #include <atomic>
 #include <climits>
 #include <cstring>
@@ -94,6 +96,38 @@ __global__ void rebase_offsets_kernel(int64_t n, const OffT * rp, int64_t first,
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
         out[r] = (int64_t)rp[r] - first;
+}
+
+// Column split of a CSR matrix: entries with column in [cb, ce) go to the "inside" matrix, the rest to "outside".
+template <typename OffT>
+__global__ void column_count_kernel(int64_t rows, const OffT * rp, const int32_t * col, int64_t cb, int64_t ce,
+                                    int64_t * n_in, int64_t * n_out)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t in = 0, len = 0;
+        if (r < rows) {
+            const int64_t lo = (int64_t)rp[r], hi = (int64_t)rp[r + 1];
+            len = hi - lo;
+            for (int64_t k = lo; k < hi; ++k) in += (col[k] >= cb && col[k] < ce) ? 1 : 0;
+        }
+        n_in[r] = in;
+        n_out[r] = len - in;
+    }
+}
+
+template <typename OffT>
+__global__ void column_fill_kernel(int64_t rows, const OffT * rp, const int32_t * col, const double * val, int64_t cb,
+                                   int64_t ce, const int64_t * rp_in, const int64_t * rp_out, int32_t * col_in,
+                                   double * val_in, int32_t * col_out, double * val_out)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t pi = rp_in[r], po = rp_out[r];
+        for (int64_t k = (int64_t)rp[r]; k < (int64_t)rp[r + 1]; ++k) {
+            const int32_t c = col[k];
+            if (c >= cb && c < ce) { col_in[pi] = c; val_in[pi++] = val[k]; }
+            else { col_out[po] = c; val_out[po++] = val[k]; }
+        }
+    }
 }
 
 // out[0] = min column, out[1] = max column, out[2] = lo_end, out[3] = hi_begin (see spmv_b200.h)
@@ -1108,6 +1142,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.spare_ctas")) return &m->opt_csr_spare;
     if (!strcmp(key, "csr.batch")) return &m->opt_csr_batch;
     if (!strcmp(key, "csr.probe")) return &m->opt_csr_probe;
+    if (!strcmp(key, "csr.entries")) return &m->opt_csr_entries;
     if (!strcmp(key, "csr.drop_row_major")) return &m->opt_csr_drop;
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;
@@ -1290,6 +1325,67 @@ int spmvb200_cache_trace(spmvb200_matrix_t m, const spmvb200_cache_config * cfg,
         return 0;
     }
     return fail(SPMVB200_ERR_INVALID, "unknown format");
+}
+
+// ---- column split (interior / boundary for matrices that are not banded) ------------------------------------------
+
+int spmvb200_csr_column_split(spmvb200_matrix_t src, int64_t col_begin, int64_t col_end, spmvb200_matrix_t * inside,
+                              spmvb200_matrix_t * outside)
+{
+    SPMV_TRY(check(src));
+    if (!inside || !outside || src->format != SPMVB200_CSR || col_begin < 0 || col_begin > col_end)
+        return fail(SPMVB200_ERR_INVALID, "bad argument");
+    SPMV_TRY(csr_ensure_row_major(src));
+    cudaStream_t s = src->stream;
+    const int64_t rows = src->rows;
+    Scratch<int64_t> n_in, n_out, rp_in, rp_out;
+    Scratch<unsigned char> tmp;
+    SPMV_TRY(n_in.alloc(rows + 1)); SPMV_TRY(n_out.alloc(rows + 1)); SPMV_TRY(rp_in.alloc(rows + 1)); SPMV_TRY(rp_out.alloc(rows + 1));
+    if (src->off64) column_count_kernel<int64_t><<<grid_for(rows + 1), 256, 0, s>>>(rows, (const int64_t *)src->rp, src->col, col_begin, col_end, n_in.p, n_out.p);
+    else column_count_kernel<uint32_t><<<grid_for(rows + 1), 256, 0, s>>>(rows, (const uint32_t *)src->rp, src->col, col_begin, col_end, n_in.p, n_out.p);
+    SPMV_CUDA(cudaGetLastError());
+    size_t tb = 0;
+    SPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, n_in.p, rp_in.p, rows + 1, s));
+    SPMV_TRY(tmp.alloc((int64_t)tb));
+    SPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, n_in.p, rp_in.p, rows + 1, s));
+    SPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, n_out.p, rp_out.p, rows + 1, s));
+    int64_t tot_in = 0, tot_out = 0;
+    SPMV_CUDA(cudaMemcpyAsync(&tot_in, rp_in.p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaMemcpyAsync(&tot_out, rp_out.p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    Matrix * parts[2] = {nullptr, nullptr};
+    SPMV_TRY(matrix_new(&parts[0]));
+    Guard g0(parts[0]);
+    SPMV_TRY(matrix_new(&parts[1]));
+    Guard g1(parts[1]);
+    const int64_t totals[2] = {tot_in, tot_out};
+    for (int k = 0; k < 2; k++) {
+        Matrix * m = parts[k];
+        m->format = SPMVB200_CSR;
+        m->rows = rows; m->cols = src->cols; m->nnz = totals[k]; m->stored = totals[k];
+        m->row_alignment = 1;
+        m->row_offset = src->row_offset;
+        SPMV_TRY(alloc_streamed(m, &m->col, totals[k]));
+        SPMV_TRY(alloc_streamed(m, &m->val, totals[k]));
+        SPMV_CUDA(cudaStreamSynchronize(m->stream));  // the padding memsets ran on the new matrix's own stream
+    }
+    if (rows > 0) {
+        if (src->off64) column_fill_kernel<int64_t><<<grid_for(rows), 256, 0, s>>>(rows, (const int64_t *)src->rp, src->col, src->val, col_begin, col_end, rp_in.p, rp_out.p, parts[0]->col, parts[0]->val, parts[1]->col, parts[1]->val);
+        else column_fill_kernel<uint32_t><<<grid_for(rows), 256, 0, s>>>(rows, (const uint32_t *)src->rp, src->col, src->val, col_begin, col_end, rp_in.p, rp_out.p, parts[0]->col, parts[0]->val, parts[1]->col, parts[1]->val);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    SPMV_TRY(store_offsets(parts[0], rp_in.p, rows, tot_in));
+    SPMV_TRY(store_offsets(parts[1], rp_out.p, rows, tot_out));
+    SPMV_TRY(csr_build_tiles(parts[0]));
+    SPMV_TRY(csr_build_tiles(parts[1]));
+    SPMV_TRY(finish(g0, inside));
+    const int rc = finish(g1, outside);
+    if (rc) {
+        matrix_free(*inside);
+        *inside = nullptr;
+    }
+    return rc;
 }
 
 }  // extern "C"

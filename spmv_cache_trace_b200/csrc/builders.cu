@@ -542,6 +542,18 @@ __global__ void rowcol_sorted_kernel(int64_t n, const int32_t * row, const int32
         if (row[k] < row[k - 1] || (row[k] == row[k - 1] && col[k] < col[k - 1])) *unsorted = 1;
 }
 
+__global__ void block_hist_kernel(int64_t n, const int32_t * col, int shift, unsigned long long * hist /* 256 */)
+{
+    __shared__ unsigned int local[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) local[t] = 0;
+    __syncthreads();
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&local[(col[k] >> shift) & 255], 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 256; t += blockDim.x)
+        if (local[t]) atomicAdd(&hist[t], (unsigned long long)local[t]);
+}
+
 __global__ void block_key_kernel(int64_t n, const int32_t * col, int shift, unsigned char * key, uint32_t * idx)
 {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
@@ -577,10 +589,28 @@ int coo_column_blocks(Matrix * m)
     }
     const int64_t nblocks = (m->cols + ((int64_t)1 << shift) - 1) >> shift;
     if (nblocks < 2 || nblocks > 256) return 0;
-    // automatic: worth it when the gather misses saved (about 12 B per entry measured on R-MAT 2^26) outweigh
-    // the extra sweeps over y (a 32 B sector read + written per 4 rows, about half the rows touched per block)
-    if (opt == 0 && n * 12 <= nblocks * m->rows * 8) return 0;
     cudaStream_t s = m->stream;
+    if (opt == 0) {
+        // automatic: look at the column blocks the entries really fall into (a piece of a column-split matrix
+        // references a part of x only).  Worth it when the x referenced does not fit in L2 and the gather
+        // misses saved (about 12 B per entry measured on R-MAT 2^26) outweigh the extra sweeps over y (a 32 B
+        // sector read + written per 4 rows, about half the rows touched per block, never more than its entries).
+        Scratch<unsigned long long> dh;
+        SPMV_TRY(dh.alloc(256));
+        SPMV_CUDA(cudaMemsetAsync(dh.p, 0, 256 * sizeof(unsigned long long), s));
+        block_hist_kernel<<<grid_for(n, m->sm_count), 256, 0, s>>>(n, m->coo_col, shift, dh.p);
+        SPMV_CUDA(cudaGetLastError());
+        unsigned long long hist[256];
+        SPMV_CUDA(cudaMemcpyAsync(hist, dh.p, sizeof hist, cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        int64_t nonempty = 0, ycost = 0;
+        for (int64_t b = 0; b < nblocks; b++) {
+            if (hist[b]) nonempty++;
+            ycost += std::min<int64_t>(m->rows, (int64_t)hist[b]) * 8;
+        }
+        if ((nonempty * 8) << shift <= (int64_t)l2 + l2 / 2) return 0;
+        if (n * 12 <= ycost) return 0;
+    }
     Scratch<int> flag;
     SPMV_TRY(flag.alloc(1));
     SPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));

@@ -75,6 +75,7 @@ struct spmvb200_matrix_s {
     int32_t * span_row = nullptr;  // warp / flat kernels: row holding the first entry of every span_size-entry span
     int span_size = 0;
     int32_t * flat_meta = nullptr;  // flat kernel: {first row, -, -, -, 128-bit row-start mask} per 128-entry span
+    int flat_span = 0;              // entries per span the metadata was built for (128 or 256)
     bool flat_has_empty = false;    // some row is empty: the mask cannot describe the row starts
     int32_t * slice_col = nullptr;  // sliced kernel: column_index / value with every 32-row slice stored slot-major
     double * slice_val = nullptr;
@@ -123,6 +124,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
     int64_t opt_csr_batch = 0;    // sliced kernel: slots in flight per lane (2, 4, 8), 0 = auto
+    int64_t opt_csr_entries = 0;  // flat kernel: entries per lane (4, 8), 0 = auto
     int64_t opt_csr_probe = 0;    // 1 regular traffic (values only), 2 irregular traffic (x gather only): csr-matrix-spmv.cpp:35-61
     int64_t opt_csr_drop = 0;     // sliced kernel: 1 = free the row-major column_index/value once the slot-major copy exists
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)

@@ -38,51 +38,66 @@ namespace spmvb200 {
 
 using namespace ptx;
 
-constexpr int kFlatSpan = 128;
+// E = entries per lane (4 or 8): a span is 32*E entries, its metadata 4 + E ints ({first row, -, -, -,
+// E mask words}).  E = 8 halves the number of warps and of cross-lane reductions per entry and doubles the
+// bytes a warp has in flight, which pays on small matrices whose kernels last a few warp lifetimes
+// (2-D 5-point 1000^2: 13.4-14.3 us with E = 4); E = 4 keeps 32 registers and full occupancy.
+template <int E>
+struct FlatShape {
+    static constexpr int span = 32 * E;
+    static constexpr int stride = 4 + E;  // ints of metadata per span
+};
 
-// meta[8*w + 0] = largest r with row_ptr[r] <= 128*w;  meta[8*w + 4..7] = bit e set iff a row starts at
-// entry 128*w + e, e = 1..127 (a row starting at e = 0 is the first row itself).
+// meta[stride*w + 0] = largest r with row_ptr[r] <= span*w;  meta[stride*w + 4 ..] = bit e set iff a row starts
+// at entry span*w + e, e = 1..span-1 (a row starting at e = 0 is the first row itself).
 template <typename OffT>
-__global__ void csr_flat_first_row_kernel(int64_t rows, int64_t nspans, const OffT * __restrict__ rp, int32_t * __restrict__ meta)
+__global__ void csr_flat_first_row_kernel(int64_t rows, int64_t nspans, int span, int stride, const OffT * __restrict__ rp,
+                                          int32_t * __restrict__ meta)
 {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nspans) return;
-    const int64_t target = w * kFlatSpan;
+    const int64_t target = w * span;
     int64_t lo = 0, hi = rows - 1;
     while (lo < hi) {
         const int64_t mid = (lo + hi + 1) >> 1;
         if ((int64_t)rp[mid] <= target) lo = mid; else hi = mid - 1;
     }
-    meta[8 * w] = (int32_t)lo;
+    meta[(int64_t)stride * w] = (int32_t)lo;
 }
 
 template <typename OffT>
-__global__ void csr_flat_mask_kernel(int64_t rows, const OffT * __restrict__ rp, int32_t * __restrict__ meta, int * __restrict__ has_empty)
+__global__ void csr_flat_mask_kernel(int64_t rows, int span, int stride, const OffT * __restrict__ rp, int32_t * __restrict__ meta,
+                                     int * __restrict__ has_empty)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = (int64_t)rp[r];
         if ((int64_t)rp[r + 1] == p) { *has_empty = 1; continue; }
-        const int e = (int)(p % kFlatSpan);
-        if (e) atomicOr(reinterpret_cast<unsigned *>(meta) + 8 * (p / kFlatSpan) + 4 + (e >> 5), 1u << (e & 31));
+        const int e = (int)(p % span);
+        if (e) atomicOr(reinterpret_cast<unsigned *>(meta) + (int64_t)stride * (p / span) + 4 + (e >> 5), 1u << (e & 31));
     }
 }
 
-static int csr_build_flat_meta(Matrix * m)
+static int csr_build_flat_meta(Matrix * m, int span, int stride)
 {
-    if (m->flat_meta) return 0;
-    const int64_t nspans = (m->stored + kFlatSpan - 1) / kFlatSpan;
-    SPMV_TRY(dev_alloc(m, &m->flat_meta, 8 * (nspans + 1)));
-    SPMV_CUDA(cudaMemsetAsync(m->flat_meta, 0, sizeof(int32_t) * 8 * (size_t)(nspans + 1), m->stream));
+    if (m->flat_meta && m->flat_span == span) return 0;
+    if (m->flat_meta) {
+        cudaFree(m->flat_meta);
+        m->flat_meta = nullptr;
+    }
+    const int64_t nspans = (m->stored + span - 1) / span;
+    SPMV_TRY(dev_alloc((Matrix *)nullptr, &m->flat_meta, (int64_t)stride * (nspans + 1)));
+    m->flat_span = span;
+    SPMV_CUDA(cudaMemsetAsync(m->flat_meta, 0, sizeof(int32_t) * (size_t)stride * (size_t)(nspans + 1), m->stream));
     Scratch<int> flag;
     SPMV_TRY(flag.alloc(1));
     SPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), m->stream));
     const unsigned g1 = (unsigned)((nspans + 255) / 256);
     if (m->off64) {
-        csr_flat_first_row_kernel<int64_t><<<g1, 256, 0, m->stream>>>(m->rows, nspans, (const int64_t *)m->rp, m->flat_meta);
-        csr_flat_mask_kernel<int64_t><<<grid_for(m->rows, m->sm_count), 256, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, m->flat_meta, flag.p);
+        csr_flat_first_row_kernel<int64_t><<<g1, 256, 0, m->stream>>>(m->rows, nspans, span, stride, (const int64_t *)m->rp, m->flat_meta);
+        csr_flat_mask_kernel<int64_t><<<grid_for(m->rows, m->sm_count), 256, 0, m->stream>>>(m->rows, span, stride, (const int64_t *)m->rp, m->flat_meta, flag.p);
     } else {
-        csr_flat_first_row_kernel<uint32_t><<<g1, 256, 0, m->stream>>>(m->rows, nspans, (const uint32_t *)m->rp, m->flat_meta);
-        csr_flat_mask_kernel<uint32_t><<<grid_for(m->rows, m->sm_count), 256, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, m->flat_meta, flag.p);
+        csr_flat_first_row_kernel<uint32_t><<<g1, 256, 0, m->stream>>>(m->rows, nspans, span, stride, (const uint32_t *)m->rp, m->flat_meta);
+        csr_flat_mask_kernel<uint32_t><<<grid_for(m->rows, m->sm_count), 256, 0, m->stream>>>(m->rows, span, stride, (const uint32_t *)m->rp, m->flat_meta, flag.p);
     }
     SPMV_CUDA(cudaGetLastError());
     int has_empty = 0;
@@ -96,46 +111,61 @@ static int csr_build_flat_meta(Matrix * m)
 // (csr_spmv_inner_loop_regular_traffic, csr-matrix-spmv.cpp:35-47); 2 = "irregular traffic": y_i += sum_k
 // x[j_k], the gather alone without the values (:49-61).  The reference keeps the two as diagnostics; here
 // they split a kernel's time into its streaming and its gather part.
-template <typename OffT, int WARPS, bool MASK, int PROBE>
+template <typename OffT, int WARPS, int E, bool MASK, int PROBE>
 __global__ void __launch_bounds__(WARPS * 32)
 csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, const OffT * __restrict__ rp,
                 const int32_t * __restrict__ col, const double * __restrict__ val,
                 const int32_t * __restrict__ meta, const double * __restrict__ x, double * __restrict__ y, double alpha)
 {
-    __shared__ __align__(16) int32_t smark[MASK ? 1 : WARPS][kFlatSpan];
+    constexpr int SPAN = FlatShape<E>::span, STRIDE = FlatShape<E>::stride;
+    __shared__ __align__(16) int32_t smark[MASK ? 1 : WARPS][SPAN];
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t w = (int64_t)blockIdx.x * WARPS + warp;
     if (w >= nspans) return;  // no CTA-wide barrier below
-    const int64_t kw = w * kFlatSpan;
-    const int64_t kend = min(kw + (int64_t)kFlatSpan, stored);
-    const int64_t k0 = kw + 4 * lane;
+    const int64_t kw = w * SPAN;
+    const int64_t kend = min(kw + (int64_t)SPAN, stored);
+    const int64_t k0 = kw + E * lane;
     const uint64_t pol = policy_evict_first();
 
-    // the span in flight (arrays are padded past `stored` with (0, 0.0))
-    int4 c4 = make_int4(0, 0, 0, 0);
-    if (PROBE != 1) c4 = ldg_stream_i4(col + k0, pol);
-    double a[4] = {1.0, 1.0, 1.0, 1.0};
-    if (PROBE != 2) ldg_stream_d4(val + k0, a);
-    int r[4];
+    // the span in flight (arrays are padded past `stored` with (0, 0.0)): E/4 128-bit and E/4 256-bit loads per lane
+    int c[E];
+    double a[E];
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) {
+        int4 c4 = make_int4(0, 0, 0, 0);
+        if (PROBE != 1) c4 = ldg_stream_i4(col + k0 + 4 * q, pol);
+        c[4 * q] = c4.x; c[4 * q + 1] = c4.y; c[4 * q + 2] = c4.z; c[4 * q + 3] = c4.w;
+        double a4[4] = {1.0, 1.0, 1.0, 1.0};
+        if (PROBE != 2) ldg_stream_d4(val + k0 + 4 * q, a4);
+        a[4 * q] = a4[0]; a[4 * q + 1] = a4[1]; a[4 * q + 2] = a4[2]; a[4 * q + 3] = a4[3];
+    }
+    int r[E];
+    const int r_lo = __ldg(meta + (int64_t)STRIDE * w);
     if (MASK) {
-        const int r_lo = __ldg(meta + 8 * w);
-        const int4 mk = __ldg(reinterpret_cast<const int4 *>(meta + 8 * w + 4));
-        const int word = lane >> 3, sh = (4 * lane) & 31;
-        const unsigned m0 = (unsigned)mk.x, m1 = (unsigned)mk.y, m2 = (unsigned)mk.z, m3 = (unsigned)mk.w;
-        const unsigned mw = word == 0 ? m0 : word == 1 ? m1 : word == 2 ? m2 : m3;
-        const int below = (word > 0 ? __popc(m0) : 0) + (word > 1 ? __popc(m1) : 0) + (word > 2 ? __popc(m2) : 0);
-        r[0] = r_lo + below + __popc(mw & ((2u << sh) - 1u));  // rows started at entries 1 .. 4*lane
-        r[1] = r[0] + (int)((mw >> (sh + 1)) & 1u);
-        r[2] = r[1] + (int)((mw >> (sh + 2)) & 1u);
-        r[3] = r[2] + (int)((mw >> (sh + 3)) & 1u);
+        unsigned mk[E];
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q) {
+            const int4 t = __ldg(reinterpret_cast<const int4 *>(meta + (int64_t)STRIDE * w + 4) + q);
+            mk[4 * q] = (unsigned)t.x; mk[4 * q + 1] = (unsigned)t.y; mk[4 * q + 2] = (unsigned)t.z; mk[4 * q + 3] = (unsigned)t.w;
+        }
+        const int word = (E * lane) >> 5, sh = (E * lane) & 31;
+        unsigned mw = mk[0];
+        int below = 0;
+#pragma unroll
+        for (int q = 1; q < E; ++q) {
+            if (word >= q) { below += __popc(mk[q - 1]); mw = mk[q]; }
+        }
+        r[0] = r_lo + below + __popc(mw & ((2u << sh) - 1u));  // rows started at entries 1 .. E*lane
+#pragma unroll
+        for (int j = 1; j < E; ++j) r[j] = r[j - 1] + (int)((mw >> (sh + j)) & 1u);  // sh + j <= 31: sh is a multiple of E
     } else {
-        const int r_lo = __ldg(meta + 8 * w);
         // marks: mark[k - kw] = (last row that starts at entry k) - r_lo, 0 where no row starts
         int32_t * mark = smark[warp];
-        *reinterpret_cast<int4 *>(mark + 4 * lane) = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q) *reinterpret_cast<int4 *>(mark + E * lane + 4 * q) = make_int4(0, 0, 0, 0);
         __syncwarp();
         for (int64_t rb = (int64_t)r_lo + 1; rb < rows; rb += 32) {
             const int64_t rr = rb + lane;
@@ -144,11 +174,15 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
             if (__shfl_sync(0xffffffffu, p >= kend ? 1 : 0, 31)) break;  // row_ptr is monotone
         }
         __syncwarp();
-        int4 o = *reinterpret_cast<const int4 *>(mark + 4 * lane);
-        o.y = max(o.x, o.y);
-        o.z = max(o.y, o.z);
-        o.w = max(o.z, o.w);
-        int run = o.w;  // inclusive max-scan of the lanes' last marks
+        int o[E];
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q) {
+            const int4 t = *reinterpret_cast<const int4 *>(mark + E * lane + 4 * q);
+            o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 1; j < E; ++j) o[j] = max(o[j - 1], o[j]);
+        int run = o[E - 1];  // inclusive max-scan of the lanes' last marks
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, run, d);
@@ -156,40 +190,40 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
         }
         int before = __shfl_up_sync(0xffffffffu, run, 1);
         if (lane == 0) before = 0;
-        r[0] = r_lo + max(before, o.x);
-        r[1] = r_lo + max(before, o.y);
-        r[2] = r_lo + max(before, o.z);
-        r[3] = r_lo + max(before, o.w);
+#pragma unroll
+        for (int j = 0; j < E; ++j) r[j] = r_lo + max(before, o[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < E; ++j)
         if (k0 + j >= kend) r[j] = -1;
 
     // Everything above reads only the immutable matrix; x and y may come from the previous launch.
     if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
-    double x0 = 1.0, x1 = 1.0, x2 = 1.0, x3 = 1.0;
-    if (PROBE != 1) { x0 = __ldg(x + c4.x); x1 = __ldg(x + c4.y); x2 = __ldg(x + c4.z); x3 = __ldg(x + c4.w); }
-    const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
-    warp_segmented_add4(lane, r, p, y, alpha);
+    double p[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) p[j] = PROBE != 1 ? __ldg(x + c[j]) : 1.0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) p[j] = __dmul_rn(a[j], p[j]);
+    warp_segmented_add<E>(lane, r, p, y, alpha);
 }
 
-template <typename OffT, int WARPS>
+template <typename OffT, int WARPS, int E>
 static int launch_flat_variant(Matrix * m)
 {
-    SPMV_TRY(csr_build_flat_meta(m));
+    SPMV_TRY(csr_build_flat_meta(m, FlatShape<E>::span, FlatShape<E>::stride));
     if (m->dry_run) return 0;
-    const int64_t nspans = (m->stored + kFlatSpan - 1) / kFlatSpan;
+    const int64_t nspans = (m->stored + FlatShape<E>::span - 1) / FlatShape<E>::span;
     const int64_t grid = (nspans + WARPS - 1) / WARPS;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     SPMV_TRY(clear_y_for_beta0(m));
     const RunMode rm = run_mode(m);
-    auto kernel = m->flat_has_empty ? csr_flat_kernel<OffT, WARPS, false, 0> : csr_flat_kernel<OffT, WARPS, true, 0>;
-    if (WARPS == 4 && m->opt_csr_probe == 1)
-        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, false, 1> : csr_flat_kernel<OffT, 4, true, 1>;
-    else if (WARPS == 4 && m->opt_csr_probe == 2)
-        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, false, 2> : csr_flat_kernel<OffT, 4, true, 2>;
+    auto kernel = m->flat_has_empty ? csr_flat_kernel<OffT, WARPS, E, false, 0> : csr_flat_kernel<OffT, WARPS, E, true, 0>;
+    if (WARPS == 4 && E == 4 && m->opt_csr_probe == 1)
+        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, 4, false, 1> : csr_flat_kernel<OffT, 4, 4, true, 1>;
+    else if (WARPS == 4 && E == 4 && m->opt_csr_probe == 2)
+        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, 4, false, 2> : csr_flat_kernel<OffT, 4, 4, true, 2>;
     else if (m->opt_csr_probe != 0)
-        return fail(SPMVB200_ERR_INVALID, "csr.probe must be 0, 1 or 2 (and csr.threads 128)");
+        return fail(SPMVB200_ERR_INVALID, "csr.probe must be 0, 1 or 2 (with csr.threads 128 and csr.entries 4)");
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, WARPS * 32u, 0, m->stream, rm.pdl, m->rows,
                             m->stored, nspans, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col,
                             (const double *)m->val, (const int32_t *)m->flat_meta, (const double *)m->x, m->y, m->alpha));
@@ -197,17 +231,31 @@ static int launch_flat_variant(Matrix * m)
     return 0;
 }
 
+template <typename OffT>
+static int launch_flat_off(Matrix * m, int threads, int entries)
+{
+    if (entries == 4) {
+        if (threads == 64) return launch_flat_variant<OffT, 2, 4>(m);
+        if (threads == 128) return launch_flat_variant<OffT, 4, 4>(m);
+        if (threads == 256) return launch_flat_variant<OffT, 8, 4>(m);
+    } else if (entries == 8) {
+        if (threads == 64) return launch_flat_variant<OffT, 2, 8>(m);
+        if (threads == 128) return launch_flat_variant<OffT, 4, 8>(m);
+        if (threads == 256) return launch_flat_variant<OffT, 8, 8>(m);
+    } else {
+        return fail(SPMVB200_ERR_INVALID, "csr.entries must be 4 or 8");
+    }
+    return fail(SPMVB200_ERR_INVALID, "csr.threads must be 64, 128 or 256 for the flat kernel");
+}
+
 int launch_csr_flat(Matrix * m)
 {
     const int threads = (int)(m->opt_csr_threads ? m->opt_csr_threads : 128);
+    // the probes are built for 4 entries per lane only
+    const int entries = m->opt_csr_probe ? 4 : (int)(m->opt_csr_entries ? m->opt_csr_entries : 4);
     m->kernel_name = m->opt_csr_probe == 1 ? "csr_flat_kernel<regular traffic>"
                      : m->opt_csr_probe == 2 ? "csr_flat_kernel<irregular traffic>" : "csr_flat_kernel";
-    switch (threads) {
-    case 64: return m->off64 ? launch_flat_variant<int64_t, 2>(m) : launch_flat_variant<uint32_t, 2>(m);
-    case 128: return m->off64 ? launch_flat_variant<int64_t, 4>(m) : launch_flat_variant<uint32_t, 4>(m);
-    case 256: return m->off64 ? launch_flat_variant<int64_t, 8>(m) : launch_flat_variant<uint32_t, 8>(m);
-    }
-    return fail(SPMVB200_ERR_INVALID, "csr.threads must be 64, 128 or 256 for the flat kernel");
+    return m->off64 ? launch_flat_off<int64_t>(m, threads, entries) : launch_flat_off<uint32_t>(m, threads, entries);
 }
 
 }  // namespace spmvb200

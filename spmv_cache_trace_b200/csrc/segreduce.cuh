@@ -1,5 +1,5 @@
 // segreduce.cuh -- y[row] += sum of the products of a run of equal row indices, for a warp that
-// holds 128 consecutive entries, four per lane (lane l: entries 4l..4l+3).
+// holds 32*E consecutive entries, E per lane (lane l: entries E*l .. E*l+E-1).
 //
 // Each lane sums its own runs serially.  Runs that lie strictly inside a lane are added to y at
 // once; the lane's first and last run may continue in the neighbouring lanes, so the sums of the
@@ -13,16 +13,17 @@
 
 namespace spmvb200 {
 
-// alpha scales every sum on its way out (alpha = 1.0 is exact).
-__device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4], const double (&p)[4],
-                                                    double * __restrict__ y, double alpha = 1.0)
+// alpha scales every sum on its way out (alpha = 1.0 is exact).  E = entries per lane.
+template <int E>
+__device__ __forceinline__ void warp_segmented_add(int lane, const int (&r)[E], const double (&p)[E],
+                                                   double * __restrict__ y, double alpha = 1.0)
 {
     using ptx::red_add_f64;
     int cur_row = r[0];
     double cur = p[0], head = 0.0;
     bool single = true;  // the lane holds one run only
 #pragma unroll
-    for (int j = 1; j < 4; ++j) {
+    for (int j = 1; j < E; ++j) {
         if (r[j] == cur_row) {
             cur = __dadd_rn(cur, p[j]);
         } else {
@@ -33,10 +34,10 @@ __device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4],
         }
     }
     // across lanes: my first run may continue the previous lane's last run
-    const int prev_last = __shfl_up_sync(0xffffffffu, r[3], 1);
+    const int prev_last = __shfl_up_sync(0xffffffffu, r[E - 1], 1);
     const int next_first = __shfl_down_sync(0xffffffffu, r[0], 1);
     const bool cont = lane > 0 && prev_last == r[0];
-    const bool next_cont = lane < 31 && next_first == r[3];
+    const bool next_cont = lane < 31 && next_first == r[E - 1];
     const unsigned heads = __ballot_sync(0xffffffffu, !(single && cont));
     const int dist = lane - (31 - __clz(heads & (0xffffffffu >> (31 - lane))));
     const int longest = __reduce_max_sync(0xffffffffu, dist);
@@ -50,7 +51,13 @@ __device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4],
     }
     const double prev_s = __shfl_up_sync(0xffffffffu, s, 1);
     if (!single && r[0] >= 0) red_add_f64(y + r[0], __dmul_rn(alpha, cont ? __dadd_rn(prev_s, head) : head));
-    if (!next_cont && r[3] >= 0) red_add_f64(y + r[3], __dmul_rn(alpha, s));
+    if (!next_cont && r[E - 1] >= 0) red_add_f64(y + r[E - 1], __dmul_rn(alpha, s));
+}
+
+__device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4], const double (&p)[4],
+                                                    double * __restrict__ y, double alpha = 1.0)
+{
+    warp_segmented_add<4>(lane, r, p, y, alpha);
 }
 
 }  // namespace spmvb200

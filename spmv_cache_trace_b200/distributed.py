@@ -140,7 +140,12 @@ class DistributedSpMV:
     """Iterated x <- A x on a row partition of A, local rows already resident as a CSR DeviceMatrix."""
 
     def __init__(self, sp, torch, dist, local, starts, rank: int, mode: str = "auto", overlap: bool = True,
-                 spare_ctas: int = 2):
+                 spare_ctas: int = 2, fmt=None, column_split: bool = False):
+        """`local`: this rank's rows.  A CSR block is analysed (column span -> halo or all-gather, interior/boundary row
+        split).  `column_split` (CSR block, all-gather exchange): the block is cut by COLUMNS instead -- the entries
+        that reference the rank's own slice of x form one matrix, which runs while x is being gathered, the rest a
+        second one that runs afterwards and adds to the same rows; for matrices without a band (power law) this is the
+        only way to overlap.  `fmt`: format the pieces are converted to (e.g. HYB for BASELINE configs[3])."""
         self.sp, self.torch, self.dist = sp, torch, dist
         self.rank, self.starts = rank, np.asarray(starts, dtype=np.int64)
         self.P = len(starts) - 1
@@ -151,8 +156,18 @@ class DistributedSpMV:
         # ping-pong x buffers (+ slack so vector loads past the end stay in bounds)
         self.X = [torch.zeros(self.n + 16, dtype=torch.float64, device=dev) for _ in range(2)]
         self.compute = torch.cuda.Stream()
-        self.comm = torch.cuda.Stream()
-        span = local.column_span(self.s, self.e)
+        # the exchange runs on a high-priority stream: its (cooperative) NCCL kernel must get SM slots while the
+        # interior SpMV, whose grid fills every SM for the whole step, is running
+        self.comm = torch.cuda.Stream(priority=-1)
+        self.accumulate = set()  # ids of blocks that add to rows another block of the same step has written
+        if column_split and local.info.format == sp.CSR and self.P > 1:
+            span = {"col_min": 0, "col_max": self.n - 1, "lo_end": self.rows, "hi_begin": 0}
+            mode = "allgather"
+        elif local.info.format == sp.CSR:
+            span = local.column_span(self.s, self.e)
+        else:  # ELL / COO / hybrid row blocks: no column analysis, every rank is taken to need all of x
+            span = {"col_min": 0, "col_max": self.n - 1, "lo_end": self.rows, "hi_begin": 0}
+            mode = "allgather"
         need = [(0, 0)] * self.P
         mine = torch.tensor([span["col_min"], span["col_max"] + 1], dtype=torch.int64, device=dev)
         if self.P > 1:
@@ -164,10 +179,21 @@ class DistributedSpMV:
         self.plan = make_exchange_plan(self.starts, need, rank, mode)
         blocks = split_rows(span["lo_end"], span["hi_begin"], self.rows) if overlap and self.P > 1 else [(0, self.rows, True)]
         self.blocks = []
-        for b, e, remote in blocks:
-            A = local if (b, e) == (0, self.rows) else local.row_block(b, e)
+        pieces = None
+        if column_split and local.info.format == sp.CSR and self.P > 1:
+            inside, outside = local.column_split(self.s, self.e)
+            if fmt is not None and fmt != sp.CSR:
+                inside, outside = inside.convert(fmt), outside.convert(fmt)
+            pieces = [(inside, 0, self.rows, False), (outside, 0, self.rows, True)]
+            self.accumulate.add(id(outside))
+        elif fmt is not None and fmt != local.info.format:
+            local = local.convert(fmt)
+            blocks = [(0, self.rows, True)]
+        if pieces is None:
+            pieces = [(local if (b, e) == (0, self.rows) else local.row_block(b, e), b, e, remote) for b, e, remote in blocks]
+        for A, b, e, remote in pieces:
             A.set_stream(self.compute.cuda_stream)
-            A.set_option("beta0", 1)
+            A.set_option("beta0", 0 if id(A) in self.accumulate else 1)
             if not remote and self.P > 1:
                 # The interior kernel is persistent and would fill every SM; keep CTA slots free so
                 # the NCCL kernel of the concurrent exchange is not locked out until it drains.
@@ -223,10 +249,167 @@ class DistributedSpMV:
 
 
 # --------------------------------------------------------------------------------------------
+# bench.py --gpus N --workload c4_hyb: BASELINE configs[3], hybrid ELL+COO on the R-MAT 2^26 x 32 matrix, row-partitioned
+# --------------------------------------------------------------------------------------------
+
+def bench_hybrid(args) -> int:
+    """Rows cut into `world` blocks of equal non-zeros; every rank converts ITS rows to the hybrid format (the ELL part
+    and the COO tail both follow the row owner) and x is all-gathered between iterations: a power-law
+    matrix references all of x from every block, so there is no halo to exploit and nothing to overlap with."""
+    import torch
+    import torch.distributed as dist
+
+    import spmv_cache_trace_b200 as sp
+    from bench import METRIC, NOMINAL_HBM_GBS, UNIT, ClockSampler, measured_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    sp.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    scale_log2 = int(os.environ.get("SPMV_BENCH_RMAT_SCALE", "26"))
+    ef = int(os.environ.get("SPMV_BENCH_RMAT_EF", "32"))
+    seed = 0x5EED0004
+    N = 1 << scale_log2
+    peak, peak_src = measured_peak()
+
+    full = sp.generators.rmat(scale_log2, ef, seed, fmt=sp.CSR)  # every rank: the partition needs the global row_ptr
+    starts = sp.partition.rows_nnz(full, world)
+    s, e = int(starts[rank]), int(starts[rank + 1])
+    block = full.row_block(s, e)
+    nnz = full.num_entries
+    del full
+    # the reference's hybrid of this rank's rows defines the bytes counted (one ELL part + one COO tail per rank) ...
+    inf = block.convert(sp.HYB).info
+    sizes = torch.tensor([12 * inf.num_ell_entries + 16 * inf.num_coo_entries, inf.num_coo_entries, inf.ell_row_length],
+                         dtype=torch.int64, device="cuda")
+    # ... what runs is that block cut by columns (own slice of x / the rest), each piece converted to hybrid, so that
+    # the own-columns piece overlaps the all-gather (SPMV_COLUMN_SPLIT=0: one hybrid matrix per rank, no overlap)
+    split = os.environ.get("SPMV_COLUMN_SPLIT", "1") != "0" and world > 1
+    allsizes = [torch.zeros_like(sizes) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allsizes, sizes)
+    else:
+        allsizes = [sizes]
+    per_rank = [[int(v) for v in t.tolist()] for t in allsizes]
+    B = sum(p[0] for p in per_rank) + 16 * N
+
+    ALPHA = 1.0 / 8192.0  # keeps x_(k+1) = alpha A x_k finite: hub rows of the R-MAT matrix sum ~10^6 entries
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng = DistributedSpMV(sp, torch, dist, block, starts, rank, mode="allgather", overlap=False, fmt=sp.HYB, column_split=split)
+    del block
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    eng.set_x(torch.rand(e - s, generator=g, dtype=torch.float64) - 0.5)
+    for _ in range(max(args.warmup, 3)):
+        eng.step(scale=ALPHA)
+    eng.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = sp.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(eng.compute)
+    for _ in range(args.steps):
+        eng.step(scale=ALPHA)
+    ev1.record(eng.compute)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if os.environ.get("SPMV_DEBUG_TIMES"):
+        print(f"[rank {rank}] rows {e - s} step {float(ms.item()) / args.steps:.3f} ms pieces "
+              f"{[(int(A.info.ell_row_length), int(A.info.num_coo_entries), A.get_option('coo.col_block_log2')) for A, _, _, _ in eng.blocks]}",
+              flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    t = float(ms.item()) * 1e-3 / args.steps
+    xnorm = float(torch.linalg.vector_norm(eng.x_local()).item())
+    launches = int(sp.launch_count() - launches0)
+    # end to end: the rank's slice of x up from pinned host memory, its slice of the result back
+    hx = torch.empty(e - s, dtype=torch.float64).pin_memory()
+    hy = torch.empty(e - s, dtype=torch.float64).pin_memory()
+    hx.copy_(torch.rand(e - s, dtype=torch.float64) - 0.5)
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    ev0.record(eng.compute)
+    for _ in range(e2e_steps):
+        with torch.cuda.stream(eng.compute):
+            eng.x_local().copy_(hx, non_blocking=True)
+        eng.step(scale=ALPHA)
+        with torch.cuda.stream(eng.compute):
+            hy.copy_(eng.x_local(), non_blocking=True)
+        eng.compute.synchronize()
+    ev1.record(eng.compute)
+    torch.cuda.synchronize()
+    ems = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    kernel = eng.blocks[0][0].kernel_name
+    recv = eng.plan.recv_bytes
+    pieces = [{"rows": int(A.info.rows), "ell_row_length": int(A.info.ell_row_length), "num_coo_entries": int(A.info.num_coo_entries),
+               "needs_remote_x": bool(r)} for A, _, _, r in eng.blocks]
+    del eng
+    sampler.stop()
+
+    single = None
+    if world > 1 and rank == 0 and not getattr(args, "no_single", False):
+        try:
+            H = sp.generators.rmat(scale_log2, ef, seed, fmt=sp.HYB)
+            steps1 = max(3, min(args.steps, 10))
+            total_ms, _ = sp.time_rotating([H], steps1, 3, False)
+            single = {"ms_per_step": total_ms / steps1, "algorithmic_bytes": int(H.algorithmic_bytes())}
+            del H
+        except Exception as ex:
+            single = {"error": str(ex)}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": B / t / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c4_hyb_row_partitioned", "description": f"row-partitioned hybrid ELL+COO, R-MAT 2^{scale_log2} x {ef} "
+                       "(config 4), x_(k+1) = alpha A x_k, one step = all-gather of x + ELL kernel + COO kernel per rank",
+                       "rows": N, "nonzeros": int(nnz), "algorithmic_bytes": int(B),
+                       "partition": "balanced non-zeros (spmvb200_partition_rows_nnz)", "row_starts": [int(v) for v in starts],
+                       "per_rank": [{"matrix_size": p[0], "num_coo_entries": p[1], "ell_row_length": p[2]} for p in per_rank],
+                       "exchange": "allgather", "recv_bytes_per_step_per_rank": int(recv),
+                       "overlap": "column split: the entries that reference the rank's own slice of x run during the all-gather"
+                                  if split else "none", "rank0_pieces": pieces,
+                       "l2": "working set per rank far larger than L2"},
+            "gflops": 2.0 * nnz / t / 1e9, "frac_of_8TBs_nominal_per_gpu": B / t / 1e9 / world / NOMINAL_HBM_GBS,
+            "roofline": {"bound": "hbm", "achieved": B / world / t / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": B / world / t / 1e9 / peak, "traffic": None,
+                         "kernel": kernel + " (per rank; step time includes the exchange)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(B / world)},
+            "e2e": {"value": B / (float(ems.item()) * 1e-3 / e2e_steps) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * N,
+                    "d2h_bytes_per_step": 8 * N, "ms_per_step": float(ems.item()) / e2e_steps,
+                    "call": "per rank: pinned x slice -> device, exchange + SpMV, y slice -> pinned host"},
+            "gpu_launches": launches, "clocks": sampler.summary(t0, t1), "x_norm": xnorm,
+        }
+        if single and "ms_per_step" in single:
+            line["single_gpu"] = {"ms_per_step": single["ms_per_step"], "gbs": single["algorithmic_bytes"] / (single["ms_per_step"] * 1e-3) / 1e9,
+                                  "speedup": single["ms_per_step"] / (t * 1e3)}
+        elif single:
+            line["single_gpu"] = single
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
 # bench.py --gpus N  (N > 1)
 # --------------------------------------------------------------------------------------------
 
 def bench_main(args) -> int:
+    if getattr(args, "workload", None) == "c4_hyb":
+        return bench_hybrid(args)
     import torch
     import torch.distributed as dist
 

@@ -347,6 +347,13 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
             y = csr_matrix.spmv(A, x, y0.copy())
             assert_within(y, yref, bound, f"csr threads={threads} tile={tile} stages={stages} lanes={lanes} "
                                           f"algo={algo} pdl={pdl} ctas={ctas}")
+    A.set_option("csr.algo", 4)  # the flat kernel with 8 entries per lane (256-entry spans), rows with and without gaps
+    for threads in (64, 128, 256):
+        A.set_option("csr.threads", threads)
+        A.set_option("csr.entries", 8)
+        assert_within(csr_matrix.spmv(A, x, y0.copy()), yref, bound, f"flat, 8 entries per lane, threads={threads}")
+        A.set_option("csr.entries", 4)
+        assert_within(csr_matrix.spmv(A, x, y0.copy()), yref, bound, f"flat, back to 4 entries per lane, threads={threads}")
     for fmt, kw in (("coo", {}), ("coo", {"mode": COO_ATOMIC}), ("hybrid", {})):
         B = build(fmt, mm, **kw)
         y = B * x + y0
@@ -521,6 +528,9 @@ def test_config1_poisson2d_1000x1000_full_size(oracle, fmt):
         for algo in (1, 2, 3, 4, 5):
             A.set_option("csr.algo", algo)
             assert np.array_equal(A * x, yref), f"csr.algo={algo}"
+        A.set_option("csr.algo", 4)
+        A.set_option("csr.entries", 8)  # no empty rows: the bit-mask path with 256-entry spans
+        assert np.array_equal(A * x, yref), "flat, 8 entries per lane"
 
 
 def test_config2_poisson3d_128_ell_full_size(oracle):
@@ -777,6 +787,31 @@ def test_launch_ordering_follows_the_data_hazards(oracle):
     A.bind_x(A.y_device())
     A.spmv(); A.spmv()
     assert A.get_option("last_launch.overlapped") == 0
+
+
+def test_column_split_is_a_partition_of_the_entries(oracle):
+    """spmvb200_csr_column_split: A = inside + outside, entry for entry (the multi-GPU overlap for unbanded matrices)."""
+    rng = np.random.default_rng(31)
+    rows, cols = 2500, 4000
+    i, j, a = ragged_matrix(rng, rows, cols, long_rows=(7, 900), long_len=1500, short_max=10, empty_every=9)
+    x = rng.uniform(-1, 1, cols)
+    O = oracle.csr(rows, cols, i, j, a)
+    A = csr_matrix.from_matrix_market(matrix_market.from_entries(rows, cols, i, j, a))
+    for cb, ce in ((1000, 2600), (0, cols), (0, 0), (3999, 4000)):
+        inside, outside = A.column_split(cb, ce)
+        ei, eo = inside.export(), outside.export()
+        rp, cj, av = np.asarray(O.row_ptr, np.int64), np.asarray(O.column_index), np.asarray(O.value)
+        sel = (cj >= cb) & (cj < ce)
+        row_of = np.repeat(np.arange(rows), np.diff(rp))
+        for e, mask in ((ei, sel), (eo, ~sel)):
+            assert np.array_equal(e["column_index"], cj[mask]) and np.array_equal(e["value"], av[mask])
+            assert np.array_equal(np.diff(e["row_ptr"]), np.bincount(row_of[mask], minlength=rows))
+        assert inside.num_entries + outside.num_entries == A.num_entries
+        y = inside * x + outside * x
+        assert_within(y, oracle.csr_spmv(O, x), 2 * oracle.csr_abs_rowsum(O, x), f"split [{cb},{ce})")
+        for fmt in (sp.HYB, sp.COO):
+            assert_within(inside.convert(fmt) * x + outside.convert(fmt) * x, oracle.csr_spmv(O, x),
+                          2 * oracle.csr_abs_rowsum(O, x), f"split [{cb},{ce}) as format {fmt}")
 
 
 def test_kernels_really_launch():

@@ -70,6 +70,41 @@ def main():
                 del full
             del eng
             dist.barrier()
+    # BASELINE configs[3] at reduced scale: hybrid ELL+COO row blocks of an R-MAT matrix, equal non-zeros per rank,
+    # x all-gathered (uneven slices), y = alpha*A*x through the kernels' alpha / beta0 path
+    scale, ef, seed, alpha = 18, 32, 0x5EED0004, 1.0 / 64.0
+    full = sp.generators.rmat(scale, ef, seed, fmt=sp.CSR)
+    Nr = 1 << scale
+    rstarts = sp.partition.rows_nnz(full, world)
+    rs, re_ = int(rstarts[rank]), int(rstarts[rank + 1])
+    for fmt, split in ((sp.HYB, False), (sp.HYB, True), (sp.COO, False), (sp.COO, True), (sp.CSR, True)):
+        if split:  # the block cut by columns: own slice of x (overlaps the all-gather) / the rest (adds afterwards)
+            block = full.row_block(rs, re_)
+            eng = DistributedSpMV(sp, torch, dist, block, rstarts, rank, mode="auto", overlap=True, fmt=fmt, column_split=True)
+        else:
+            block = full.row_block(rs, re_).convert(fmt)
+            eng = DistributedSpMV(sp, torch, dist, block, rstarts, rank, mode="auto", overlap=True)
+        xr = np.random.default_rng(7).uniform(-1, 1, Nr)
+        eng.set_x(xr[rs:re_])
+        for _ in range(args.iters):
+            eng.step(scale=alpha)
+        eng.synchronize()
+        parts = [torch.zeros(int(rstarts[q + 1] - rstarts[q]), dtype=torch.float64, device="cuda") for q in range(world)]
+        dist.all_gather(parts, eng.x_local().contiguous())
+        got = torch.cat(parts).cpu().numpy()
+        if rank == 0:
+            x = xr.copy()
+            for _ in range(args.iters):
+                x = alpha * (full * x)
+            err = np.abs(got - x).max()
+            lim = 1e-9 * max(1.0, np.abs(x).max())
+            status = "ok" if err <= lim else "FAIL"
+            ok = ok and err <= lim
+            print(f"dist_check P={world} rmat 2^{scale}x{ef} format={sp.FORMAT_NAMES[fmt]} column_split={split} plan={eng.plan.mode} "
+                  f"row_starts={[int(v) for v in rstarts]} kernels={[A.kernel_name for A, _, _, _ in eng.blocks]} "
+                  f"max|err|={err:.3e} {status}", flush=True)
+        del eng, block
+        dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
         sys.exit(1)
