@@ -360,6 +360,8 @@ def bench_hybrid(args) -> int:
     if world > 1 and rank == 0 and not getattr(args, "no_single", False):
         try:
             H = sp.generators.rmat(scale_log2, ef, seed, fmt=sp.HYB)
+            H.set_option("beta0", 1)  # the same operation the ranks perform: y = alpha*A*x, no exchange
+            H.set_alpha(ALPHA)
             steps1 = max(3, min(args.steps, 10))
             total_ms, _ = sp.time_rotating([H], steps1, 3, False)
             single = {"ms_per_step": total_ms / steps1, "algorithmic_bytes": int(H.algorithmic_bytes())}
@@ -507,6 +509,8 @@ def bench_main(args) -> int:
     if world > 1 and rank == 0 and not getattr(args, "no_single", False):
         try:
             full = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR)
+            full.set_option("beta0", 1)  # the same operation the ranks perform: y = alpha*A*x, no exchange
+            full.set_alpha(SCALE)
             total_ms, _ = sp.time_rotating([full], max(3, min(args.steps, 10)), 3, False)
             single = total_ms / max(3, min(args.steps, 10))
             del full
