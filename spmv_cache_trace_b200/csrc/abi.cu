@@ -1,7 +1,7 @@
 // abi.cu -- the extern "C" surface of libspmvb200.so (see include/spmv_b200.h).
 //
 // Thin by design: argument checks, handle bookkeeping, host<->device copies, and dispatch to the
-// builders (builders.cu, generators.cu) and kernel launchers (kernels.cu).  No arithmetic of the
+// builders (builders.cu, generators.cu) and kernel launchers (kernels_*.cu).  No arithmetic of the
 // SpMV path is done on the host anywhere in this library.
 #include "common.cuh"
 #include "mm_host.hpp"

@@ -1,16 +1,20 @@
 // common.cuh -- internal declarations shared by the translation units of libspmvb200.so.
 //
-// Device layouts (all allocations 256 B aligned by cudaMalloc):
-//   CSR  row_ptr  uint32[rows+1] (int64 when stored >= 2^32), column_index int32[], value f64[];
-//        column_index/value are padded with (0, 0.0) up to a whole number of nnz tiles so a
-//        bulk-async (TMA) copy of any tile stays inside the allocation;
-//        tile_row int32[ntiles+1]: row that owns the first non-zero of each tile.
+// Device layouts (all allocations 256 B aligned by cudaMalloc; streamed arrays carry >= 8192 zeroed
+// elements of slack so vector loads and bulk copies of a last partial span stay inside the allocation):
+//   CSR  row_ptr uint32[rows+1] (int64 when stored >= 2^32), column_index int32[], value f64[], plus the
+//        launch metadata of the selected kernel, built by spmvb200_prepare or the first launch:
+//        flat_meta  {first row, -, -, -, E mask words} per 32*E stored entries (flat kernel, default);
+//        slice_col / slice_val  a second copy of the entries with every 32-row slice stored slot-major
+//                   (sliced kernel, long regular rows; the row-major copy may then be dropped);
+//        tile_row / span_row    tile and span tables of the first-generation stream / warp kernels.
 //   ELL  COLUMN-MAJOR: slot l of row i lives at l*pitch + i (pitch = rows rounded up to 32), so
-//        the 32 lanes of a warp read 32 consecutive rows of one slot with 128-bit loads.
+//        the 32 lanes of a warp read 32 consecutive rows of one slot with 64..256-bit loads.
 //        (The reference layout is row-major, k = i*row_length + l, ell-matrix.cpp:254.)
-//   COO  row_index int32[], column_index int32[], value f64[], padded to whole tiles;
-//        SEGMENTED mode keeps them stably sorted by row.
-//   HYB  the ELL arrays plus the COO arrays of the tail (row-major sorted, as the reference builds them).
+//   COO  row_index int32[], column_index int32[], value f64[]; SEGMENTED mode stores them stably sorted
+//        by row and, when x is much larger than L2, partitioned by column block (coo_col_shift).
+//   HYB  the ELL arrays plus the COO arrays of the tail (row-major sorted as the reference builds them,
+//        then possibly column-blocked like COO).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -237,7 +241,7 @@ inline RunMode run_mode(Matrix * m)
     return r;
 }
 
-// ---- launchers implemented in kernels.cu ---------------------------------------------------
+// ---- launchers (kernels_csr*.cu, kernels_ell.cu, kernels_coo.cu) ------------------------------
 int launch_csr(Matrix * m);
 int launch_ell(Matrix * m, bool accumulate_into_y);
 int launch_coo(Matrix * m);

@@ -1,9 +1,13 @@
-// kernels_csr.cu -- CSR SpMV for sm_100a:  y += A*x.
+// kernels_csr.cu -- CSR SpMV for sm_100a:  y += A*x.  Kernel selection (launch_csr) and the shared-memory
+// staged "stream" kernel.
 //
 // Replaces csr_spmv + csr_spmv_inner_loop (reference matrix/csr-matrix-spmv.cpp:21-33, 63-76),
 // the body of csr_spmv_kernel::run (kernels/csr-spmv.cpp:64-67).
 //
-// Design notes (they hold for the ELL and COO kernels too):
+// The default kernels are register-staged and live in kernels_csr_flat.cu (split by non-zeros) and
+// kernels_csr_sliced.cu (lane per row, long regular rows); the stream kernel below is the first
+// generation, kept as "csr.algo" 1 / 2 and as the path that sums rows inside a tile in the reference's
+// order.  Its design notes; the points on reductions, PDL and cache policy hold for every kernel:
 //   * SpMV is HBM-bandwidth bound (2 flop per 12 streamed bytes): what matters is keeping enough
 //     bytes in flight and touching every matrix byte once.  The non-zeros (not the rows) are cut
 //     into equal contiguous chunks, one per CTA of a persistent grid, so every CTA streams the same
