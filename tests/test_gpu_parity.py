@@ -607,6 +607,82 @@ def test_stencil27_rowsum_property_large():
     assert np.array_equal(y3, expect)
 
 
+def _free_gib():
+    import ctypes
+    try:
+        cudart = ctypes.CDLL("libcudart.so")
+    except OSError:
+        return 1e9  # cannot tell: let the library report an allocation failure
+    free, total = ctypes.c_size_t(), ctypes.c_size_t()
+    if cudart.cudaMemGetInfo(ctypes.byref(free), ctypes.byref(total)) != 0:
+        return 1e9
+    return free.value / 2 ** 30
+
+
+def test_config5_stencil27_512_full_size_rowsum():
+    """BASELINE config 5 at full size on one GPU (134 217 728 rows, 3 609 741 304 non-zeros): with x = 1 every
+    interior row of the 27-point operator sums to exactly 0 and the boundary rows to 27 - (#neighbours + 1)."""
+    if _free_gib() < 120:
+        pytest.skip("needs ~100 GB of device memory")
+    n = 512
+    A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+    assert A.num_entries == (3 * n - 2) ** 3 == 3609741304
+    assert A.algorithmic_bytes() == 46001250212
+    y = A * np.ones(n ** 3)
+    assert A.kernel_name == "csr_sliced_kernel"
+    y3 = y.reshape(n, n, n)
+    assert np.all(y3[1:-1, 1:-1, 1:-1] == 0.0)
+    idx = np.arange(n)
+    span = np.where((idx == 0) | (idx == n - 1), 2, 3)
+    assert np.array_equal(y3, 27.0 - (span[:, None, None] * span[None, :, None] * span[None, None, :]))
+    A.set_option("csr.algo", 4)  # the flat kernel on the same matrix (integer data: every order is exact)
+    assert np.array_equal(A * np.ones(n ** 3), y)
+
+
+def test_config3_rmat24_full_size_cross_format():
+    """BASELINE config 3 at full size (R-MAT 2^24 x 16, 263 434 015 non-zeros after dedupe): COO (both modes) agrees
+    with CSR, and the product is linear, within the per-row tolerance scaled by the largest row bound."""
+    if _free_gib() < 60:
+        pytest.skip("needs ~40 GB of device memory")
+    scale, ef, seed = 24, 16, 0x5EED0003
+    n = 1 << scale
+    A = sp.generators.rmat(scale, ef, seed)
+    assert A.num_entries == 263434015
+    rng = np.random.default_rng(24)
+    x1, x2 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    y1, y2 = A * x1, A * x2
+    lim = 1e-12 * 16 * max(np.abs(y1).max(), 1.0) * 64  # rows hold up to ~3e5 entries of size <= 1
+    y12 = A * (x1 + 2 * x2)
+    assert np.abs(y12 - (y1 + 2 * y2)).max() <= 4 * lim
+    for mode in (COO_SEGMENTED, COO_ATOMIC):
+        C = A.convert(sp.COO, mode)
+        yc = C * x1
+        assert C.kernel_name == "coo_warp4_kernel"
+        assert np.abs(yc - y1).max() <= lim, f"coo mode {mode}"
+        del C
+
+
+def test_config4_rmat26_full_size_hybrid():
+    """BASELINE config 4 at full size (R-MAT 2^26 x 32, 2 103 842 462 non-zeros): the hybrid split follows the
+    reference rule (W = 2), the tail is stored in column blocks, and hybrid agrees with CSR."""
+    if _free_gib() < 150:
+        pytest.skip("needs ~120 GB of device memory")
+    scale, ef, seed = 26, 32, 0x5EED0004
+    n = 1 << scale
+    A = sp.generators.rmat(scale, ef, seed)
+    assert A.num_entries == 2103842462
+    rng = np.random.default_rng(26)
+    x = rng.uniform(-1, 1, n)
+    y = A * x
+    H = A.convert(sp.HYB)
+    del A
+    assert (H.ell_row_length, H.num_coo_entries) == (2, 2046572613)
+    assert H.get_option("coo.col_block_log2") > 0
+    yh = H * x
+    lim = 1e-12 * 32 * max(np.abs(y).max(), 1.0) * 64
+    assert np.abs(yh - y).max() <= lim
+
+
 # --------------------------------------------------------------------------------------------
 # row partition (the "N ranks in one process" analogue of the reference's 2-thread tests)
 # --------------------------------------------------------------------------------------------
