@@ -138,6 +138,58 @@ def test_two_ranks_unstructured_no_interior(tmp_path):
     assert all(int(p[1]) == 1 for p in plans)  # every row needs remote x: one block, no overlap
 
 
+def column_split_worker(rank, world, port, case, starts, out_dir):
+    """The overlap for matrices without a band: a rank's rows are cut by COLUMNS into the entries that reference
+    its own slice of x (computed BEFORE the exchange, with every remote x poisoned) and the rest (added after)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, i, j, a = case
+    rp, col, val = csr_from_entries(n, i, j, a)
+    s, e = int(starts[rank]), int(starts[rank + 1])
+    plan = make_exchange_plan(starts, [(0, n)] * world, rank, "allgather")
+    own = (col >= s) & (col < e)
+    v_in, v_out = np.where(own, val, 0.0), np.where(own, 0.0, val)
+    c_in = np.where(own, col, s)  # the inside piece never indexes outside [s, e)
+    X = [torch.zeros(n, dtype=torch.float64) for _ in range(2)]
+    x0 = np.random.default_rng(5).uniform(-1, 1, n)
+    X[0][s:e] = torch.from_numpy(x0[s:e])
+    for k in range(3):
+        cur, nxt = X[k % 2], X[(k + 1) % 2]
+        xin = cur.numpy().copy()
+        xin[:s] = np.nan
+        xin[e:] = np.nan
+        y = local_spmv(rp, c_in, v_in, xin, s, e)  # y = A_inside x, stored
+        assert not np.isnan(y).any()
+        exchange(dist, cur, starts, rank, plan)
+        y += local_spmv(rp, col, v_out, cur.numpy(), s, e)  # y += A_outside x
+        nxt[s:e] = torch.from_numpy(y)
+    np.save(os.path.join(out_dir, f"y_{rank}.npy"), X[3 % 2][s:e].numpy())
+    np.save(os.path.join(out_dir, f"plan_{rank}.npy"), np.array([plan.recv_bytes, int(own[rp[s]:rp[e]].sum())]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_column_split_overlap(tmp_path):
+    rng = np.random.default_rng(13)
+    n = 70
+    mask = rng.random((n, n)) < 0.2
+    mask[np.arange(n), np.arange(n)] = True
+    i, j = np.nonzero(mask)
+    case = (n, (i + 1).astype(np.int64), (j + 1).astype(np.int64), rng.uniform(-0.1, 0.1, len(i)))
+    starts = np.array([0, 25, 70], dtype=np.int64)  # uneven, like a balanced-nnz cut of a power-law matrix
+    mp.spawn(column_split_worker, args=(2, 29541, case, starts, str(tmp_path)), nprocs=2, join=True)
+    rp, col, val = csr_from_entries(n, case[1], case[2], case[3])
+    x = np.random.default_rng(5).uniform(-1, 1, n)
+    for _ in range(3):
+        x = local_spmv(rp, col, val, x, 0, n)
+    got = np.concatenate([np.load(tmp_path / f"y_{r}.npy") for r in range(2)])
+    np.testing.assert_allclose(got, x, rtol=0, atol=1e-12 * np.abs(x).max())
+    plans = [np.load(tmp_path / f"plan_{r}.npy") for r in range(2)]
+    assert [int(p[0]) for p in plans] == [8 * 45, 8 * 25]  # all-gather: everything but the own slice
+    assert all(int(p[1]) > 0 for p in plans)  # both ranks had work to overlap with the exchange
+
+
 def test_plan_arithmetic():
     starts = partition_rows_ref(100, 4)
     assert starts.tolist() == [0, 25, 50, 75, 100]
