@@ -293,7 +293,8 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               -1 = never overlap.
  *               "pdl" (default 1): programmatic dependent launch on/off.
  *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (split by non-zeros,
- *               4 entries per lane, rows from span metadata), 5 sliced (lane per row on a slot-major copy of
+ *               "csr.entries" 4|8 per lane, rows from span metadata; "csr.rowptr_path" 1 = matrices with empty
+ *               rows rebuild the row numbers from row_ptr instead of the row map), 5 sliced (lane per row on a slot-major copy of
  *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" 1 = free the row-major
  *               column_index/value once that copy exists -- they are rebuilt on demand by export, convert,
  *               row_block, column_span and the other kernels); "csr.probe" 1 = regular traffic

@@ -1143,6 +1143,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.batch")) return &m->opt_csr_batch;
     if (!strcmp(key, "csr.probe")) return &m->opt_csr_probe;
     if (!strcmp(key, "csr.entries")) return &m->opt_csr_entries;
+    if (!strcmp(key, "csr.rowptr_path")) return &m->opt_csr_rowptr_path;
     if (!strcmp(key, "csr.drop_row_major")) return &m->opt_csr_drop;
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;

@@ -80,7 +80,9 @@ struct spmvb200_matrix_s {
     int span_size = 0;
     int32_t * flat_meta = nullptr;  // flat kernel: {first row, -, -, -, 128-bit row-start mask} per 128-entry span
     int flat_span = 0;              // entries per span the metadata was built for (128 or 256)
-    bool flat_has_empty = false;    // some row is empty: the mask cannot describe the row starts
+    bool flat_has_empty = false;    // some row is empty: the metadata numbers the non-empty rows, flat_rowmap translates back
+    bool flat_meta_compressed = false;
+    int32_t * flat_rowmap = nullptr;  // non-empty row number -> row
     int32_t * slice_col = nullptr;  // sliced kernel: column_index / value with every 32-row slice stored slot-major
     double * slice_val = nullptr;
     bool slice_unavailable = false;  // the copy could not be allocated: automatic selection stays with the flat kernel
@@ -128,6 +130,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_algo = 0;     // 0 auto, 1 direct (thread forms its row's products), 2 product pass
     int64_t opt_csr_ctas = 0;     // CTAs per SM of the persistent grid, 0 = auto
     int64_t opt_csr_batch = 0;    // sliced kernel: slots in flight per lane (2, 4, 8), 0 = auto
+    int64_t opt_csr_rowptr_path = 0;  // flat kernel, matrices with empty rows: 1 = rebuild row numbers from row_ptr (MASK = false path)
     int64_t opt_csr_entries = 0;  // flat kernel: entries per lane (4, 8), 0 = auto
     int64_t opt_csr_probe = 0;    // 1 regular traffic (values only), 2 irregular traffic (x gather only): csr-matrix-spmv.cpp:35-61
     int64_t opt_csr_drop = 0;     // sliced kernel: 1 = free the row-major column_index/value once the slot-major copy exists

@@ -13,10 +13,12 @@
 //     starts, so row(e) = first_row + popcount(mask bits 1..e) -- a handful of integer instructions,
 //     no dependent load behind the streamed data.  The kernel therefore reads the metadata INSTEAD of
 //     row_ptr (0.25 B per entry instead of 4 B per row); row_ptr stays resident for export, partition
-//     and the other kernels.  Matrices with empty rows (several rows start at one entry, which a bit
-//     cannot say) take the MASK = false path: the rows that start inside the span are read from row_ptr
-//     (coalesced, 32 rows per round), scattered as "row - first_row" into a warp-private line of shared
-//     memory (atomicMax) and turned into row numbers by an inclusive max-scan.
+//     and the other kernels.  Empty rows (several rows start at one entry, which a bit cannot say) are
+//     handled by numbering only the NON-EMPTY rows in the metadata and translating back through a row map
+//     (int32 per non-empty row) where a sum leaves for y.  ("csr.rowptr_path" = 1 selects the older
+//     MASK = false path instead: the rows that start inside the span are read from row_ptr, scattered as
+//     "row - first_row" into a warp-private line of shared memory (atomicMax) and turned into row numbers
+//     by an inclusive max-scan -- a dependent trip through row_ptr.)
 //     All of this reads immutable matrix data only and runs before griddepcontrol.wait.
 //   * x is gathered through the read-only path, four gathers in flight per lane.
 //   * The products are summed per run of equal rows by warp_segmented_add4 (segreduce.cuh): serially
@@ -30,6 +32,8 @@
 #include "launch.cuh"
 #include "ptx.cuh"
 #include "segreduce.cuh"
+
+#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <climits>
@@ -50,9 +54,10 @@ struct FlatShape {
 
 // meta[stride*w + 0] = largest r with row_ptr[r] <= span*w;  meta[stride*w + 4 ..] = bit e set iff a row starts
 // at entry span*w + e, e = 1..span-1 (a row starting at e = 0 is the first row itself).
+// cidx (optional): number of non-empty rows before row r; then the metadata holds that number instead of r.
 template <typename OffT>
 __global__ void csr_flat_first_row_kernel(int64_t rows, int64_t nspans, int span, int stride, const OffT * __restrict__ rp,
-                                          int32_t * __restrict__ meta)
+                                          const int32_t * __restrict__ cidx, int32_t * __restrict__ meta)
 {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nspans) return;
@@ -62,7 +67,22 @@ __global__ void csr_flat_first_row_kernel(int64_t rows, int64_t nspans, int span
         const int64_t mid = (lo + hi + 1) >> 1;
         if ((int64_t)rp[mid] <= target) lo = mid; else hi = mid - 1;
     }
-    meta[(int64_t)stride * w] = (int32_t)lo;
+    meta[(int64_t)stride * w] = cidx ? cidx[lo] : (int32_t)lo;
+}
+
+template <typename OffT>
+__global__ void csr_nonempty_flag_kernel(int64_t rows, const OffT * __restrict__ rp, int32_t * __restrict__ flag)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+        flag[r] = (int64_t)rp[r + 1] > (int64_t)rp[r] ? 1 : 0;
+}
+
+template <typename OffT>
+__global__ void csr_rowmap_kernel(int64_t rows, const OffT * __restrict__ rp, const int32_t * __restrict__ cidx,
+                                  int32_t * __restrict__ rowmap)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+        if ((int64_t)rp[r + 1] > (int64_t)rp[r]) rowmap[cidx[r]] = (int32_t)r;
 }
 
 template <typename OffT>
@@ -77,34 +97,71 @@ __global__ void csr_flat_mask_kernel(int64_t rows, int span, int stride, const O
     }
 }
 
+template <typename OffT>
+static int csr_build_flat_meta_t(Matrix * m, int span, int stride)
+{
+    cudaStream_t s = m->stream;
+    const OffT * rp = (const OffT *)m->rp;
+    const int64_t nspans = (m->stored + span - 1) / span;
+    SPMV_TRY(dev_alloc((Matrix *)nullptr, &m->flat_meta, (int64_t)stride * (nspans + 1)));
+    m->flat_span = span;
+    SPMV_CUDA(cudaMemsetAsync(m->flat_meta, 0, sizeof(int32_t) * (size_t)stride * (size_t)(nspans + 1), s));
+    Scratch<int> flag;
+    SPMV_TRY(flag.alloc(1));
+    SPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+    csr_flat_mask_kernel<OffT><<<grid_for(m->rows, m->sm_count), 256, 0, s>>>(m->rows, span, stride, rp, m->flat_meta, flag.p);
+    SPMV_CUDA(cudaGetLastError());
+    int has_empty = 0;
+    SPMV_CUDA(cudaMemcpyAsync(&has_empty, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    m->flat_has_empty = has_empty != 0;
+    Scratch<int32_t> nonempty, cidx;
+    if (m->flat_has_empty && !m->flat_rowmap) {  // number the non-empty rows: cidx[r] = how many lie before row r
+        Scratch<unsigned char> tmp;
+        SPMV_TRY(nonempty.alloc(m->rows + 1)); SPMV_TRY(cidx.alloc(m->rows + 1));
+        SPMV_CUDA(cudaMemsetAsync(nonempty.p + m->rows, 0, sizeof(int32_t), s));
+        csr_nonempty_flag_kernel<OffT><<<grid_for(m->rows, m->sm_count), 256, 0, s>>>(m->rows, rp, nonempty.p);
+        SPMV_CUDA(cudaGetLastError());
+        size_t tb = 0;
+        SPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nonempty.p, cidx.p, m->rows + 1, s));
+        SPMV_TRY(tmp.alloc((int64_t)tb));
+        SPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nonempty.p, cidx.p, m->rows + 1, s));
+        int32_t count = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&count, cidx.p + m->rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        SPMV_TRY(dev_alloc((Matrix *)nullptr, &m->flat_rowmap, (int64_t)count + 1));
+        csr_rowmap_kernel<OffT><<<grid_for(m->rows, m->sm_count), 256, 0, s>>>(m->rows, rp, cidx.p, m->flat_rowmap);
+        SPMV_CUDA(cudaGetLastError());
+    } else if (m->flat_has_empty) {  // span size changed: the numbering is needed again for the first-row entries
+        Scratch<unsigned char> tmp;
+        SPMV_TRY(nonempty.alloc(m->rows + 1)); SPMV_TRY(cidx.alloc(m->rows + 1));
+        SPMV_CUDA(cudaMemsetAsync(nonempty.p + m->rows, 0, sizeof(int32_t), s));
+        csr_nonempty_flag_kernel<OffT><<<grid_for(m->rows, m->sm_count), 256, 0, s>>>(m->rows, rp, nonempty.p);
+        size_t tb = 0;
+        SPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nonempty.p, cidx.p, m->rows + 1, s));
+        SPMV_TRY(tmp.alloc((int64_t)tb));
+        SPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nonempty.p, cidx.p, m->rows + 1, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+    }
+    // the MASK = false path ("csr.rowptr_path") wants real row numbers in the metadata, the mask path the
+    // numbering of the non-empty rows
+    m->flat_meta_compressed = m->flat_has_empty && !m->opt_csr_rowptr_path;
+    csr_flat_first_row_kernel<OffT><<<(unsigned)((nspans + 255) / 256), 256, 0, s>>>(
+        m->rows, nspans, span, stride, rp, m->flat_meta_compressed ? cidx.p : nullptr, m->flat_meta);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 static int csr_build_flat_meta(Matrix * m, int span, int stride)
 {
-    if (m->flat_meta && m->flat_span == span) return 0;
+    const bool want_compressed = m->flat_has_empty && !m->opt_csr_rowptr_path;
+    if (m->flat_meta && m->flat_span == span && m->flat_meta_compressed == want_compressed) return 0;
     if (m->flat_meta) {
         cudaFree(m->flat_meta);
         m->flat_meta = nullptr;
     }
-    const int64_t nspans = (m->stored + span - 1) / span;
-    SPMV_TRY(dev_alloc((Matrix *)nullptr, &m->flat_meta, (int64_t)stride * (nspans + 1)));
-    m->flat_span = span;
-    SPMV_CUDA(cudaMemsetAsync(m->flat_meta, 0, sizeof(int32_t) * (size_t)stride * (size_t)(nspans + 1), m->stream));
-    Scratch<int> flag;
-    SPMV_TRY(flag.alloc(1));
-    SPMV_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), m->stream));
-    const unsigned g1 = (unsigned)((nspans + 255) / 256);
-    if (m->off64) {
-        csr_flat_first_row_kernel<int64_t><<<g1, 256, 0, m->stream>>>(m->rows, nspans, span, stride, (const int64_t *)m->rp, m->flat_meta);
-        csr_flat_mask_kernel<int64_t><<<grid_for(m->rows, m->sm_count), 256, 0, m->stream>>>(m->rows, span, stride, (const int64_t *)m->rp, m->flat_meta, flag.p);
-    } else {
-        csr_flat_first_row_kernel<uint32_t><<<g1, 256, 0, m->stream>>>(m->rows, nspans, span, stride, (const uint32_t *)m->rp, m->flat_meta);
-        csr_flat_mask_kernel<uint32_t><<<grid_for(m->rows, m->sm_count), 256, 0, m->stream>>>(m->rows, span, stride, (const uint32_t *)m->rp, m->flat_meta, flag.p);
-    }
-    SPMV_CUDA(cudaGetLastError());
-    int has_empty = 0;
-    SPMV_CUDA(cudaMemcpyAsync(&has_empty, flag.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    SPMV_CUDA(cudaStreamSynchronize(m->stream));
-    m->flat_has_empty = has_empty != 0;
-    return 0;
+    return m->off64 ? csr_build_flat_meta_t<int64_t>(m, span, stride) : csr_build_flat_meta_t<uint32_t>(m, span, stride);
 }
 
 // PROBE: 0 = y += A*x; 1 = "regular traffic": y_i += sum_k a_k, the matrix values streamed, no gather
@@ -115,7 +172,8 @@ template <typename OffT, int WARPS, int E, bool MASK, int PROBE>
 __global__ void __launch_bounds__(WARPS * 32)
 csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, const OffT * __restrict__ rp,
                 const int32_t * __restrict__ col, const double * __restrict__ val,
-                const int32_t * __restrict__ meta, const double * __restrict__ x, double * __restrict__ y, double alpha)
+                const int32_t * __restrict__ meta, const int32_t * __restrict__ rowmap, const double * __restrict__ x,
+                double * __restrict__ y, double alpha)
 {
     constexpr int SPAN = FlatShape<E>::span, STRIDE = FlatShape<E>::stride;
     __shared__ __align__(16) int32_t smark[MASK ? 1 : WARPS][SPAN];
@@ -204,7 +262,7 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
     for (int j = 0; j < E; ++j) p[j] = PROBE != 1 ? __ldg(x + c[j]) : 1.0;
 #pragma unroll
     for (int j = 0; j < E; ++j) p[j] = __dmul_rn(a[j], p[j]);
-    warp_segmented_add<E>(lane, r, p, y, alpha);
+    warp_segmented_add<E>(lane, r, p, y, alpha, MASK ? rowmap : nullptr);
 }
 
 template <typename OffT, int WARPS, int E>
@@ -217,16 +275,19 @@ static int launch_flat_variant(Matrix * m)
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     SPMV_TRY(clear_y_for_beta0(m));
     const RunMode rm = run_mode(m);
-    auto kernel = m->flat_has_empty ? csr_flat_kernel<OffT, WARPS, E, false, 0> : csr_flat_kernel<OffT, WARPS, E, true, 0>;
+    const bool rowptr_path = m->flat_has_empty && !m->flat_meta_compressed;
+    auto kernel = rowptr_path ? csr_flat_kernel<OffT, WARPS, E, false, 0> : csr_flat_kernel<OffT, WARPS, E, true, 0>;
     if (WARPS == 4 && E == 4 && m->opt_csr_probe == 1)
-        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, 4, false, 1> : csr_flat_kernel<OffT, 4, 4, true, 1>;
+        kernel = rowptr_path ? csr_flat_kernel<OffT, 4, 4, false, 1> : csr_flat_kernel<OffT, 4, 4, true, 1>;
     else if (WARPS == 4 && E == 4 && m->opt_csr_probe == 2)
-        kernel = m->flat_has_empty ? csr_flat_kernel<OffT, 4, 4, false, 2> : csr_flat_kernel<OffT, 4, 4, true, 2>;
+        kernel = rowptr_path ? csr_flat_kernel<OffT, 4, 4, false, 2> : csr_flat_kernel<OffT, 4, 4, true, 2>;
     else if (m->opt_csr_probe != 0)
         return fail(SPMVB200_ERR_INVALID, "csr.probe must be 0, 1 or 2 (with csr.threads 128 and csr.entries 4)");
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, WARPS * 32u, 0, m->stream, rm.pdl, m->rows,
                             m->stored, nspans, rm.independent, (const OffT *)m->rp, (const int32_t *)m->col,
-                            (const double *)m->val, (const int32_t *)m->flat_meta, (const double *)m->x, m->y, m->alpha));
+                            (const double *)m->val, (const int32_t *)m->flat_meta,
+                            (const int32_t *)(m->flat_meta_compressed ? m->flat_rowmap : nullptr), (const double *)m->x, m->y,
+                            m->alpha));
     count_launch();
     return 0;
 }

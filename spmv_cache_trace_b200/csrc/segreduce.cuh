@@ -14,11 +14,14 @@
 namespace spmvb200 {
 
 // alpha scales every sum on its way out (alpha = 1.0 is exact).  E = entries per lane.
+// rowmap (optional): the row ids in r are indices into it (the flat CSR kernel numbers only the non-empty
+// rows); it is consulted only where a sum leaves for y.
 template <int E>
 __device__ __forceinline__ void warp_segmented_add(int lane, const int (&r)[E], const double (&p)[E],
-                                                   double * __restrict__ y, double alpha = 1.0)
+                                                   double * __restrict__ y, double alpha = 1.0,
+                                                   const int32_t * __restrict__ rowmap = nullptr)
 {
-    using ptx::red_add_f64;
+    auto red_add_f64 = [&](int row, double v) { ptx::red_add_f64(y + (rowmap ? __ldg(rowmap + row) : row), v); };
     int cur_row = r[0];
     double cur = p[0], head = 0.0;
     bool single = true;  // the lane holds one run only
@@ -28,7 +31,7 @@ __device__ __forceinline__ void warp_segmented_add(int lane, const int (&r)[E], 
             cur = __dadd_rn(cur, p[j]);
         } else {
             if (single) { head = cur; single = false; }
-            else if (cur_row >= 0) red_add_f64(y + cur_row, __dmul_rn(alpha, cur));
+            else if (cur_row >= 0) red_add_f64(cur_row, __dmul_rn(alpha, cur));
             cur_row = r[j];
             cur = p[j];
         }
@@ -50,8 +53,8 @@ __device__ __forceinline__ void warp_segmented_add(int lane, const int (&r)[E], 
         }
     }
     const double prev_s = __shfl_up_sync(0xffffffffu, s, 1);
-    if (!single && r[0] >= 0) red_add_f64(y + r[0], __dmul_rn(alpha, cont ? __dadd_rn(prev_s, head) : head));
-    if (!next_cont && r[E - 1] >= 0) red_add_f64(y + r[E - 1], __dmul_rn(alpha, s));
+    if (!single && r[0] >= 0) red_add_f64(r[0], __dmul_rn(alpha, cont ? __dadd_rn(prev_s, head) : head));
+    if (!next_cont && r[E - 1] >= 0) red_add_f64(r[E - 1], __dmul_rn(alpha, s));
 }
 
 __device__ __forceinline__ void warp_segmented_add4(int lane, const int (&r)[4], const double (&p)[4],

@@ -354,6 +354,13 @@ def test_rows_cut_by_tiles_and_rows_longer_than_a_tile(oracle, seed):
         assert_within(csr_matrix.spmv(A, x, y0.copy()), yref, bound, f"flat, 8 entries per lane, threads={threads}")
         A.set_option("csr.entries", 4)
         assert_within(csr_matrix.spmv(A, x, y0.copy()), yref, bound, f"flat, back to 4 entries per lane, threads={threads}")
+        # this matrix has empty rows: the default numbers the non-empty rows + row map; the older path reads row_ptr
+        A.set_option("csr.rowptr_path", 1)
+        assert_within(csr_matrix.spmv(A, x, y0.copy()), yref, bound, f"flat, row_ptr path, threads={threads}")
+        A.set_option("csr.entries", 8)
+        assert_within(csr_matrix.spmv(A, x, y0.copy()), yref, bound, f"flat, row_ptr path, 8 entries, threads={threads}")
+        A.set_option("csr.entries", 4)
+        A.set_option("csr.rowptr_path", 0)
     for fmt, kw in (("coo", {}), ("coo", {"mode": COO_ATOMIC}), ("hybrid", {})):
         B = build(fmt, mm, **kw)
         y = B * x + y0
