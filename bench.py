@@ -390,7 +390,9 @@ def run_single_gpu(args):
                 continue
             try:
                 big = name in ("c3_coo", "c3_coo_atomic", "c4_hyb", "c5_csr")
-                r, keep = measure_device(sp, name, 20 if big else 200, 3, props["l2_bytes"], peak)
+                # the small matrices take 13-36 us per launch: enough launches that clock ramp-up after the idle
+                # time of matrix generation does not colour the result
+                r, keep = measure_device(sp, name, 20 if big else 2000, 3 if big else 100, props["l2_bytes"], peak)
                 del keep
                 extra.append(r)
             except Exception as e:
