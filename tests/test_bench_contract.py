@@ -1,0 +1,68 @@
+"""The bench.py contract: the reference arm really runs here (CPU), and the committed GPU lines carry every key
+the driver reads (profiles/r01_bench_*.json are the lines bench.py printed on the B200 box)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def last_json_line(text):
+    lines = [l for l in text.splitlines() if l.startswith("{")]
+    assert lines, text[-2000:]
+    return json.loads(lines[-1])
+
+
+def test_reference_arm_runs_on_the_host_cores():
+    from oracle.oracle import Ref
+    if not Ref.available():
+        pytest.skip("oracle/_ref/libspmvref.so not built")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = last_json_line(p.stdout)
+    assert BASE_KEYS <= set(line) and line["impl"] == "reference"
+    assert line["metric"] == "spmv_effective_bandwidth" and line["unit"] == "GB/s" and line["higher_is_better"] is True
+    assert line["config"]["workload"] == "c2_ell" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] > 0
+    assert cb["algorithmic_bytes"] == 209715200  # BASELINE config 2: 176 160 768 + 2 x 16 777 216
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_do_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("name", ["r01_bench_n1.json", "r01_bench_n2.json", "r01_bench_n8.json", "r01_bench_c4_hyb_n2.json"])
+def test_committed_gpu_lines_carry_the_contract(name):
+    line = last_json_line(open(os.path.join(ROOT, "profiles", name)).read())
+    assert BASE_KEYS <= set(line), sorted(BASE_KEYS - set(line))
+    assert line["metric"] == "spmv_effective_bandwidth" and line["unit"] == "GB/s" and line["dtype"] == "f64"
+    assert line["data"] == "synthetic" and line["vs_baseline"] is None and line["higher_is_better"] is True
+    assert "workload" in line["config"] and "model" not in line["config"]
+    r = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = line["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["h2d_bytes_per_step"] > 0
+    assert e["value"] < line["value"]  # host buffers cross PCIe every step: never the device-resident number
+    assert line["gpu_launches"] > 0
+    c = line["clocks"]
+    assert c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if line["n_gpus"] == 1:
+        assert line["scaling"] == "weak" and line["config"]["workload"] == "c2_ell"
+        cb = line["cpu_baseline"]
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] in ("reference", "port")
+        assert r["traffic"] and 0.95 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.1
+        assert {f["workload"] for f in line["formats"]} >= {"c1_csr", "c1_ell", "c1_coo", "c1_hyb", "c3_coo", "c4_hyb", "c5_csr"}
+    else:
+        assert line["scaling"] == "strong" and line["single_gpu"]["speedup"] > 1.0
