@@ -71,7 +71,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or not _newer(o, [s] + headers):
-            flags = NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else [])
+            flags = NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + os.environ.get("SPMVB200_CFLAGS", "").split()
             jobs.append([nvcc, "-ccbin", cxx] + flags + ["-I", INCLUDE, "-c", s, "-o", o])
     for src in CXX_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")

@@ -99,8 +99,8 @@ int csr_ensure_row_major(Matrix * m)
     return 0;
 }
 
-template <typename OffT, int U>
-__global__ void __launch_bounds__(128, U <= 4 ? 16 : 8)
+template <typename OffT, int U, int THREADS>
+__global__ void __launch_bounds__(THREADS, (U <= 4 ? 2048 : 1024) / THREADS)
 csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
                   const int32_t * __restrict__ scol, const double * __restrict__ sval, const double * __restrict__ x,
                   double * __restrict__ y)
@@ -109,7 +109,6 @@ csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const 
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i - lane >= rows) return;  // whole warp past the end
-    const uint64_t pol = policy_evict_first();
     const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
     const int len = (int)min(hi - lo, (int64_t)INT_MAX);
     int64_t pos = __shfl_sync(0xffffffffu, lo, 0);  // offset of the slice = row_ptr of its first row
@@ -125,8 +124,12 @@ csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const 
             const bool active = len > l0 + u;
             const unsigned mask = __ballot_sync(0xffffffffu, active);
             const int64_t p = pos + __popc(mask & below);
-            c[u] = active ? ldg_stream_i1(scol + p, pol) : 0;
-            a[u] = active ? ldg_stream_d1(sval + p, pol) : 0.0;
+            // Plain read-only loads (L1 allocation, normal L2 policy), unlike the other kernels' streams: a
+            // slot's 128 / 256 B of a slice start wherever the previous slot ended, so consecutive requests share
+            // sectors, and with L1::no_allocate + L2 evict-first the shared sectors were fetched from DRAM twice
+            // (6.06 GB read for 5.73 GB on 27-point 256^3; 512^3: 7.31 -> 7.00 ms with plain loads).
+            c[u] = active ? __ldg(scol + p) : 0;
+            a[u] = active ? __ldg(sval + p) : 0.0;
             pos += __popc(mask);
         }
         if (!waited) {  // the matrix is immutable; x and y may come from the previous launch
@@ -183,20 +186,35 @@ int launch_csr_sliced(Matrix * m)
     SPMV_TRY(csr_build_sliced(m));
     m->kernel_name = "csr_sliced_kernel";
     if (m->dry_run) return 0;
-    const int64_t grid = (m->rows + 127) / 128;
+    const int threads = (int)(m->opt_csr_threads ? m->opt_csr_threads : 128);
+    const int64_t grid = (m->rows + threads - 1) / threads;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     const RunMode rm = run_mode(m);
     const int store = m->run_beta0 ? 1 : 0;
     m->run_beta0 = false;
     const int batch = (int)(m->opt_csr_batch ? m->opt_csr_batch : 4);
-#define SPMV_SLICED(OFF, UU)                                                                                              \
-    SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU>, (unsigned)grid, 128u, 0, m->stream, rm.pdl, m->rows, rm.independent, \
-                            store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col, (const double *)m->slice_val,            \
-                            (const double *)m->x, m->y))
-    if (batch == 4) { if (m->off64) SPMV_SLICED(int64_t, 4); else SPMV_SLICED(uint32_t, 4); }
-    else if (batch == 8) { if (m->off64) SPMV_SLICED(int64_t, 8); else SPMV_SLICED(uint32_t, 8); }
-    else if (batch == 2) { if (m->off64) SPMV_SLICED(int64_t, 2); else SPMV_SLICED(uint32_t, 2); }
-    else return fail(SPMVB200_ERR_INVALID, "csr.batch must be 2, 4 or 8");
+#define SPMV_SLICED(OFF, UU, TT)                                                                                          \
+    SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, m->rows,  \
+                            rm.independent, store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col,          \
+                            (const double *)m->slice_val, (const double *)m->x, m->y))
+#define SPMV_SLICED_T(UU, TT)                                             \
+    do {                                                                  \
+        if (m->off64) SPMV_SLICED(int64_t, UU, TT);                       \
+        else SPMV_SLICED(uint32_t, UU, TT);                               \
+    } while (0)
+    if (threads == 128) {
+        if (batch == 4) SPMV_SLICED_T(4, 128);
+        else if (batch == 8) SPMV_SLICED_T(8, 128);
+        else if (batch == 2) SPMV_SLICED_T(2, 128);
+        else return fail(SPMVB200_ERR_INVALID, "csr.batch must be 2, 4 or 8");
+    } else if (threads == 256 && batch == 4) {
+        SPMV_SLICED_T(4, 256);
+    } else if (threads == 512 && batch == 4) {
+        SPMV_SLICED_T(4, 512);
+    } else {
+        return fail(SPMVB200_ERR_INVALID, "sliced kernel: csr.threads 128 (csr.batch 2|4|8) or 256|512 (csr.batch 4)");
+    }
+#undef SPMV_SLICED_T
 #undef SPMV_SLICED
     count_launch();
     return 0;

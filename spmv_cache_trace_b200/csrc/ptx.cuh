@@ -58,7 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
 __device__ __forceinline__ uint64_t policy_evict_first()
 {
     uint64_t p;
+#ifdef SPMVB200_STREAM_EVICT_NORMAL  // experiment switch (build.py: SPMVB200_CFLAGS=-DSPMVB200_STREAM_EVICT_NORMAL)
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
     return p;
 }
 
