@@ -13,7 +13,14 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <new>
+#include <stdexcept>
 #include <vector>
+
+// No exception crosses the C ABI: host-side allocations (std::vector, std::string, new) may throw.
+#define SPMV_ABI_CATCH                                                                                  \
+    catch (const std::bad_alloc &) { return ::spmvb200::fail(SPMVB200_ERR_NOMEM, "out of host memory"); } \
+    catch (const std::exception & e) { return ::spmvb200::fail(SPMVB200_ERR_INVALID, e.what()); }
 
 namespace spmvb200 {
 
@@ -329,31 +336,34 @@ int spmvb200_version(void) { return SPMVB200_VERSION; }
 int64_t spmvb200_launch_count(void) { return g_launches.load(); }
 
 int spmvb200_set_global_option(const char * key, int64_t value)
-{
+try {
     if (!key) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (!strcmp(key, "force_offsets64")) { g_force_off64 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "coo.col_block_log2")) { g_coo_col_block_log2 = value; return 0; }
     return fail(SPMVB200_ERR_INVALID, std::string("unknown global option ") + key);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_device_count(int * count)
-{
+try {
     if (!count) return fail(SPMVB200_ERR_INVALID, "null argument");
     *count = 0;
     cudaError_t e = cudaGetDeviceCount(count);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_set_device(int device)
-{
+try {
     SPMV_CUDA(cudaSetDevice(device));
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_device_props(int device, char * name, size_t name_cap, int * sm_count, int64_t * l2_bytes,
                           int64_t * mem_bytes, int * cc_major, int * cc_minor)
-{
+try {
     cudaDeviceProp p;
     SPMV_CUDA(cudaGetDeviceProperties(&p, device));
     if (name && name_cap) { strncpy(name, p.name, name_cap - 1); name[name_cap - 1] = 0; }
@@ -364,29 +374,33 @@ int spmvb200_device_props(int device, char * name, size_t name_cap, int * sm_cou
     if (cc_minor) *cc_minor = p.minor;
     return 0;
 }
+SPMV_ABI_CATCH
 
 // ---- Matrix Market (host) ---------------------------------------------------------------------
 
 int spmvb200_mm_parse(const char * text, size_t len, spmvb200_mm_t * out)
-{
+try {
     if (!text || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
     return mm_parse_text(text, len, out);
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_load(const char * path, spmvb200_mm_t * out)
-{
+try {
     if (!path || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
     return mm_load_path(path, out);
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_from_entries(int32_t rows, int32_t columns, int32_t n, const int32_t * i, const int32_t * j,
                              const double * a, spmvb200_mm_t * out)
-{
+try {
     if (!out || rows < 0 || columns < 0 || n < 0 || (n > 0 && (!i || !j || !a)))
         return fail(SPMVB200_ERR_INVALID, "bad argument");
     return mm_from_entries(rows, columns, n, i, j, a, out);
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_info(spmvb200_mm_t mm, int32_t * rows, int32_t * columns, int32_t * n, int32_t * field,
                      int32_t * symmetry, int32_t * format)
-{
+try {
     if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
     if (rows) *rows = mm->rows;
     if (columns) *columns = mm->columns;
@@ -396,21 +410,24 @@ int spmvb200_mm_info(spmvb200_mm_t mm, int32_t * rows, int32_t * columns, int32_
     if (format) *format = mm->format;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_entries(spmvb200_mm_t mm, const int32_t ** i, const int32_t ** j, const double ** a)
-{
+try {
     if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
     if (i) *i = mm->i.data();
     if (j) *j = mm->j.data();
     if (a) *a = mm->a.data();
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_row_lengths(spmvb200_mm_t mm, int32_t * lengths)
-{
+try {
     if (!mm || !lengths) return fail(SPMVB200_ERR_INVALID, "null argument");
     return mm_row_lengths(mm, lengths);
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_max_row_length(spmvb200_mm_t mm, int32_t * out)
-{
+try {
     if (!mm || !out) return fail(SPMVB200_ERR_INVALID, "null argument");
     std::vector<int32_t> len((size_t)std::max(mm->rows, 1));
     SPMV_TRY(mm_row_lengths(mm, len.data()));
@@ -419,16 +436,19 @@ int spmvb200_mm_max_row_length(spmvb200_mm_t mm, int32_t * out)
     *out = best;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_sort_row_major(spmvb200_mm_t mm)
-{
+try {
     if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
     return mm_sort(mm, true);
 }
+SPMV_ABI_CATCH
 int spmvb200_mm_sort_column_major(spmvb200_mm_t mm)
-{
+try {
     if (!mm) return fail(SPMVB200_ERR_INVALID, "null mm handle");
     return mm_sort(mm, false);
 }
+SPMV_ABI_CATCH
 void spmvb200_mm_free(spmvb200_mm_t mm) { delete mm; }
 
 // ---- builders from Matrix Market ----------------------------------------------------------------
@@ -453,16 +473,17 @@ static int csr_from_mm(spmvb200_mm_t mm, int32_t row_alignment, Matrix ** out)
 }
 
 int spmvb200_csr_from_mm(spmvb200_mm_t mm, int32_t row_alignment, spmvb200_matrix_t * out)
-{
+try {
     SPMV_TRY(need_coordinate(mm, out));
     Matrix * m = nullptr;
     SPMV_TRY(csr_from_mm(mm, row_alignment, &m));
     Guard g(m);
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_coo_from_mm(spmvb200_mm_t mm, int32_t coo_mode, spmvb200_matrix_t * out)
-{
+try {
     SPMV_TRY(need_coordinate(mm, out));
     Matrix * m = nullptr;
     SPMV_TRY(matrix_new(&m));
@@ -496,9 +517,10 @@ int spmvb200_coo_from_mm(spmvb200_mm_t mm, int32_t coo_mode, spmvb200_matrix_t *
     SPMV_TRY(coo_adopt(m, mm->rows, mm->columns, n, row, col, val, coo_mode, false));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_ell_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix_t * out)
-{
+try {
     SPMV_TRY(need_coordinate(mm, out));
     Matrix * csr = nullptr;
     SPMV_TRY(csr_from_mm(mm, 1, &csr));
@@ -509,9 +531,10 @@ int spmvb200_ell_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix
     SPMV_TRY(ell_from_csr(csr, skip_padding, true, m));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_hyb_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix_t * out)
-{
+try {
     SPMV_TRY(need_coordinate(mm, out));
     Matrix * csr = nullptr;
     SPMV_TRY(csr_from_mm(mm, 1, &csr));
@@ -522,12 +545,13 @@ int spmvb200_hyb_from_mm(spmvb200_mm_t mm, int32_t skip_padding, spmvb200_matrix
     SPMV_TRY(hyb_from_csr(csr, skip_padding, true, m));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 // ---- from converted host arrays --------------------------------------------------------------------
 
 int spmvb200_csr_create64(int64_t rows, int64_t columns, int64_t num_entries, const int64_t * row_ptr,
                           const int32_t * column_index, const double * value, spmvb200_matrix_t * out)
-{
+try {
     if (!out || rows < 0 || columns < 0 || !row_ptr) return fail(SPMVB200_ERR_INVALID, "bad argument");
     if (rows >= INT32_MAX || columns >= INT32_MAX) return fail(SPMVB200_ERR_UNSUPPORTED, "rows/columns must fit int32");
     const int64_t stored = row_ptr[rows];
@@ -552,20 +576,22 @@ int spmvb200_csr_create64(int64_t rows, int64_t columns, int64_t num_entries, co
     SPMV_CUDA(cudaStreamSynchronize(s));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_csr_create(int32_t rows, int32_t columns, int32_t num_entries, const int32_t * row_ptr,
                         const int32_t * column_index, const double * value, spmvb200_matrix_t * out)
-{
+try {
     if (!out || rows < 0 || !row_ptr) return fail(SPMVB200_ERR_INVALID, "bad argument");
     std::vector<int64_t> rp((size_t)rows + 1);
     for (int32_t r = 0; r <= rows; r++) rp[r] = row_ptr[r];
     return spmvb200_csr_create64(rows, columns, num_entries, rp.data(), column_index, value, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_coo_create(int32_t rows, int32_t columns, int64_t n, const int32_t * row_index,
                         const int32_t * column_index, const double * value, int32_t coo_mode,
                         spmvb200_matrix_t * out)
-{
+try {
     if (!out || rows < 0 || columns < 0 || n < 0 || (n > 0 && (!row_index || !column_index || !value)))
         return fail(SPMVB200_ERR_INVALID, "bad argument");
     Matrix * m = nullptr;
@@ -576,11 +602,12 @@ int spmvb200_coo_create(int32_t rows, int32_t columns, int64_t n, const int32_t 
     SPMV_TRY(coo_adopt(m, rows, columns, n, m->coo_row, m->coo_col, m->coo_val, coo_mode, false));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_ell_create(int32_t rows, int32_t columns, int32_t num_entries, int32_t row_length,
                         const int32_t * column_index, const double * value, int32_t skip_padding,
                         spmvb200_matrix_t * out)
-{
+try {
     if (!out || rows < 0 || columns < 0 || row_length < 0) return fail(SPMVB200_ERR_INVALID, "bad argument");
     if ((int64_t)rows * row_length > 0 && (!column_index || !value)) return fail(SPMVB200_ERR_INVALID, "bad argument");
     Matrix * m = nullptr;
@@ -591,12 +618,13 @@ int spmvb200_ell_create(int32_t rows, int32_t columns, int32_t num_entries, int3
     SPMV_TRY(upload_ell_rowmajor(m, rows, row_length, column_index, value, skip_padding));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_hyb_create(int32_t rows, int32_t columns, int32_t num_entries, int32_t ell_row_length,
                         const int32_t * ell_column_index, const double * ell_value, int32_t ell_skip_padding,
                         int32_t num_coo_entries, const int32_t * coo_row_index, const int32_t * coo_column_index,
                         const double * coo_value, spmvb200_matrix_t * out)
-{
+try {
     if (!out || rows < 0 || columns < 0 || ell_row_length < 0 || num_coo_entries < 0)
         return fail(SPMVB200_ERR_INVALID, "bad argument");
     Matrix * m = nullptr;
@@ -616,6 +644,7 @@ int spmvb200_hyb_create(int32_t rows, int32_t columns, int32_t num_entries, int3
     m->format = keep_format; m->nnz = keep_nnz; m->stored = keep_stored;
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 // ---- generators / conversion -------------------------------------------------------------------------
 
@@ -633,7 +662,7 @@ static int convert_from_csr(Matrix * csr, int32_t format, int32_t arg, bool chec
 }
 
 int spmvb200_convert(spmvb200_matrix_t src, int32_t format, int32_t arg, spmvb200_matrix_t * out)
-{
+try {
     SPMV_TRY(check(src));
     if (!out) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (src->format != SPMVB200_CSR || src->row_alignment != 1)
@@ -642,10 +671,11 @@ int spmvb200_convert(spmvb200_matrix_t src, int32_t format, int32_t arg, spmvb20
     SPMV_CUDA(cudaStreamSynchronize(src->stream));
     return convert_from_csr(src, format, arg, false, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_gen_stencil(int32_t kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end,
                          int32_t format, spmvb200_matrix_t * out)
-{
+try {
     if (!out || nx < 1 || ny < 1 || nz < 1) return fail(SPMVB200_ERR_INVALID, "bad argument");
     const int64_t n = nx * ny * nz;
     if (row_begin == 0 && row_end == 0) row_end = n;
@@ -658,10 +688,11 @@ int spmvb200_gen_stencil(int32_t kind, int64_t nx, int64_t ny, int64_t nz, int64
     if (format == SPMVB200_CSR) return finish(g, out);
     return convert_from_csr(csr, format, 0, false, out);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_gen_rmat(int32_t scale, int32_t edge_factor, uint64_t seed, double a, double b, double c,
                       int64_t row_begin, int64_t row_end, int32_t format, int32_t coo_mode, spmvb200_matrix_t * out)
-{
+try {
     if (!out || scale < 1 || scale > 30 || edge_factor < 1) return fail(SPMVB200_ERR_INVALID, "bad argument");
     const int64_t n = (int64_t)1 << scale;
     if (row_begin == 0 && row_end == 0) row_end = n;
@@ -673,11 +704,12 @@ int spmvb200_gen_rmat(int32_t scale, int32_t edge_factor, uint64_t seed, double 
     if (format == SPMVB200_CSR) return finish(g, out);
     return convert_from_csr(csr, format, format == SPMVB200_COO ? coo_mode : 0, false, out);
 }
+SPMV_ABI_CATCH
 
 // ---- inspection / export ----------------------------------------------------------------------------------
 
 int spmvb200_matrix_info(spmvb200_matrix_t m, spmvb200_info * info)
-{
+try {
     if (!m || !info) return fail(SPMVB200_ERR_INVALID, "null argument");
     memset(info, 0, sizeof *info);
     info->format = m->format; info->coo_mode = m->coo_mode;
@@ -695,9 +727,10 @@ int spmvb200_matrix_info(spmvb200_matrix_t m, spmvb200_info * info)
     info->device_bytes = m->device_bytes; info->row_offset = m->row_offset;
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_csr_export(spmvb200_matrix_t m, int64_t * row_ptr, int32_t * column_index, double * value)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_CSR) return fail(SPMVB200_ERR_INVALID, "not a CSR matrix");
     if (column_index || value) SPMV_TRY(csr_ensure_row_major(m));
@@ -718,6 +751,7 @@ int spmvb200_csr_export(spmvb200_matrix_t m, int64_t * row_ptr, int32_t * column
     SPMV_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
+SPMV_ABI_CATCH
 
 // device_order = false: the row-major order of the reference (a column-blocked matrix is sorted back first)
 static int export_coo_arrays(Matrix * m, int32_t * row, int32_t * col, double * val, bool device_order = false)
@@ -760,102 +794,115 @@ static int export_ell_arrays(Matrix * m, int32_t * col_rm, double * val_rm)
 }
 
 int spmvb200_coo_export(spmvb200_matrix_t m, int32_t * row_index, int32_t * column_index, double * value)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_COO) return fail(SPMVB200_ERR_INVALID, "not a COO matrix");
     return export_coo_arrays(m, row_index, column_index, value);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_ell_export(spmvb200_matrix_t m, int32_t * column_index, double * value)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_ELL) return fail(SPMVB200_ERR_INVALID, "not an ELL matrix");
     return export_ell_arrays(m, column_index, value);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_hyb_export(spmvb200_matrix_t m, int32_t * ell_column_index, double * ell_value, int32_t * coo_row_index,
                         int32_t * coo_column_index, double * coo_value)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_HYB) return fail(SPMVB200_ERR_INVALID, "not a hybrid matrix");
     SPMV_TRY(export_ell_arrays(m, ell_column_index, ell_value));
     return export_coo_arrays(m, coo_row_index, coo_column_index, coo_value);
 }
+SPMV_ABI_CATCH
 
 // ---- vectors ---------------------------------------------------------------------------------------------------
 
 int spmvb200_set_x(spmvb200_matrix_t m, const double * x)
-{
+try {
     SPMV_TRY(check(m));
     if (!x) return fail(SPMVB200_ERR_INVALID, "null argument");
     SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, m->stream));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_set_y(spmvb200_matrix_t m, const double * y)
-{
+try {
     SPMV_TRY(check(m));
     if (!y) return fail(SPMVB200_ERR_INVALID, "null argument");
     SPMV_CUDA(cudaMemcpyAsync(m->y, y, sizeof(double) * (size_t)m->rows, cudaMemcpyHostToDevice, m->stream));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_get_x(spmvb200_matrix_t m, double * x)
-{
+try {
     SPMV_TRY(check(m));
     if (!x) return fail(SPMVB200_ERR_INVALID, "null argument");
     SPMV_CUDA(cudaMemcpyAsync(x, m->x, sizeof(double) * (size_t)m->cols, cudaMemcpyDeviceToHost, m->stream));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_get_y(spmvb200_matrix_t m, double * y)
-{
+try {
     SPMV_TRY(check(m));
     if (!y) return fail(SPMVB200_ERR_INVALID, "null argument");
     SPMV_CUDA(cudaMemcpyAsync(y, m->y, sizeof(double) * (size_t)m->rows, cudaMemcpyDeviceToHost, m->stream));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_fill_x(spmvb200_matrix_t m, double v)
-{
+try {
     SPMV_TRY(check(m));
     return fill_device(m->x, m->cols, v, m->stream);
 }
+SPMV_ABI_CATCH
 int spmvb200_fill_y(spmvb200_matrix_t m, double v)
-{
+try {
     SPMV_TRY(check(m));
     return fill_device(m->y, m->rows, v, m->stream);
 }
+SPMV_ABI_CATCH
 int spmvb200_x_device(spmvb200_matrix_t m, void ** p)
-{
+try {
     if (!m || !p) return fail(SPMVB200_ERR_INVALID, "null argument");
     *p = m->x;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_y_device(spmvb200_matrix_t m, void ** p)
-{
+try {
     if (!m || !p) return fail(SPMVB200_ERR_INVALID, "null argument");
     *p = m->y;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_bind_x(spmvb200_matrix_t m, void * p)
-{
+try {
     SPMV_TRY(check(m));
     if (!p) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (m->own_x) { cudaFree(m->x); m->device_bytes -= 8 * (m->cols + 8); }
     m->x = (double *)p; m->own_x = false;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_bind_y(spmvb200_matrix_t m, void * p)
-{
+try {
     SPMV_TRY(check(m));
     if (!p) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (m->own_y) { cudaFree(m->y); m->device_bytes -= 8 * (m->rows + 8); }
     m->y = (double *)p; m->own_y = false;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_set_stream(spmvb200_matrix_t m, void * stream)
-{
+try {
     SPMV_TRY(check(m));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     if (m->own_stream) {
@@ -865,17 +912,20 @@ int spmvb200_set_stream(spmvb200_matrix_t m, void * stream)
     m->stream = (cudaStream_t)stream; m->own_stream = false;
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_host_alloc(size_t bytes, void ** p)
-{
+try {
     if (!p) return fail(SPMVB200_ERR_INVALID, "null argument");
     SPMV_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
     return 0;
 }
+SPMV_ABI_CATCH
 int spmvb200_host_free(void * p)
-{
+try {
     SPMV_CUDA(cudaFreeHost(p));
     return 0;
 }
+SPMV_ABI_CATCH
 
 // ---- run ----------------------------------------------------------------------------------------------------------
 
@@ -909,14 +959,15 @@ static int launch(Matrix * m)
 }
 
 int spmvb200_set_alpha(spmvb200_matrix_t m, double alpha)
-{
+try {
     if (!m) return fail(SPMVB200_ERR_INVALID, "null matrix handle");
     m->alpha = alpha;
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_prepare(spmvb200_matrix_t m)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_CSR) return 0;  // only the CSR kernels keep launch metadata
     m->dry_run = true;
@@ -928,20 +979,23 @@ int spmvb200_prepare(spmvb200_matrix_t m)
     stream_synced(m->stream);
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_spmv(spmvb200_matrix_t m)
-{
+try {
     SPMV_TRY(check_run(m));
     return launch(m);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_sync(spmvb200_matrix_t m)
-{
+try {
     SPMV_TRY(check(m));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     stream_synced(m->stream);
     return 0;
 }
+SPMV_ABI_CATCH
 
 // Host-buffer form of y += A*x.  The bytes that must cross PCIe are fixed (x and y up, y down), so
 // the only lever is to use both directions at once: for ELL the rows are cut into chunks; x goes up
@@ -999,7 +1053,7 @@ static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chu
 }
 
 int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
-{
+try {
     SPMV_TRY(check(m));
     if (!x || !y) return fail(SPMVB200_ERR_INVALID, "null argument");
     cudaStream_t s = m->stream;
@@ -1038,9 +1092,10 @@ int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
     stream_synced(s);
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_time(spmvb200_matrix_t m, int warmup, int reps, float * ms)
-{
+try {
     SPMV_TRY(check(m));
     if (reps < 0 || warmup < 0 || (reps > 0 && !ms)) return fail(SPMVB200_ERR_INVALID, "bad argument");
     for (int w = 0; w < warmup; w++) SPMV_TRY(launch(m));
@@ -1054,10 +1109,11 @@ int spmvb200_time(spmvb200_matrix_t m, int warmup, int reps, float * ms)
     }
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_time_rotating(const spmvb200_matrix_t * ms, int n, int warmup, int steps, float * total_ms,
                            float * per_launch_ms)
-{
+try {
     if (!ms || n < 1 || steps < 1 || warmup < 0 || !total_ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
     for (int k = 0; k < n; k++) SPMV_TRY(check(ms[k]));
     cudaStream_t s = ms[0]->stream;
@@ -1099,10 +1155,11 @@ int spmvb200_time_rotating(const spmvb200_matrix_t * ms, int n, int warmup, int 
     for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
     return rc;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_time_host_rotating(const spmvb200_matrix_t * ms, int n, const double * const * xs, double * const * ys,
                                 int warmup, int steps, float * total_ms)
-{
+try {
     if (!ms || !xs || !ys || n < 1 || steps < 1 || warmup < 0 || !total_ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
     for (int k = 0; k < n; k++) SPMV_TRY(check(ms[k]));
     cudaStream_t s = ms[0]->stream;
@@ -1128,6 +1185,7 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t * ms, int n, const doubl
     for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
     return rc;
 }
+SPMV_ABI_CATCH
 
 static int64_t * option_slot(Matrix * m, const char * key)
 {
@@ -1159,16 +1217,17 @@ static int64_t * option_slot(Matrix * m, const char * key)
 }
 
 int spmvb200_set_option(spmvb200_matrix_t m, const char * key, int64_t value)
-{
+try {
     if (!m || !key) return fail(SPMVB200_ERR_INVALID, "null argument");
     int64_t * slot = option_slot(m, key);
     if (!slot) return fail(SPMVB200_ERR_INVALID, std::string("unknown option ") + key);
     *slot = value;
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_get_option(spmvb200_matrix_t m, const char * key, int64_t * value)
-{
+try {
     if (!m || !key || !value) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (!strcmp(key, "coo.col_block_log2")) {  // read-only: the column-block size the builder applied (0 = none)
         *value = m->coo_col_shift;
@@ -1187,27 +1246,30 @@ int spmvb200_get_option(spmvb200_matrix_t m, const char * key, int64_t * value)
     *value = *slot;
     return 0;
 }
+SPMV_ABI_CATCH
 
 const char * spmvb200_kernel_name(spmvb200_matrix_t m) { return m ? m->kernel_name : ""; }
 
 int spmvb200_destroy(spmvb200_matrix_t m)
-{
+try {
     matrix_free(m);
     return 0;
 }
+SPMV_ABI_CATCH
 
 // ---- row partition ---------------------------------------------------------------------------------------------------
 
 int spmvb200_partition_rows_ref(int64_t rows, int32_t parts, int64_t * starts)
-{
+try {
     if (rows < 0 || parts < 1 || !starts) return fail(SPMVB200_ERR_INVALID, "bad argument");
     const int64_t rpt = (rows + parts - 1) / parts;  // csr-matrix.cpp:79
     for (int32_t p = 0; p <= parts; p++) starts[p] = std::min<int64_t>(rows, (int64_t)p * rpt);
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t * starts)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_CSR || parts < 1 || !starts) return fail(SPMVB200_ERR_INVALID, "bad argument");
     Scratch<int64_t> d;
@@ -1220,10 +1282,11 @@ int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t * st
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col_end, int64_t * col_min,
                              int64_t * col_max, int64_t * lo_end, int64_t * hi_begin)
-{
+try {
     SPMV_TRY(check(m));
     if (m->format != SPMVB200_CSR) return fail(SPMVB200_ERR_INVALID, "not a CSR matrix");
     SPMV_TRY(csr_ensure_row_major(m));
@@ -1244,9 +1307,10 @@ int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col
     if (hi_begin) *hi_begin = h[3];
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_csr_row_block(spmvb200_matrix_t src, int64_t row_begin, int64_t row_end, spmvb200_matrix_t * out)
-{
+try {
     SPMV_TRY(check(src));
     if (!out || src->format != SPMVB200_CSR || row_begin < 0 || row_end > src->rows || row_begin > row_end)
         return fail(SPMVB200_ERR_INVALID, "bad argument");
@@ -1285,11 +1349,12 @@ int spmvb200_csr_row_block(spmvb200_matrix_t src, int64_t row_begin, int64_t row
     SPMV_CUDA(cudaStreamSynchronize(s));
     return finish(g, out);
 }
+SPMV_ABI_CATCH
 
 // ---- cache model on a device matrix -------------------------------------------------------------------------------
 
 int spmvb200_cache_trace(spmvb200_matrix_t m, const spmvb200_cache_config * cfg, spmvb200_cache_misses * out)
-{
+try {
     SPMV_TRY(check(m));
     if (!cfg || !out || cfg->parts < 1) return fail(SPMVB200_ERR_INVALID, "bad argument");
     if (m->format == SPMVB200_CSR) {
@@ -1327,12 +1392,13 @@ int spmvb200_cache_trace(spmvb200_matrix_t m, const spmvb200_cache_config * cfg,
     }
     return fail(SPMVB200_ERR_INVALID, "unknown format");
 }
+SPMV_ABI_CATCH
 
 // ---- column split (interior / boundary for matrices that are not banded) ------------------------------------------
 
 int spmvb200_csr_column_split(spmvb200_matrix_t src, int64_t col_begin, int64_t col_end, spmvb200_matrix_t * inside,
                               spmvb200_matrix_t * outside)
-{
+try {
     SPMV_TRY(check(src));
     if (!inside || !outside || src->format != SPMVB200_CSR || col_begin < 0 || col_begin > col_end)
         return fail(SPMVB200_ERR_INVALID, "bad argument");
@@ -1388,5 +1454,6 @@ int spmvb200_csr_column_split(spmvb200_matrix_t src, int64_t col_begin, int64_t 
     }
     return rc;
 }
+SPMV_ABI_CATCH
 
 }  // extern "C"

@@ -31,7 +31,14 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <new>
+#include <stdexcept>
 #include <vector>
+
+// No exception crosses the C ABI: host-side allocations (std::vector, std::string, new) may throw.
+#define SPMV_ABI_CATCH                                                                                  \
+    catch (const std::bad_alloc &) { return ::spmvb200::fail(SPMVB200_ERR_NOMEM, "out of host memory"); } \
+    catch (const std::exception & e) { return ::spmvb200::fail(SPMVB200_ERR_INVALID, e.what()); }
 
 namespace spmvb200 {
 int fail(int code, const std::string & msg);
@@ -360,7 +367,7 @@ extern "C" {
 
 int spmvb200_cache_trace_csr(int64_t rows, int64_t columns, const int64_t * row_ptr, const int32_t * column_index,
                              const spmvb200_cache_config * cfg, spmvb200_cache_misses * out)
-{
+try {
     if (int rc = check_config(cfg, out)) return rc;
     if (rows < 0 || columns < 0 || !row_ptr || (!column_index && row_ptr[rows] > 0)) return fail(SPMVB200_ERR_INVALID, "bad CSR arrays");
     const int P = cfg->parts;
@@ -378,10 +385,11 @@ int spmvb200_cache_trace_csr(int64_t rows, int64_t columns, const int64_t * row_
     simulate(src, *cfg, out);
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_cache_trace_ell(int64_t rows, int64_t columns, int64_t row_length, const int32_t * column_index_row_major,
                              const spmvb200_cache_config * cfg, spmvb200_cache_misses * out)
-{
+try {
     if (int rc = check_config(cfg, out)) return rc;
     if (rows < 0 || columns < 0 || row_length < 0 || (!column_index_row_major && rows * row_length > 0))
         return fail(SPMVB200_ERR_INVALID, "bad ELL arrays");
@@ -398,10 +406,11 @@ int spmvb200_cache_trace_ell(int64_t rows, int64_t columns, int64_t row_length, 
     simulate(src, *cfg, out);
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_cache_trace_coo(int64_t rows, int64_t columns, int64_t num_entries, const int32_t * row_index,
                              const int32_t * column_index, const spmvb200_cache_config * cfg, spmvb200_cache_misses * out)
-{
+try {
     if (int rc = check_config(cfg, out)) return rc;
     if (rows < 0 || columns < 0 || num_entries < 0 || (num_entries > 0 && (!row_index || !column_index)))
         return fail(SPMVB200_ERR_INVALID, "bad COO arrays");
@@ -418,5 +427,6 @@ int spmvb200_cache_trace_coo(int64_t rows, int64_t columns, int64_t num_entries,
     simulate(src, *cfg, out);
     return 0;
 }
+SPMV_ABI_CATCH
 
 }  // extern "C"

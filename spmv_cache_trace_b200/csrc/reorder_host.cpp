@@ -13,8 +13,15 @@
 #include "mm_host.hpp"
 
 #include <algorithm>
+#include <new>
 #include <numeric>
+#include <stdexcept>
 #include <string>
+
+// No exception crosses the C ABI: host-side allocations (std::vector, std::string, new) may throw.
+#define SPMV_ABI_CATCH                                                                                  \
+    catch (const std::bad_alloc &) { return ::spmvb200::fail(SPMVB200_ERR_NOMEM, "out of host memory"); } \
+    catch (const std::exception & e) { return ::spmvb200::fail(SPMVB200_ERR_INVALID, e.what()); }
 
 #include "../../include/spmv_b200.h"
 
@@ -102,23 +109,26 @@ using namespace spmvb200;
 extern "C" {
 
 int spmvb200_mm_order_rcm(spmvb200_mm_t mm, int32_t * new_order)
-{
+try {
     if (!mm || !new_order) return fail(SPMVB200_ERR_INVALID, "null argument");
     return mm_order_rcm(mm, new_order);
 }
+SPMV_ABI_CATCH
 
 int spmvb200_mm_order_gp(spmvb200_mm_t mm, int32_t nparts, int32_t * new_order)
-{
+try {
     (void)nparts;
     if (!mm || !new_order) return fail(SPMVB200_ERR_INVALID, "null argument");
     for (int32_t v = 0; v < mm->rows; v++) new_order[v] = v;
     return 0;
 }
+SPMV_ABI_CATCH
 
 int spmvb200_mm_permute(spmvb200_mm_t mm, const int32_t * new_order)
-{
+try {
     if (!mm || !new_order) return fail(SPMVB200_ERR_INVALID, "null argument");
     return mm_permute(mm, new_order);
 }
+SPMV_ABI_CATCH
 
 }  // extern "C"
