@@ -29,8 +29,11 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <new>
 #include <stdexcept>
 #include <vector>
@@ -336,18 +339,40 @@ void simulate(std::vector<std::unique_ptr<Source>> & src, const spmvb200_cache_c
         }
         return;
     }
-    for (int p = 0; p < P; ++p) {
+    // private caches: the parts are independent of each other, one host thread each
+    auto run_part = [&](int p) {
         Lru cache(lines);
         for (int pass = cfg.warmup ? 0 : 1; pass < 2; ++pass) {
             src[p]->rewind();
-            std::fill(last.begin(), last.end(), ~0ull);
+            for (int k = 0; k < 3; ++k) last[(size_t)p * 3 + k] = ~0ull;
             Ref r;
             while (src[p]->next(r)) {
                 const bool miss = touch(cache, p, r);
                 if (pass == 1) count(out[p], r, miss);
             }
         }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (P == 1 || hw == 1) {
+        for (int p = 0; p < P; ++p) run_part(p);
+        return;
     }
+    std::exception_ptr failure;
+    std::mutex failure_mutex;
+    for (int first = 0; first < P; first += (int)hw) {  // at most `hw` parts at a time
+        std::vector<std::thread> workers;
+        for (int p = first; p < std::min<int>(P, first + (int)hw); ++p)
+            workers.emplace_back([&, p] {
+                try {
+                    run_part(p);
+                } catch (...) {
+                    std::lock_guard<std::mutex> lk(failure_mutex);
+                    failure = std::current_exception();
+                }
+            });
+        for (auto & w : workers) w.join();
+    }
+    if (failure) std::rethrow_exception(failure);
 }
 
 int check_config(const spmvb200_cache_config * cfg, const spmvb200_cache_misses * out)
