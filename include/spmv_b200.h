@@ -102,8 +102,9 @@ int64_t spmvb200_launch_count(void);
  * offsets on the device (normally only when stored_entries >= 2^32) so that path can be tested.
  * "coo.col_block_log2": the builders of SEGMENTED COO matrices and of the hybrid tail may store the
  * row-sorted entries partitioned by column block (blocks of 2^k columns, rows ascending inside a block)
- * so that a block's slice of x stays in L2; 0 (default) = automatic (only when x is larger than 1.5 L2
- * and the extra sweeps over y cost less than the gather misses), -1 = never, k > 0 = always, with 2^k
+ * so that a block's slice of x stays in L2; 0 (default) = automatic (only when the x referenced is larger
+ * than 0.75 L2, the gathers are not local already -- more than three column blocks touched per 2^20
+ * consecutive entries -- and the extra sweeps over y cost less than the gather misses), -1 = never, k > 0 = always, with 2^k
  * columns.  Exports restore the row-major order.  spmvb200_get_option(m, "coo.col_block_log2") tells
  * what was applied to a matrix. */
 int spmvb200_set_global_option(const char *key, int64_t value);

@@ -554,6 +554,26 @@ __global__ void block_hist_kernel(int64_t n, const int32_t * col, int shift, uns
         if (local[t]) atomicAdd(&hist[t], (unsigned long long)local[t]);
 }
 
+// For every chunk of 2^20 consecutive entries: which column blocks does it touch (256-bit mask)?
+__global__ void block_spread_kernel(int64_t n, const int32_t * col, int shift, unsigned int * masks /* [chunks][8] */)
+{
+    __shared__ unsigned int local[8];
+    const int64_t chunk = blockIdx.y;
+    if (threadIdx.x < 8) local[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t b = chunk << 20, e = min(n, b + ((int64_t)1 << 20));
+    unsigned int mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t k = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < e; k += (int64_t)gridDim.x * blockDim.x) {
+        const int blk = (col[k] >> shift) & 255;
+        mine[blk >> 5] |= 1u << (blk & 31);
+    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (mine[w]) atomicOr(&local[w], mine[w]);
+    __syncthreads();
+    if (threadIdx.x < 8 && local[threadIdx.x]) atomicOr(&masks[chunk * 8 + threadIdx.x], local[threadIdx.x]);
+}
+
 __global__ void block_key_kernel(int64_t n, const int32_t * col, int shift, unsigned char * key, uint32_t * idx)
 {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
@@ -583,7 +603,7 @@ int coo_column_blocks(Matrix * m)
     SPMV_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m->device));
     int shift = (int)opt;
     if (opt == 0) {
-        if (l2 <= 0 || 8 * m->cols <= (int64_t)l2 + l2 / 2) return 0;  // x fits (or nearly): nothing to gain
+        if (l2 <= 0 || 8 * m->cols <= (int64_t)l2 / 4 * 3) return 0;  // x fits in L2 with room to spare: nothing to gain
         shift = 0;
         while (((int64_t)16 << shift) <= l2 / 2) shift++;  // largest block with 8 * 2^shift <= L2/2
     }
@@ -608,8 +628,22 @@ int coo_column_blocks(Matrix * m)
             if (hist[b]) nonempty++;
             ycost += std::min<int64_t>(m->rows, (int64_t)hist[b]) * 8;
         }
-        if ((nonempty * 8) << shift <= (int64_t)l2 + l2 / 2) return 0;
+        if ((nonempty * 8) << shift <= (int64_t)l2 / 4 * 3) return 0;
         if (n * 12 <= ycost) return 0;
+        // ... and only when the gathers are NOT local already: a banded matrix (stencil) touches one or two column
+        // blocks per million consecutive entries, and cutting its rows into blocks would only add sweeps over y
+        const int64_t chunks = (n + ((int64_t)1 << 20) - 1) >> 20;
+        Scratch<unsigned int> dm;
+        SPMV_TRY(dm.alloc(chunks * 8));
+        SPMV_CUDA(cudaMemsetAsync(dm.p, 0, sizeof(unsigned int) * 8 * (size_t)chunks, s));
+        block_spread_kernel<<<dim3(16, (unsigned)chunks), 256, 0, s>>>(n, m->coo_col, shift, dm.p);
+        SPMV_CUDA(cudaGetLastError());
+        std::vector<unsigned int> masks((size_t)chunks * 8);
+        SPMV_CUDA(cudaMemcpyAsync(masks.data(), dm.p, sizeof(unsigned int) * masks.size(), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        int64_t touched = 0;
+        for (unsigned int v : masks) touched += __builtin_popcount(v);
+        if (touched <= 3 * chunks) return 0;  // at most three blocks per chunk on average: local enough
     }
     Scratch<int> flag;
     SPMV_TRY(flag.alloc(1));

@@ -663,10 +663,26 @@ def test_config3_rmat24_full_size_cross_format():
     assert np.abs(y12 - (y1 + 2 * y2)).max() <= 4 * lim
     for mode in (COO_SEGMENTED, COO_ATOMIC):
         C = A.convert(sp.COO, mode)
+        # x (134 MB) is of the size of L2 and the gathers are scattered: the row-sorted entries get column blocks;
+        # file order (ATOMIC mode) is never touched
+        assert (C.get_option("coo.col_block_log2") > 0) == (mode == COO_SEGMENTED)
         yc = C * x1
         assert C.kernel_name == "coo_warp4_kernel"
         assert np.abs(yc - y1).max() <= lim, f"coo mode {mode}"
         del C
+
+
+def test_banded_coo_is_not_column_blocked():
+    """A stencil whose x is as large as R-MAT 2^24's (3D 7-point 256^3, 134 MB): its gathers are local already, so the
+    automatic rule must leave the row-sorted order alone."""
+    if _free_gib() < 20:
+        pytest.skip("needs ~10 GB of device memory")
+    n = 256
+    C = sp.generators.stencil(sp.STENCIL_3D7, n, n, n, fmt=sp.COO)
+    assert C.get_option("coo.col_block_log2") == 0
+    y = C * np.ones(n ** 3)
+    y3 = y.reshape(n, n, n)
+    assert np.all(y3[1:-1, 1:-1, 1:-1] == 0.0)  # 6 - 6 neighbours
 
 
 def test_config4_rmat26_full_size_hybrid():
