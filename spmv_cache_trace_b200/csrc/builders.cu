@@ -607,6 +607,8 @@ int coo_column_blocks(Matrix * m)
         shift = 0;
         while (((int64_t)16 << shift) <= l2 / 2) shift++;  // largest block with 8 * 2^shift <= L2/2
     }
+    if (opt == 0)
+        while (((m->cols + ((int64_t)1 << shift) - 1) >> shift) > 256) shift++;  // one-byte block keys: at most 256 blocks
     const int64_t nblocks = (m->cols + ((int64_t)1 << shift) - 1) >> shift;
     if (nblocks < 2 || nblocks > 256) return 0;
     cudaStream_t s = m->stream;
