@@ -292,7 +292,9 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               ordering.  On a caller-provided stream (spmvb200_set_stream) nothing is assumed unless
  *               this option is 1 = the caller promises that no kernel in flight writes this matrix's x.
  *               -1 = never overlap.
- *               "pdl" (default 1): programmatic dependent launch on/off.
+ *               "pdl" (default 1): programmatic dependent launch, used on the stream the matrix owns; on a
+ *               caller-provided stream (which the caller may have tied to other streams with events) launches
+ *               are plain unless "pdl" = 2; 0 = never.
  *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (split by non-zeros,
  *               "csr.entries" 4|8 per lane, rows from span metadata; "csr.rowptr_path" 1 = matrices with empty
  *               rows rebuild the row numbers from row_ptr instead of the row map), 5 sliced (lane per row on a slot-major copy of

@@ -282,10 +282,16 @@ void plan_run(Matrix * m, bool conservative)
     const uintptr_t y0 = (uintptr_t)m->y, y1 = y0 + 8u * (uintptr_t)m->rows;
     std::lock_guard<std::mutex> lk(g_stream_mu);
     auto it = g_streams.find(m->stream);
-    if (it == g_streams.end()) {  // not a library stream: the caller's promise is all there is
-        m->run_independent = m->opt_independent > 0 && !conservative;
+    if (it == g_streams.end()) {
+        // Not a library stream.  The caller may have tied it to other streams with events (the multi-GPU mode does:
+        // exchange <-> compute), and a kernel launched with the PDL attribute next to such an edge was observed to
+        // break the ordering the events are there for (tools/dist_check.py, hybrid pieces, steps issued back to back:
+        // wrong rows with PDL, none without).  So on foreign streams launches are plain unless "pdl" = 2 insists.
+        m->run_pdl = m->opt_pdl == 2;
+        m->run_independent = m->run_pdl && m->opt_independent > 0 && !conservative;
         return;
     }
+    if (conservative) m->run_pdl = false;  // the host-buffer paths order their pieces with events too
     StreamRec & r = it->second;
     const bool proven = r.valid && !overlaps(x0, x1, r.wlo, r.whi) && !overlaps(y0, y1, r.rlo, r.rhi) &&
                         !overlaps(y0, y1, r.slo, r.shi);

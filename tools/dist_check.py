@@ -26,7 +26,7 @@ from spmv_cache_trace_b200.distributed import DistributedSpMV, partition_rows_re
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=96)
-    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=6)
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
@@ -44,10 +44,8 @@ def main():
         for overlap in (True, False):
             eng = DistributedSpMV(sp, torch, dist, local, starts, rank, mode=mode, overlap=overlap)
             eng.set_x(x0[s:e])
-            for _ in range(args.iters):
-                eng.step()
-                eng.synchronize()
-                eng.x_local().mul_(1.0 / 32.0)  # keep the iterates O(1)
+            for _ in range(args.iters):  # issued back to back, no host synchronisation between the steps
+                eng.step(scale=1.0 / 32.0)  # keep the iterates O(1)
             eng.synchronize()
             parts = [torch.zeros(int(starts[q + 1] - starts[q]), dtype=torch.float64, device="cuda") for q in range(world)]
             dist.all_gather(parts, eng.x_local().contiguous())
