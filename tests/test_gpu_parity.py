@@ -880,6 +880,25 @@ def test_launch_ordering_follows_the_data_hazards(oracle):
         assert A.get_option("last_launch.overlapped") == 0  # y is cleared first: ordered
         assert np.array_equal(A.get_y(), y1)
         A.set_option("beta0", 0)
+    # a caller-provided stream may be tied to other streams by events the library cannot see: plain launches there
+    # (the library's own stream keeps programmatic dependent launch)
+    import ctypes
+    A = sp.generators.stencil(sp.STENCIL_2D5, n, n, 1)
+    A.set_x(x); A.fill_y(0.0)
+    A.spmv(); A.spmv()
+    assert (A.get_option("last_launch.pdl"), A.get_option("last_launch.overlapped")) == (1, 1)
+    cudart = ctypes.CDLL("libcudart.so")
+    stream = ctypes.c_void_p()
+    assert cudart.cudaStreamCreate(ctypes.byref(stream)) == 0
+    A.sync()
+    A.set_stream(stream.value)
+    A.spmv(); A.spmv()
+    assert (A.get_option("last_launch.pdl"), A.get_option("last_launch.overlapped")) == (0, 0)
+    A.set_option("pdl", 2)  # the caller insists
+    A.spmv()
+    assert A.get_option("last_launch.pdl") == 1
+    A.sync()
+    assert np.array_equal(A.get_y(), 5 * y1)
     # x bound to the matrix's own y: every launch reads what the previous one wrote
     A = sp.generators.stencil(sp.STENCIL_2D5, n, n, 1)
     A.fill_y(1.0)
