@@ -187,6 +187,7 @@ def measure_device(sp, name, steps, warmup, l2_bytes, peak, per_launch=True, max
         "ms_per_step": total_ms / steps, "gbs": B / t / 1e9, "gflops": 2.0 * inf.num_entries / t / 1e9,
         "frac_of_8TBs": B / t / 1e9 / NOMINAL_HBM_GBS, "frac_of_measured_peak": B / t / 1e9 / peak,
         "l2_cold_copies": copies,
+        "traffic": ncu_traffic(name),  # dram__bytes_read + write of one launch from the committed ncu capture, if any
     }
     if inf.format == sp.HYB:
         res.update(ell_row_length=int(inf.ell_row_length), num_coo_entries=int(inf.num_coo_entries))
