@@ -298,9 +298,9 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *   CSR         "csr.algo" 1 stream/direct, 2 stream/product, 3 warp-granular, 4 flat (split by non-zeros,
  *               "csr.entries" 4|8 per lane, rows from span metadata; "csr.rowptr_path" 1 = matrices with empty
  *               rows rebuild the row numbers from row_ptr instead of the row map), 5 sliced (lane per row on a slot-major copy of
- *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" 1 = free the row-major
- *               column_index/value once that copy exists -- they are rebuilt on demand by export, convert,
- *               row_block, column_span and the other kernels); "csr.probe" 1 = regular traffic
+ *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" (default 1) = free the row-major
+ *               column_index/value once that copy exists, so the matrix is resident once -- they are rebuilt on
+ *               demand by export, convert, row_block, column_span and the other kernels; 0 = keep both copies); "csr.probe" 1 = regular traffic
  *               (y_i += sum a_k, values streamed, no gather), 2 = irregular traffic (y_i += sum x[j_k], the
  *               gather alone): spmv_regular_traffic / spmv_irregular_traffic of the reference
  *               (csr-matrix-spmv.cpp:35-61, 119-146); "csr.algo" 0 = automatic: sliced when the mean row has
@@ -349,6 +349,104 @@ int spmvb200_csr_column_split(spmvb200_matrix_t m, int64_t col_begin, int64_t co
  * and can run while the exchange of x is still in flight. */
 int spmvb200_csr_column_span(spmvb200_matrix_t m, int64_t col_begin, int64_t col_end,
                              int64_t *col_min, int64_t *col_max, int64_t *lo_end, int64_t *hi_begin);
+
+/* ---- the row-partitioned multi-GPU mode (one rank per GPU) ---------------------- */
+/* The reference is one process: thread t of its OpenMP team owns rows [t*ceil(rows/T), ...) (matrix/csr-matrix.cpp:77-95)
+ * and runs Kernel::run together with the others between barriers (profile-kernel.cpp:159-161).  Here a RANK owns a row
+ * block on its own GPU, and the iteration x_(k+1) = alpha*A*x_k needs one exchange of x per step.  A communicator
+ * connects the ranks; two kinds exist behind the same handle:
+ *   - in-process ("local"): all ranks live in one process (one host thread may drive them all, or one thread per rank,
+ *     e.g. the OpenMP team of profile_kernel with a barrier between steps); x moves by direct peer copies over NVLink
+ *     (cudaMemcpyPeerAsync), ordered by CUDA events between the ranks' streams.  Several ranks may share a GPU,
+ *     which is how the single-GPU tests exercise the multi-rank logic.
+ *   - NCCL: one process per rank (torchrun, MPI, ...): the caller carries the 128-byte id from rank 0 to the others.
+ *     NCCL is loaded at run time (dlopen of libnccl.so.2); the library has no link-time dependency on it. */
+typedef struct spmvb200_comm_s *spmvb200_comm_t;
+typedef struct spmvb200_dist_s *spmvb200_dist_t;
+#define SPMVB200_COMM_ID_BYTES 128
+
+/* In-process communicator: comms[r] is rank r's handle, living on devices[r] (NULL: device r % device_count). */
+int spmvb200_comm_create_local(int nranks, const int *devices, spmvb200_comm_t *comms /* nranks */);
+/* NCCL communicator.  Rank 0 calls _unique_id and ships the bytes to the other ranks by any means; then EVERY rank
+ * calls _create_nccl (collective; the calling thread's current device is the rank's GPU). */
+int spmvb200_comm_unique_id(void *id /* SPMVB200_COMM_ID_BYTES */);
+int spmvb200_comm_create_nccl(const void *id, int rank, int nranks, spmvb200_comm_t *out);
+int spmvb200_comm_rank(spmvb200_comm_t c, int *rank, int *nranks, int *device);
+/* Collectives for the plumbing around a measurement: barrier; max / sum of one double over the ranks.
+ * In-process communicators: call from one thread per rank, or for rank 0..n-1 in order from one thread. */
+int spmvb200_comm_barrier(spmvb200_comm_t c);
+int spmvb200_comm_allreduce(spmvb200_comm_t c, double *value, int op /* 0 max, 1 sum, 2 min */);
+int spmvb200_comm_destroy(spmvb200_comm_t c);
+
+/* How x travels between steps. */
+typedef enum {
+    SPMVB200_EXCHANGE_AUTO = 0,      /* halo when every rank needs at most a quarter of x from the others */
+    SPMVB200_EXCHANGE_ALLGATHER = 1, /* every rank receives every other slice (north star: "NCCL all-gather of x") */
+    SPMVB200_EXCHANGE_HALO = 2       /* every rank receives exactly the column range its rows reference */
+} spmvb200_exchange;
+/* spmvb200_dist_create flags */
+#define SPMVB200_DIST_CONSUME_LOCAL 1 /* the executor may destroy `local` once its row blocks exist (halves the footprint) */
+#define SPMVB200_DIST_COLUMN_SPLIT 2  /* cut the block by COLUMNS (own slice of x / the rest) instead of by rows: for
+                                         matrices without a band (power law); all-gather exchange */
+#define SPMVB200_DIST_NO_OVERLAP 4    /* one block per rank, run after the exchange */
+
+/* The exchange plan, as plain arithmetic (no device, no communicator): rank `rank` of `parts` owns columns
+ * [starts[rank], starts[rank+1]) of x; need_lo/need_hi[q] = the column range rank q's rows reference (hi exclusive).
+ * Returns the mode chosen and up to `cap` (peer, lo, hi) triples for the sends and the receives of `rank`
+ * (all-gather: none listed; recv_bytes = 8 * (n - own)). */
+int spmvb200_exchange_plan(int32_t parts, const int64_t *starts, const int64_t *need_lo, const int64_t *need_hi,
+                           int32_t rank, int32_t mode, int32_t cap, int32_t *chosen_mode,
+                           int32_t *n_sends, int64_t *sends /* 3*cap */, int32_t *n_recvs, int64_t *recvs /* 3*cap */,
+                           int64_t *recv_bytes);
+
+/* Executor of x_(k+1) = alpha*A*x_k for this rank.  `local`: the rank's rows [starts[rank], starts[rank+1]) with GLOBAL
+ * column indices (spmvb200_gen_stencil(..., row_begin, row_end, ...), spmvb200_csr_row_block, spmvb200_csr_create64), CSR;
+ * ELL / COO / hybrid blocks are accepted with the all-gather exchange.  `format`: format the pieces are converted to
+ * before they run (SPMVB200_CSR = leave as is; SPMVB200_HYB for BASELINE configs[3]).  Collective over the communicator.
+ * The rank's rows are cut into blocks: rows that reference only the rank's own slice of x run on one stream WHILE the
+ * exchange is in flight on a second (high-priority) stream; rows that need remote x run on a third stream as soon as the
+ * exchange has delivered it -- concurrently with the first block, so the step costs max(interior, exchange + boundary).
+ * x lives in two full-length device buffers used in ping-pong; step k reads X_k and writes its rows of alpha*A*X_k into
+ * its slice of X_(k+1) with plain stores ("beta0"), so there is no y -> x copy, no clearing pass and no scaling pass. */
+int spmvb200_dist_create(spmvb200_comm_t comm, spmvb200_matrix_t local, const int64_t *starts /* nranks+1 */,
+                         int32_t exchange, int32_t format, int32_t flags, spmvb200_dist_t *out);
+/* The rank's slice of the CURRENT x: host -> device, device -> host, device pointer. */
+int spmvb200_dist_set_x(spmvb200_dist_t d, const double *x_local_host);
+int spmvb200_dist_get_x(spmvb200_dist_t d, double *x_local_host);
+int spmvb200_dist_x_device(spmvb200_dist_t d, void **ptr);
+/* One step, asynchronous.  In-process communicators: issue step k of every rank before step k+1 of any. */
+int spmvb200_dist_step(spmvb200_dist_t d, double alpha);
+int spmvb200_dist_sync(spmvb200_dist_t d);
+/* `steps` steps of every executor in ds[0..n), bracketed by CUDA events on each rank's streams, after `warmup` untimed
+ * ones; ms[r] = device time of ds[r].  The caller takes the maximum over the ranks.  NCCL: n = 1 (the process's own
+ * rank; the ranks meet at a barrier before the timed steps).  In-process: all ranks of the communicator, driven by the
+ * calling thread. */
+int spmvb200_dist_time(const spmvb200_dist_t *ds, int n, int warmup, int steps, double alpha, float *ms /* n */);
+/* End to end: `steps` INDEPENDENT products y_i = alpha*A*x_i, the rank's slice of every x_i coming from and the rank's
+ * rows of every y_i going to (pinned) host memory.  Pipelined: the upload of step i+1 and the download of step i-1 run on
+ * copy streams while step i computes.  ms (may be NULL) = device time of the whole sequence.  Synchronises. */
+int spmvb200_dist_run_host(spmvb200_dist_t d, int steps, const double *const *x_local_host, double *const *y_local_host,
+                           double alpha, float *ms);
+typedef struct {
+    int32_t rank, nranks;
+    int32_t exchange;             /* the mode in use (spmvb200_exchange)                         */
+    int32_t n_blocks;             /* kernels' row blocks / column pieces                          */
+    int32_t n_sends, n_recvs;
+    int64_t recv_bytes_per_step;  /* bytes of x this rank receives per step                       */
+    int64_t send_bytes_per_step;
+    int64_t rows, row_begin;
+    int64_t num_entries;          /* non-zeros of the rank's rows                                 */
+    int64_t interior_rows;        /* rows that run during the exchange                            */
+    int64_t device_bytes;         /* matrices + x buffers resident on this rank's GPU             */
+    int64_t launches_per_step;
+    int64_t steps_done;
+} spmvb200_dist_info_t;
+int spmvb200_dist_info(spmvb200_dist_t d, spmvb200_dist_info_t *info);
+/* Block b of the executor (0 <= b < n_blocks): its row range inside the rank, whether it needs remote x, and the
+ * kernel it runs. */
+int spmvb200_dist_block(spmvb200_dist_t d, int32_t b, int64_t *row_begin, int64_t *row_end, int32_t *needs_remote_x,
+                        spmvb200_matrix_t *matrix);
+int spmvb200_dist_destroy(spmvb200_dist_t d);
 
 /* ---- the reference's cache model for the chosen partition (host side) -------- */
 

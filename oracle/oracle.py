@@ -358,6 +358,29 @@ class Oracle:
         rp = _i32(row_ptr)
         return int(self.lib.orc_csr_nonzeros_per_thread(_ptr(rp, _i32p), C.c_int32(rows), C.c_int(t), C.c_int(T)))
 
+    # -- R-MAT at full size (C twin of the device generator; numpy twin: generators_ref.rmat_entries) ---------
+    def rmat_csr(self, scale: int, edge_factor: int, seed: int, a=0.57, b=0.19, c=0.19) -> Csr:
+        """The R-MAT matrix as the CSR the reference's converter produces from its sorted, de-duplicated entries
+        (row_ptr = prefix counts, columns ascending inside a row).  Built directly: the converter's sort would be the
+        identity on this input (checked against orc_csr_from_entries at small sizes in tests/test_oracle_golden.py)."""
+        m = edge_factor << scale
+        n = 1 << scale
+        keys = np.empty(m, dtype=np.uint64)
+        self.lib.orc_rmat_keys(C.c_int(scale), C.c_uint64(seed), C.c_double(a), C.c_double(b), C.c_double(c),
+                               C.c_uint64(0), C.c_uint64(m), keys.ctypes.data_as(C.POINTER(C.c_uint64)))
+        keys.sort()
+        keep = np.empty(m, dtype=bool)
+        keep[0] = True
+        np.not_equal(keys[1:], keys[:-1], out=keep[1:])
+        keys = keys[keep]
+        del keep
+        nnz = int(keys.shape[0])
+        col = np.empty(nnz, dtype=np.int32)
+        val = np.empty(nnz, dtype=np.float64)
+        self.lib.orc_rmat_unpack(C.c_int64(nnz), keys.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(col, _i32p), _ptr(val, _f64p))
+        rp = np.searchsorted(keys, np.arange(n + 1, dtype=np.uint64) << np.uint64(32)).astype(np.int32)
+        return Csr(n, n, nnz, 1, rp, col, val, 12 * nnz + 4 * (n + 1))
+
     def partition_rows_ref(self, rows, P):
         out = np.zeros(P + 1, dtype=np.int64)
         self.lib.orc_partition_rows_ref(C.c_int64(rows), C.c_int(P), out.ctypes.data_as(C.POINTER(C.c_int64)))

@@ -769,3 +769,51 @@ void orc_partition_rows_nnz(int64_t rows, const int64_t *row_ptr, int P, int64_t
     }
     starts[P] = rows;
 }
+
+/* ======================================================================== */
+/* R-MAT edges of the synthetic power-law matrices (BASELINE configs 3, 4)   */
+/* ======================================================================== */
+/* Not a reference function: the reference has no generators.  This restates OUR device generator
+ * (spmv_cache_trace_b200/csrc/generators.cu; numpy twin: oracle/generators_ref.py::rmat_entries) in C so
+ * that the full-size parity tests can build their host matrix in seconds instead of minutes of numpy. */
+static uint64_t orc_splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* keys[e - e0] = (row << 32) | col of edge draw e, e in [e0, e1) */
+void orc_rmat_keys(int scale, uint64_t seed, double a, double b, double c, uint64_t e0, uint64_t e1, uint64_t *keys)
+{
+    const double ta = a, tb = a + b, tc = a + b + c;
+    int64_t k, n = (int64_t)(e1 - e0);
+#pragma omp parallel for schedule(static)
+    for (k = 0; k < n; ++k) {
+        const uint64_t e = e0 + (uint64_t)k;
+        uint64_t row = 0, col = 0;
+        int level;
+        for (level = 0; level < scale; ++level) {
+            const uint64_t h = orc_splitmix64(seed + e * 0x9E3779B97F4A7C15ull + (uint64_t)level * 0xBF58476D1CE4E5B9ull);
+            const double u = (double)(h >> 11) * 0x1.0p-53;
+            const int q = u < ta ? 0 : (u < tb ? 1 : (u < tc ? 2 : 3));
+            row = (row << 1) | (uint64_t)(q >> 1);
+            col = (col << 1) | (uint64_t)(q & 1);
+        }
+        keys[k] = (row << 32) | col;
+    }
+}
+
+/* From the sorted, de-duplicated keys: column index and value(i, j) = 2*u(hash(key)) - 1 of every entry, and the
+ * number of entries of every row (rows + 1 counters, the last one unused). */
+void orc_rmat_unpack(int64_t n, const uint64_t *keys, int32_t *col, double *val)
+{
+    int64_t k;
+#pragma omp parallel for schedule(static)
+    for (k = 0; k < n; ++k) {
+        const uint64_t h = orc_splitmix64(keys[k] ^ 0xD1B54A32D192ED03ull);
+        col[k] = (int32_t)(uint32_t)keys[k];
+        val[k] = 2.0 * ((double)(h >> 11) * 0x1.0p-53) - 1.0;
+    }
+}

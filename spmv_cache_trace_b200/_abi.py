@@ -51,6 +51,17 @@ class CacheMisses(C.Structure):
         "misses_x_remote", "misses_y_local", "misses_y_remote", "x_references", "x_remote_references")]
 
 
+class DistInfo(C.Structure):
+    """spmvb200_dist_info_t"""
+    _fields_ = [
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("exchange", C.c_int32), ("n_blocks", C.c_int32),
+        ("n_sends", C.c_int32), ("n_recvs", C.c_int32),
+        ("recv_bytes_per_step", C.c_int64), ("send_bytes_per_step", C.c_int64),
+        ("rows", C.c_int64), ("row_begin", C.c_int64), ("num_entries", C.c_int64), ("interior_rows", C.c_int64),
+        ("device_bytes", C.c_int64), ("launches_per_step", C.c_int64), ("steps_done", C.c_int64),
+    ]
+
+
 _ccp = C.POINTER(CacheConfig)
 _cmp = C.POINTER(CacheMisses)
 
@@ -132,6 +143,26 @@ SIGNATURES = {
     "spmvb200_cache_trace_ell": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, i32p, _ccp, _cmp]),
     "spmvb200_cache_trace_coo": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, i32p, i32p, _ccp, _cmp]),
     "spmvb200_cache_trace": (C.c_int, [vp, _ccp, _cmp]),
+    "spmvb200_comm_create_local": (C.c_int, [C.c_int, C.POINTER(C.c_int), vpp]),
+    "spmvb200_comm_unique_id": (C.c_int, [vp]),
+    "spmvb200_comm_create_nccl": (C.c_int, [vp, C.c_int, C.c_int, vpp]),
+    "spmvb200_comm_rank": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "spmvb200_comm_barrier": (C.c_int, [vp]),
+    "spmvb200_comm_allreduce": (C.c_int, [vp, f64p, C.c_int]),
+    "spmvb200_comm_destroy": (C.c_int, [vp]),
+    "spmvb200_exchange_plan": (C.c_int, [C.c_int32, i64p, i64p, i64p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i64p,
+                                         i32p, i64p, i64p]),
+    "spmvb200_dist_create": (C.c_int, [vp, vp, i64p, C.c_int32, C.c_int32, C.c_int32, vpp]),
+    "spmvb200_dist_set_x": (C.c_int, [vp, f64p]),
+    "spmvb200_dist_get_x": (C.c_int, [vp, f64p]),
+    "spmvb200_dist_x_device": (C.c_int, [vp, vpp]),
+    "spmvb200_dist_step": (C.c_int, [vp, C.c_double]),
+    "spmvb200_dist_sync": (C.c_int, [vp]),
+    "spmvb200_dist_time": (C.c_int, [vpp, C.c_int, C.c_int, C.c_int, C.c_double, f32p]),
+    "spmvb200_dist_run_host": (C.c_int, [vp, C.c_int, C.POINTER(f64p), C.POINTER(f64p), C.c_double, f32p]),
+    "spmvb200_dist_info": (C.c_int, [vp, C.POINTER(DistInfo)]),
+    "spmvb200_dist_block": (C.c_int, [vp, C.c_int32, i64p, i64p, i32p, vpp]),
+    "spmvb200_dist_destroy": (C.c_int, [vp]),
 }
 
 _lib = None

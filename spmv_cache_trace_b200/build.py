@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "libspmvb200.so")
 CLI = os.path.join(HERE, "bin", "spmv-b200")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-CUDA_SOURCES = ["abi.cu", "kernels_csr.cu", "kernels_csr_warp.cu", "kernels_csr_flat.cu", "kernels_csr_sliced.cu", "kernels_ell.cu", "kernels_coo.cu", "builders.cu", "generators.cu"]
+CUDA_SOURCES = ["abi.cu", "kernels_csr.cu", "kernels_csr_warp.cu", "kernels_csr_flat.cu", "kernels_csr_sliced.cu", "kernels_ell.cu", "kernels_coo.cu", "builders.cu", "generators.cu", "dist.cu"]
 CXX_SOURCES = ["mm_host.cpp", "cache_model.cpp", "reorder_host.cpp"]
 HEADERS = ["common.cuh", "ptx.cuh", "launch.cuh", "segreduce.cuh", "mm_host.hpp", os.path.join(INCLUDE, "spmv_b200.h")]
 
@@ -83,7 +83,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             outputs = list(ex.map(lambda c: _run(c, verbose), jobs))
     if jobs or not os.path.exists(LIB):
-        _run([nvcc, "-ccbin", cxx, "-shared", "-o", LIB] + objs + ["-lz", "-Xlinker", "--no-undefined"], verbose)
+        _run([nvcc, "-ccbin", cxx, "-shared", "-o", LIB] + objs + ["-lz", "-ldl", "-Xlinker", "--no-undefined"], verbose)
     if ptxas_info:
         print("\n".join(outputs))
     # the C++ host layer above the C ABI: Kernel-plugin mirror + the profile-mode CLI

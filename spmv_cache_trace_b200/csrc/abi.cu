@@ -49,6 +49,7 @@ int store_offsets(Matrix * m, const int64_t * d_rp64, int64_t rows, int64_t stor
 int gen_stencil(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end, Matrix * csr);
 int gen_rmat(int scale, int edge_factor, uint64_t seed, double a, double b, double c, int64_t row_begin,
              int64_t row_end, Matrix * csr);
+int launch_csr_sliced(Matrix * m);  // kernels_csr_sliced.cu
 
 __global__ void transpose_to_colmajor_kernel(int64_t rows, int64_t W, int64_t pitch, const int32_t * col_rm,
                                              const double * val_rm, int32_t * ecol, double * eval)
@@ -295,6 +296,12 @@ void plan_run(Matrix * m, bool conservative)
     StreamRec & r = it->second;
     const bool proven = r.valid && !overlaps(x0, x1, r.wlo, r.whi) && !overlaps(y0, y1, r.rlo, r.rhi) &&
                         !overlaps(y0, y1, r.slo, r.shi);
+    // The kernels gather x through the read-only path (ld.global.nc), which PTX defines only for data that nothing
+    // writes during the kernel's lifetime -- and under PDL that lifetime begins while the predecessor is still
+    // running.  A launch whose x may have been written by a kernel in flight (an iteration x_{k+1} = A x_k with
+    // the buffers swapped by bind_x / bind_y; or anything the record cannot vouch for) is therefore issued without
+    // the PDL attribute: ordinary stream serialisation, the whole predecessor retired before the first CTA starts.
+    if (!r.valid || overlaps(x0, x1, r.wlo, r.whi)) m->run_pdl = false;
     if (!conservative && m->run_pdl && !m->opt_beta0 && !m->run_beta0 &&
         (m->opt_independent > 0 || (m->opt_independent == 0 && proven))) {
         m->run_independent = true;  // validity of the record is unchanged; its ranges grow
@@ -935,6 +942,22 @@ SPMV_ABI_CATCH
 
 // ---- run ----------------------------------------------------------------------------------------------------------
 
+// The timing entry points run several matrices on one stream.  The matrices keep owning their own streams: the
+// loan is undone when the scope ends, on the error paths too (a matrix left pointing at a stream it does not own
+// would destroy it a second time in matrix_free and leak its own).
+struct StreamLoan {
+    const spmvb200_matrix_t * ms;
+    int n;
+    std::vector<cudaStream_t> saved;
+    StreamLoan(const spmvb200_matrix_t * ms, int n, cudaStream_t s) : ms(ms), n(n), saved((size_t)n)
+    {
+        for (int k = 0; k < n; k++) { saved[(size_t)k] = ms[k]->stream; ms[k]->stream = s; }
+    }
+    ~StreamLoan() { for (int k = 0; k < n; k++) ms[k]->stream = saved[(size_t)k]; }
+    StreamLoan(const StreamLoan &) = delete;
+    StreamLoan & operator=(const StreamLoan &) = delete;
+};
+
 static int launch_format(Matrix * m)
 {
     switch (m->format) {
@@ -1017,6 +1040,10 @@ static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chu
         for (auto & e : m->ev_chunk) SPMV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     cudaStream_t up = m->upload_stream;
+    // Kernels queued earlier on the matrix's stream (an asynchronous spmvb200_spmv) may still gather from m->x and
+    // add to m->y: the uploads below must not overtake them.
+    SPMV_CUDA(cudaEventRecord(m->ev_x, s));
+    SPMV_CUDA(cudaStreamWaitEvent(up, m->ev_x, 0));
     const int64_t per = round_up((m->rows + chunks - 1) / chunks, 1024);
     SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, up));
     SPMV_CUDA(cudaEventRecord(m->ev_x, up));
@@ -1088,6 +1115,34 @@ try {
         }
         cudaGetLastError();  // not a registered host pointer: fall through to the copying paths
     }
+    if (m->format == SPMVB200_CSR && m->opt_host_zero_copy && m->rows > 0 && m->stored > 0 && csr_uses_sliced_kernel(m)) {
+        // the sliced CSR kernel owns whole rows like the ELL kernel: same zero-copy form (x up by DMA, then one kernel
+        // that reads y_old from and writes y_new to the pinned host buffer while it streams the matrix from HBM)
+        cudaPointerAttributes ay{};
+        if (!m->slice_col) {  // build the slot-major copy now; if it does not fit the flat kernel runs and y is copied
+            m->dry_run = true;
+            const int rc = launch_csr(m);
+            m->dry_run = false;
+            if (rc) return rc;
+        }
+        if (m->slice_col && cudaPointerGetAttributes(&ay, y) == cudaSuccess && ay.type == cudaMemoryTypeHost && ay.devicePointer) {
+            SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
+            m->host_y_in = m->opt_beta0 ? nullptr : (const double *)ay.devicePointer;
+            m->host_y_out = (double *)ay.devicePointer;
+            const int64_t keep = m->opt_beta0;
+            m->opt_beta0 = 0;
+            plan_run(m, true);
+            const int rc = launch_csr_sliced(m);
+            m->opt_beta0 = keep;
+            m->host_y_in = nullptr;
+            m->host_y_out = nullptr;
+            if (rc) return rc;
+            SPMV_CUDA(cudaStreamSynchronize(s));
+            stream_synced(s);
+            return 0;
+        }
+        cudaGetLastError();
+    }
     const int chunks = (int)(m->opt_host_chunks ? std::min<int64_t>(m->opt_host_chunks, 16) : 4);
     if (m->format == SPMVB200_ELL && chunks > 1 && m->rows >= 64 * 1024) return spmv_host_pipelined(m, x, y, chunks, nullptr);
     SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
@@ -1123,17 +1178,10 @@ try {
     if (!ms || n < 1 || steps < 1 || warmup < 0 || !total_ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
     for (int k = 0; k < n; k++) SPMV_TRY(check(ms[k]));
     cudaStream_t s = ms[0]->stream;
-    std::vector<cudaStream_t> saved(n);
-    for (int k = 0; k < n; k++) {
-        SPMV_CUDA(cudaStreamSynchronize(ms[k]->stream));
-        saved[k] = ms[k]->stream;
-        ms[k]->stream = s;
-    }
+    for (int k = 0; k < n; k++) SPMV_CUDA(cudaStreamSynchronize(ms[k]->stream));
+    StreamLoan loan(ms, n, s);  // every matrix launches on ms[0]'s stream until this scope ends, however it ends
     int rc = 0;
-    for (int k = 0; k < n; k++) {
-        SPMV_TRY(spmvb200_prepare(ms[k]));
-        ms[k]->stream = s;  // (prepare ran on the shared stream too)
-    }
+    for (int k = 0; k < n; k++) SPMV_TRY(spmvb200_prepare(ms[k]));
     auto run = [&]() -> int {
         for (int w = 0; w < warmup; w++) SPMV_TRY(launch(ms[w % n]));
         SPMV_CUDA(cudaStreamSynchronize(s));
@@ -1158,7 +1206,6 @@ try {
     };
     rc = run();
     if (rc == 0) stream_synced(s);
-    for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
     return rc;
 }
 SPMV_ABI_CATCH
@@ -1169,12 +1216,8 @@ try {
     if (!ms || !xs || !ys || n < 1 || steps < 1 || warmup < 0 || !total_ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
     for (int k = 0; k < n; k++) SPMV_TRY(check(ms[k]));
     cudaStream_t s = ms[0]->stream;
-    std::vector<cudaStream_t> saved(n);
-    for (int k = 0; k < n; k++) {
-        SPMV_CUDA(cudaStreamSynchronize(ms[k]->stream));
-        saved[k] = ms[k]->stream;
-        ms[k]->stream = s;
-    }
+    for (int k = 0; k < n; k++) SPMV_CUDA(cudaStreamSynchronize(ms[k]->stream));
+    StreamLoan loan(ms, n, s);
     auto run = [&]() -> int {
         for (int w = 0; w < warmup; w++) SPMV_TRY(spmvb200_spmv_host(ms[w % n], xs[w % n], ys[w % n]));
         SPMV_CUDA(cudaEventRecord(ms[0]->ev0, s));
@@ -1187,9 +1230,7 @@ try {
         SPMV_CUDA(cudaEventElapsedTime(total_ms, ms[0]->ev0, ms[0]->ev1));
         return 0;
     };
-    int rc = run();
-    for (int k = 0; k < n; k++) ms[k]->stream = saved[k];
-    return rc;
+    return run();
 }
 SPMV_ABI_CATCH
 

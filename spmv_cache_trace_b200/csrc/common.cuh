@@ -133,7 +133,7 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_rowptr_path = 0;  // flat kernel, matrices with empty rows: 1 = rebuild row numbers from row_ptr (MASK = false path)
     int64_t opt_csr_entries = 0;  // flat kernel: entries per lane (4, 8), 0 = auto
     int64_t opt_csr_probe = 0;    // 1 regular traffic (values only), 2 irregular traffic (x gather only): csr-matrix-spmv.cpp:35-61
-    int64_t opt_csr_drop = 0;     // sliced kernel: 1 = free the row-major column_index/value once the slot-major copy exists
+    int64_t opt_csr_drop = 1;     // sliced kernel: free the row-major column_index/value once the slot-major copy exists (0 = keep both)
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
     int64_t opt_ell_block = 0;    // threads per block, 0 = auto
@@ -249,6 +249,7 @@ int launch_csr(Matrix * m);
 int launch_ell(Matrix * m, bool accumulate_into_y);
 int launch_coo(Matrix * m);
 int csr_build_tiles(Matrix * m);  // (re)build tile_row for the configured tile size
+bool csr_uses_sliced_kernel(Matrix * m);  // would launch_csr run the sliced kernel (the one whose threads own whole rows)?
 // The row-major column_index / value of a CSR matrix may have been dropped in favour of the slot-major copy
 // ("csr.drop_row_major"); everything that reads them calls this first (rebuilds them from the copy).
 int csr_ensure_row_major(Matrix * m);

@@ -10,6 +10,7 @@
 #include "segreduce.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 
 namespace spmvb200 {
@@ -218,11 +219,16 @@ static int launch_coo_seg(Matrix * m)
 {
     auto kernel = coo_segmented_kernel<THREADS, STAGES>;
     constexpr size_t smem = (size_t)STAGES * THREADS * kCooItems * 16 + 8 * STAGES + 16;
-    static int occupancy = 0;
+    // per device (the attribute is a property of the function ON a device) and safe to race: the worst case is that
+    // two threads set the same attribute and compute the same number
+    static std::atomic<int> occupancy_of[64];
+    const int dev = m->device >= 0 && m->device < 64 ? m->device : 0;
+    int occupancy = occupancy_of[dev].load(std::memory_order_acquire);
     if (!occupancy) {
         SPMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, THREADS, smem));
         if (occupancy < 1) return fail(SPMVB200_ERR_CUDA, "coo_segmented_kernel does not fit on an SM");
+        occupancy_of[dev].store(occupancy, std::memory_order_release);
     }
     const int ctas = m->opt_coo_ctas ? (int)std::min<int64_t>(m->opt_coo_ctas, occupancy) : occupancy;
     int64_t grid = std::min<int64_t>((int64_t)m->sm_count * ctas, std::max<int64_t>(1, (m->coo_n + 15) / 16));

@@ -42,6 +42,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 
 namespace spmvb200 {
@@ -329,11 +330,14 @@ static int launch_csr_variant(Matrix * m)
 {
     auto kernel = csr_stream_kernel<OffT, THREADS, TILE, STAGES, G>;
     constexpr size_t smem = csr_smem_bytes<OffT, TILE, STAGES>();
-    static int occupancy = 0;  // per instantiation (one device per process)
+    static std::atomic<int> occupancy_of[64];  // per instantiation and device (the attribute is per device)
+    const int dev = m->device >= 0 && m->device < 64 ? m->device : 0;
+    int occupancy = occupancy_of[dev].load(std::memory_order_acquire);
     if (!occupancy) {
         SPMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, THREADS, smem));
         if (occupancy < 1) return fail(SPMVB200_ERR_CUDA, "csr_stream_kernel does not fit on an SM");
+        occupancy_of[dev].store(occupancy, std::memory_order_release);
     }
     // csr.spare_ctas: leave that many CTA slots per SM free, e.g. for the NCCL kernel of an exchange
     // that should run concurrently (a persistent grid at full occupancy would lock it out).
@@ -398,9 +402,21 @@ int launch_csr_flat(Matrix * m);             // kernels_csr_flat.cu
 int launch_csr_sliced(Matrix * m);           // kernels_csr_sliced.cu
 int csr_max_row_length(Matrix * m);          // builders.cu
 
+bool csr_uses_sliced_kernel(Matrix * m)
+{
+    if (m->format != SPMVB200_CSR || m->rows == 0 || m->stored == 0 || m->opt_csr_probe != 0) return false;
+    if (m->opt_csr_algo == 5) return true;
+    if (m->opt_csr_algo != 0 || m->slice_unavailable) return false;
+    const int64_t avg = m->stored / std::max<int64_t>(m->rows, 1);
+    if (avg < 10) return false;
+    if (csr_max_row_length(m) != 0) return false;
+    return m->csr_maxlen <= 2 * avg;
+}
+
 int launch_csr(Matrix * m)
 {
-    if (m->rows == 0 || m->stored == 0) return 0;
+    if (m->rows == 0) return 0;
+    if (m->stored == 0) return m->dry_run ? 0 : clear_y_for_beta0(m);  // nothing to add; y = alpha*A*x still clears y
     const CsrConfig c = csr_config(m);
     // csr.algo: 0 automatic, 1 stream/direct, 2 stream/product, 3 warp-granular register-staged,
     // 4 flat (register-staged, split by non-zeros, rows from span metadata; kernels_csr_flat.cu).

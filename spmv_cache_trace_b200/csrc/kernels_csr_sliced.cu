@@ -103,7 +103,7 @@ template <typename OffT, int U, int THREADS>
 __global__ void __launch_bounds__(THREADS, (U <= 4 ? 2048 : 1024) / THREADS)
 csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
                   const int32_t * __restrict__ scol, const double * __restrict__ sval, const double * __restrict__ x,
-                  double * __restrict__ y)
+                  double * __restrict__ y, const double * __restrict__ y_in_host, double * __restrict__ y_out_host)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
@@ -144,6 +144,16 @@ csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const 
             if (len > l0 + u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
     }
     if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Zero-copy form (spmvb200_spmv_host with pinned buffers): y_old is read from and y_new written to mapped HOST
+    // memory by this kernel -- a warp moves 256 contiguous bytes each way -- so the two PCIe directions run at once
+    // and y never takes a separate trip through the copy engine.
+    if (y_out_host) {
+        if (i < rows) {
+            const double yo = y_in_host ? __ldcs(y_in_host + i) : 0.0;
+            __stcs(y_out_host + i, __dadd_rn(yo, __dmul_rn(alpha, z)));
+        }
+        return;
+    }
     // a lane owns its whole row: y = alpha*A*x is a plain store (no clearing pass, no read of y)
     if (store) { if (i < rows) y[i] = __dmul_rn(alpha, z); }
     else if (len > 0) red_add_f64(y + i, __dmul_rn(alpha, z));
@@ -190,13 +200,14 @@ int launch_csr_sliced(Matrix * m)
     const int64_t grid = (m->rows + threads - 1) / threads;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     const RunMode rm = run_mode(m);
-    const int store = m->run_beta0 ? 1 : 0;
+    const int store = (m->run_beta0 && !m->host_y_out) ? 1 : 0;
     m->run_beta0 = false;
     const int batch = (int)(m->opt_csr_batch ? m->opt_csr_batch : 4);
 #define SPMV_SLICED(OFF, UU, TT)                                                                                          \
     SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, m->rows,  \
                             rm.independent, store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col,          \
-                            (const double *)m->slice_val, (const double *)m->x, m->y))
+                            (const double *)m->slice_val, (const double *)m->x, m->y, (const double *)m->host_y_in,      \
+                            m->host_y_out))
 #define SPMV_SLICED_T(UU, TT)                                             \
     do {                                                                  \
         if (m->off64) SPMV_SLICED(int64_t, UU, TT);                       \

@@ -1,8 +1,13 @@
-"""Row-partitioned multi-GPU SpMV: one process per GPU, torch.distributed for the plumbing.
+"""Row-partitioned multi-GPU SpMV: Python face of spmvb200_comm_* / spmvb200_dist_* (include/spmv_b200.h).
+
+The executor itself lives below the C ABI (csrc/dist.cu) so that a C++ caller -- the reference's profile_kernel,
+whose OpenMP threads map one to one onto ranks -- can drive N GPUs; this module is a thin binding plus a plain-Python
+restatement of the bookkeeping (partition, exchange plan, row split) that the CPU tests run over gloo and compare
+with the library's own arithmetic (spmvb200_exchange_plan).
 
 The reference is a single-process OpenMP code; what it has is the PARTITION (every thread owns
 ceil(rows/T) consecutive rows, matrix/csr-matrix.cpp:77-95) and a model of who owns which part of x
-(aligned-allocator.hpp:156-211).  This module turns that into a distributed iteration
+(aligned-allocator.hpp:156-211).  The executor turns that into a distributed iteration
 x_{k+1} = A x_k on the GPUs of one NVSwitch domain:
 
   * rank p owns rows [s_p, s_{p+1}) of A (global column indices) and the matching slice of x and y;
@@ -17,19 +22,18 @@ x_{k+1} = A x_k on the GPUs of one NVSwitch domain:
     the interior block runs on the compute stream WHILE the exchange runs on the communication
     stream; the two boundary blocks run after the exchange's event.
 
-Everything that is not the SpMV kernel itself (partition arithmetic, the exchange plan, the
-ping-pong bookkeeping) is plain Python and is exercised on CPU by tests/test_distributed_gloo.py
-with world_size 2 over gloo, with the oracle standing in for the local kernel.
+  * the boundary blocks run on their own stream as soon as the halo has arrived, CONCURRENTLY with the interior
+    block, and the next exchange starts as soon as the boundary rows are done.
 """
 from __future__ import annotations
 
-import json
-import math
-import os
-import time
+import ctypes as C
 from dataclasses import dataclass, field
 
 import numpy as np
+
+from . import _abi
+from ._abi import f32p, f64p, i32p, i64p
 
 
 # --------------------------------------------------------------------------------------------
@@ -133,422 +137,209 @@ def split_rows(lo_end: int, hi_begin: int, rows: int):
 
 
 # --------------------------------------------------------------------------------------------
-# the GPU executor
+# the executor below the C ABI
 # --------------------------------------------------------------------------------------------
+
+EXCHANGE = {"auto": 0, "allgather": 1, "halo": 2}
+EXCHANGE_NAMES = {v: k for k, v in EXCHANGE.items()}
+CONSUME_LOCAL, COLUMN_SPLIT, NO_OVERLAP = 1, 2, 4
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        from . import matrix_error
+        raise matrix_error(_abi.lib().spmvb200_last_error().decode(), rc)
+
+
+def exchange_plan(starts, need, rank: int, mode: str = "auto") -> ExchangePlan:
+    """The library's own plan arithmetic (spmvb200_exchange_plan): must equal make_exchange_plan above."""
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    P = len(starts) - 1
+    lo = np.ascontiguousarray([a for a, _ in need], dtype=np.int64)
+    hi = np.ascontiguousarray([b for _, b in need], dtype=np.int64)
+    cap = 4 * P + 4
+    sends, recvs = np.zeros(3 * cap, np.int64), np.zeros(3 * cap, np.int64)
+    chosen, ns, nr, rb = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    _check(_abi.lib().spmvb200_exchange_plan(P, starts.ctypes.data_as(i64p), lo.ctypes.data_as(i64p), hi.ctypes.data_as(i64p),
+                                             rank, EXCHANGE[mode], cap, C.byref(chosen), C.byref(ns),
+                                             sends.ctypes.data_as(i64p), C.byref(nr), recvs.ctypes.data_as(i64p), C.byref(rb)))
+    plan = ExchangePlan(EXCHANGE_NAMES[chosen.value])
+    if plan.mode != "allgather":
+        plan.sends = [tuple(int(v) for v in sends[3 * i:3 * i + 3]) for i in range(ns.value)]
+        plan.recvs = [tuple(int(v) for v in recvs[3 * i:3 * i + 3]) for i in range(nr.value)]
+    plan.recv_bytes = int(rb.value)
+    return plan
+
+
+class Comm:
+    """spmvb200_comm_t: the ranks of a row-partitioned run."""
+
+    def __init__(self, handle, keep=None):
+        self._h = handle
+        self._keep = keep
+
+    @staticmethod
+    def local(nranks: int, devices=None):
+        """In-process communicator: returns one Comm per rank (several ranks may share a GPU)."""
+        arr = (C.c_void_p * nranks)()
+        dev = None if devices is None else (C.c_int * nranks)(*[int(v) for v in devices])
+        _check(_abi.lib().spmvb200_comm_create_local(nranks, dev, arr))
+        return [Comm(C.c_void_p(arr[r])) for r in range(nranks)]
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(_abi.lib().spmvb200_comm_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def nccl(uid: bytes, rank: int, nranks: int) -> "Comm":
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _check(_abi.lib().spmvb200_comm_create_nccl(buf, rank, nranks, C.byref(h)))
+        return Comm(h)
+
+    @staticmethod
+    def from_torch(dist, torch) -> "Comm":
+        """One process per GPU under torchrun: torch.distributed carries rank 0's id to the others (plumbing only)."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = Comm.unique_id() if rank == 0 else bytes(128)
+        t = torch.frombuffer(bytearray(uid), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        return Comm.nccl(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    @property
+    def rank(self):
+        r, n, d = C.c_int(), C.c_int(), C.c_int()
+        _check(_abi.lib().spmvb200_comm_rank(self._h, C.byref(r), C.byref(n), C.byref(d)))
+        return r.value
+
+    @property
+    def nranks(self):
+        r, n, d = C.c_int(), C.c_int(), C.c_int()
+        _check(_abi.lib().spmvb200_comm_rank(self._h, C.byref(r), C.byref(n), C.byref(d)))
+        return n.value
+
+    def barrier(self):
+        _check(_abi.lib().spmvb200_comm_barrier(self._h))
+
+    def allreduce(self, value: float, op: str = "max") -> float:
+        v = C.c_double(float(value))
+        _check(_abi.lib().spmvb200_comm_allreduce(self._h, C.byref(v), {"max": 0, "sum": 1, "min": 2}[op]))
+        return v.value
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            _abi.lib().spmvb200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
 
 class DistributedSpMV:
-    """Iterated x <- A x on a row partition of A, local rows already resident as a CSR DeviceMatrix."""
+    """spmvb200_dist_t: iterated x <- alpha A x on this rank's row block (see include/spmv_b200.h)."""
 
-    def __init__(self, sp, torch, dist, local, starts, rank: int, mode: str = "auto", overlap: bool = True,
-                 spare_ctas: int = 2, fmt=None, column_split: bool = False):
-        """`local`: this rank's rows.  A CSR block is analysed (column span -> halo or all-gather, interior/boundary row
-        split).  `column_split` (CSR block, all-gather exchange): the block is cut by COLUMNS instead -- the entries
-        that reference the rank's own slice of x form one matrix, which runs while x is being gathered, the rest a
-        second one that runs afterwards and adds to the same rows; for matrices without a band (power law) this is the
-        only way to overlap.  `fmt`: format the pieces are converted to (e.g. HYB for BASELINE configs[3])."""
-        self.sp, self.torch, self.dist = sp, torch, dist
-        self.rank, self.starts = rank, np.asarray(starts, dtype=np.int64)
-        self.P = len(starts) - 1
-        self.n = int(starts[-1])
-        self.s, self.e = int(starts[rank]), int(starts[rank + 1])
+    def __init__(self, comm: Comm, local, starts, mode: str = "auto", fmt: int = 0, column_split: bool = False,
+                 overlap: bool = True, consume_local: bool = False):
+        self.comm = comm
+        self.starts = np.ascontiguousarray(starts, dtype=np.int64)
+        flags = (CONSUME_LOCAL if consume_local else 0) | (COLUMN_SPLIT if column_split else 0) | (0 if overlap else NO_OVERLAP)
+        h = C.c_void_p()
+        _check(_abi.lib().spmvb200_dist_create(comm._h, local._h, self.starts.ctypes.data_as(i64p), EXCHANGE[mode], int(fmt),
+                                               flags, C.byref(h)))
+        self._h = h
+        self._local = local
+        if consume_local:
+            local._h = None  # the executor owns (or has destroyed) it
+        r = comm.rank
+        self.rank = r
+        self.s, self.e = int(self.starts[r]), int(self.starts[r + 1])
         self.rows = self.e - self.s
-        dev = torch.device("cuda", torch.cuda.current_device())
-        # ping-pong x buffers (+ slack so vector loads past the end stay in bounds)
-        self.X = [torch.zeros(self.n + 16, dtype=torch.float64, device=dev) for _ in range(2)]
-        self.compute = torch.cuda.Stream()
-        # the exchange runs on a high-priority stream: its (cooperative) NCCL kernel must get SM slots while the
-        # interior SpMV, whose grid fills every SM for the whole step, is running
-        self.comm = torch.cuda.Stream(priority=-1)
-        self.accumulate = set()  # ids of blocks that add to rows another block of the same step has written
-        if column_split and local.info.format == sp.CSR and self.P > 1:
-            span = {"col_min": 0, "col_max": self.n - 1, "lo_end": self.rows, "hi_begin": 0}
-            mode = "allgather"
-        elif local.info.format == sp.CSR:
-            span = local.column_span(self.s, self.e)
-        else:  # ELL / COO / hybrid row blocks: no column analysis, every rank is taken to need all of x
-            span = {"col_min": 0, "col_max": self.n - 1, "lo_end": self.rows, "hi_begin": 0}
-            mode = "allgather"
-        need = [(0, 0)] * self.P
-        mine = torch.tensor([span["col_min"], span["col_max"] + 1], dtype=torch.int64, device=dev)
-        if self.P > 1:
-            allneed = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(self.P)]
-            dist.all_gather(allneed, mine)
-            need = [tuple(int(v) for v in t.tolist()) for t in allneed]
-        else:
-            need = [tuple(int(v) for v in mine.tolist())]
-        self.plan = make_exchange_plan(self.starts, need, rank, mode)
-        blocks = split_rows(span["lo_end"], span["hi_begin"], self.rows) if overlap and self.P > 1 else [(0, self.rows, True)]
-        self.blocks = []
-        pieces = None
-        if column_split and local.info.format == sp.CSR and self.P > 1:
-            inside, outside = local.column_split(self.s, self.e)
-            if fmt is not None and fmt != sp.CSR:
-                inside, outside = inside.convert(fmt), outside.convert(fmt)
-            pieces = [(inside, 0, self.rows, False), (outside, 0, self.rows, True)]
-            self.accumulate.add(id(outside))
-        elif fmt is not None and fmt != local.info.format:
-            local = local.convert(fmt)
-            blocks = [(0, self.rows, True)]
-        if pieces is None:
-            pieces = [(local if (b, e) == (0, self.rows) else local.row_block(b, e), b, e, remote) for b, e, remote in blocks]
-        for A, b, e, remote in pieces:
-            A.set_stream(self.compute.cuda_stream)
-            A.set_option("beta0", 0 if id(A) in self.accumulate else 1)
-            if not remote and self.P > 1:
-                # The interior kernel is persistent and would fill every SM; keep CTA slots free so
-                # the NCCL kernel of the concurrent exchange is not locked out until it drains.
-                # (measured at 4 GPUs, 512^3: all-gather 3.70 -> 3.14 ms with 2 spare slots; the halo
-                # exchange moves 2 MB and is better off with the full grid: 2.38 vs 2.57 ms)
-                A.set_option("csr.spare_ctas", spare_ctas if self.plan.mode == "allgather" else 0)
-            self.blocks.append((A, b, e, remote))
-        self.local = local
-        self.k = 0
-        self.nnz_local = local.num_entries
-        self.launches_per_step = len(self.blocks)
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            _abi.lib().spmvb200_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    @property
+    def info(self) -> dict:
+        inf = _abi.DistInfo()
+        _check(_abi.lib().spmvb200_dist_info(self._h, C.byref(inf)))
+        d = {n: int(getattr(inf, n)) for n, _ in _abi.DistInfo._fields_}
+        d["exchange"] = EXCHANGE_NAMES[d["exchange"]]
+        return d
+
+    def blocks(self):
+        """[(row_begin, row_end, needs_remote_x, kernel_name)]"""
+        from . import DeviceMatrix
+        out = []
+        for b in range(self.info["n_blocks"]):
+            rb, re_, rem, mh = C.c_int64(), C.c_int64(), C.c_int32(), C.c_void_p()
+            _check(_abi.lib().spmvb200_dist_block(self._h, b, C.byref(rb), C.byref(re_), C.byref(rem), C.byref(mh)))
+            name = _abi.lib().spmvb200_kernel_name(mh).decode()
+            out.append((rb.value, re_.value, bool(rem.value), name))
+        return out
+
+    def block_matrix(self, b: int):
+        """Borrowed DeviceMatrix view of block b (do not destroy)."""
+        from . import DeviceMatrix
+        mh = C.c_void_p()
+        _check(_abi.lib().spmvb200_dist_block(self._h, b, None, None, None, C.byref(mh)))
+        m = DeviceMatrix(mh)
+        m.destroy = lambda: None  # borrowed
+        return m
 
     def set_x(self, x_local):
-        """Set this rank's slice of the current x (host or device tensor/array of `rows` values)."""
-        t = self.torch.as_tensor(x_local, dtype=self.torch.float64).to(self.X[0].device)
-        self.X[self.k % 2][self.s:self.e].copy_(t)
-        self.torch.cuda.synchronize()
+        x = np.ascontiguousarray(x_local, dtype=np.float64)
+        assert x.shape[0] == self.rows
+        _check(_abi.lib().spmvb200_dist_set_x(self._h, x.ctypes.data_as(f64p)))
 
-    def x_local(self):
-        return self.X[self.k % 2][self.s:self.e]
+    def get_x(self):
+        x = np.empty(self.rows)
+        _check(_abi.lib().spmvb200_dist_get_x(self._h, x.ctypes.data_as(f64p)))
+        return x
 
-    def step(self, scale: float = 0.0):
-        """One iteration: exchange x_k, y = A x_k written into x_{k+1}'s local slice.
-        `scale` != 0 multiplies the new slice by it (keeps long benchmark iterations finite)."""
-        torch = self.torch
-        cur, nxt = self.X[self.k % 2], self.X[(self.k + 1) % 2]
-        ready = torch.cuda.Event()
-        self.comm.wait_stream(self.compute)  # x_k's local slice was produced on the compute stream
-        with torch.cuda.stream(self.comm):
-            exchange(self.dist, cur, self.starts, self.rank, self.plan)
-            ready.record(self.comm)
-        with torch.cuda.stream(self.compute):
-            # y = alpha*A*x ("beta0" + spmvb200_set_alpha): the sliced CSR kernel owns whole rows and stores them, so
-            # there is no clearing pass over x_{k+1}, no read of it by reductions and no separate scaling kernel
-            # (8-GPU step 1.02 -> see DESIGN.md section 8); kernels that add partial sums clear their rows first.
-            alpha = scale if scale else 1.0
-            waited = False
-            # interior block first (no remote x), then the boundary blocks after the exchange
-            for A, b, e, remote in sorted(self.blocks, key=lambda t: t[3]):
-                if remote and not waited:
-                    self.compute.wait_event(ready)
-                    waited = True
-                A.bind_x(cur.data_ptr())
-                A.bind_y(nxt.data_ptr() + 8 * (self.s + b))
-                A.set_alpha(alpha)
-                A.spmv()
-            if not waited:
-                self.compute.wait_event(ready)
-        self.k += 1
+    def x_device(self) -> int:
+        p = C.c_void_p()
+        _check(_abi.lib().spmvb200_dist_x_device(self._h, C.byref(p)))
+        return p.value or 0
+
+    def step(self, alpha: float = 1.0):
+        _check(_abi.lib().spmvb200_dist_step(self._h, float(alpha)))
 
     def synchronize(self):
-        self.torch.cuda.synchronize()
+        _check(_abi.lib().spmvb200_dist_sync(self._h))
+
+    def time(self, steps: int, warmup: int = 3, alpha: float = 1.0) -> float:
+        """Device milliseconds of `steps` steps on this rank (NCCL communicators)."""
+        return time_steps([self], steps, warmup, alpha)[0]
+
+    def run_host(self, xs, ys, alpha: float = 1.0) -> float:
+        """len(xs) independent products through pinned host slices, pipelined; returns device milliseconds."""
+        n = len(xs)
+        xp = (f64p * n)(*[x.ctypes.data_as(f64p) for x in xs])
+        yp = (f64p * n)(*[y.ctypes.data_as(f64p) for y in ys])
+        ms = C.c_float()
+        _check(_abi.lib().spmvb200_dist_run_host(self._h, n, xp, yp, float(alpha), C.byref(ms)))
+        return float(ms.value)
 
 
-# --------------------------------------------------------------------------------------------
-# bench.py --gpus N --workload c4_hyb: BASELINE configs[3], hybrid ELL+COO on the R-MAT 2^26 x 32 matrix, row-partitioned
-# --------------------------------------------------------------------------------------------
-
-def bench_hybrid(args) -> int:
-    """Rows cut into `world` blocks of equal non-zeros; every rank converts ITS rows to the hybrid format (the ELL part
-    and the COO tail both follow the row owner) and x is all-gathered between iterations: a power-law
-    matrix references all of x from every block, so there is no halo to exploit and nothing to overlap with."""
-    import torch
-    import torch.distributed as dist
-
-    import spmv_cache_trace_b200 as sp
-    from bench import METRIC, NOMINAL_HBM_GBS, UNIT, ClockSampler, measured_peak
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local_rank)
-    sp.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    scale_log2 = int(os.environ.get("SPMV_BENCH_RMAT_SCALE", "26"))
-    ef = int(os.environ.get("SPMV_BENCH_RMAT_EF", "32"))
-    seed = 0x5EED0004
-    N = 1 << scale_log2
-    peak, peak_src = measured_peak()
-
-    full = sp.generators.rmat(scale_log2, ef, seed, fmt=sp.CSR)  # every rank: the partition needs the global row_ptr
-    starts = sp.partition.rows_nnz(full, world)
-    s, e = int(starts[rank]), int(starts[rank + 1])
-    block = full.row_block(s, e)
-    nnz = full.num_entries
-    del full
-    # the reference's hybrid of this rank's rows defines the bytes counted (one ELL part + one COO tail per rank) ...
-    inf = block.convert(sp.HYB).info
-    sizes = torch.tensor([12 * inf.num_ell_entries + 16 * inf.num_coo_entries, inf.num_coo_entries, inf.ell_row_length],
-                         dtype=torch.int64, device="cuda")
-    # ... what runs is that block cut by columns (own slice of x / the rest), each piece converted to hybrid, so that
-    # the own-columns piece overlaps the all-gather (SPMV_COLUMN_SPLIT=0: one hybrid matrix per rank, no overlap)
-    split = os.environ.get("SPMV_COLUMN_SPLIT", "1") != "0" and world > 1
-    allsizes = [torch.zeros_like(sizes) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(allsizes, sizes)
-    else:
-        allsizes = [sizes]
-    per_rank = [[int(v) for v in t.tolist()] for t in allsizes]
-    B = sum(p[0] for p in per_rank) + 16 * N
-
-    ALPHA = 1.0 / 8192.0  # keeps x_(k+1) = alpha A x_k finite: hub rows of the R-MAT matrix sum ~10^6 entries
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    eng = DistributedSpMV(sp, torch, dist, block, starts, rank, mode="allgather", overlap=False, fmt=sp.HYB, column_split=split)
-    del block
-    g = torch.Generator(device="cpu").manual_seed(99 + rank)
-    eng.set_x(torch.rand(e - s, generator=g, dtype=torch.float64) - 0.5)
-    for _ in range(max(args.warmup, 3)):
-        eng.step(scale=ALPHA)
-    eng.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = sp.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ev0.record(eng.compute)
-    for _ in range(args.steps):
-        eng.step(scale=ALPHA)
-    ev1.record(eng.compute)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    if os.environ.get("SPMV_DEBUG_TIMES"):
-        print(f"[rank {rank}] rows {e - s} step {float(ms.item()) / args.steps:.3f} ms pieces "
-              f"{[(int(A.info.ell_row_length), int(A.info.num_coo_entries), A.get_option('coo.col_block_log2')) for A, _, _, _ in eng.blocks]}",
-              flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    t = float(ms.item()) * 1e-3 / args.steps
-    xnorm = float(torch.linalg.vector_norm(eng.x_local()).item())
-    launches = int(sp.launch_count() - launches0)
-    # end to end: the rank's slice of x up from pinned host memory, its slice of the result back
-    hx = torch.empty(e - s, dtype=torch.float64).pin_memory()
-    hy = torch.empty(e - s, dtype=torch.float64).pin_memory()
-    hx.copy_(torch.rand(e - s, dtype=torch.float64) - 0.5)
-    e2e_steps = max(3, min(args.steps, 10))
-    if world > 1:
-        dist.barrier()
-    ev0.record(eng.compute)
-    for _ in range(e2e_steps):
-        with torch.cuda.stream(eng.compute):
-            eng.x_local().copy_(hx, non_blocking=True)
-        eng.step(scale=ALPHA)
-        with torch.cuda.stream(eng.compute):
-            hy.copy_(eng.x_local(), non_blocking=True)
-        eng.compute.synchronize()
-    ev1.record(eng.compute)
-    torch.cuda.synchronize()
-    ems = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    kernel = eng.blocks[0][0].kernel_name
-    recv = eng.plan.recv_bytes
-    pieces = [{"rows": int(A.info.rows), "ell_row_length": int(A.info.ell_row_length), "num_coo_entries": int(A.info.num_coo_entries),
-               "needs_remote_x": bool(r)} for A, _, _, r in eng.blocks]
-    del eng
-    sampler.stop()
-
-    single = None
-    if world > 1 and rank == 0 and not getattr(args, "no_single", False):
-        try:
-            H = sp.generators.rmat(scale_log2, ef, seed, fmt=sp.HYB)
-            H.set_option("beta0", 1)  # the same operation the ranks perform: y = alpha*A*x, no exchange
-            H.set_alpha(ALPHA)
-            steps1 = max(3, min(args.steps, 10))
-            total_ms, _ = sp.time_rotating([H], steps1, 3, False)
-            single = {"ms_per_step": total_ms / steps1, "algorithmic_bytes": int(H.algorithmic_bytes())}
-            del H
-        except Exception as ex:
-            single = {"error": str(ex)}
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": B / t / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c4_hyb_row_partitioned", "description": f"row-partitioned hybrid ELL+COO, R-MAT 2^{scale_log2} x {ef} "
-                       "(config 4), x_(k+1) = alpha A x_k, one step = all-gather of x + ELL kernel + COO kernel per rank",
-                       "rows": N, "nonzeros": int(nnz), "algorithmic_bytes": int(B),
-                       "partition": "balanced non-zeros (spmvb200_partition_rows_nnz)", "row_starts": [int(v) for v in starts],
-                       "per_rank": [{"matrix_size": p[0], "num_coo_entries": p[1], "ell_row_length": p[2]} for p in per_rank],
-                       "exchange": "allgather", "recv_bytes_per_step_per_rank": int(recv),
-                       "overlap": "column split: the entries that reference the rank's own slice of x run during the all-gather"
-                                  if split else "none", "rank0_pieces": pieces,
-                       "l2": "working set per rank far larger than L2"},
-            "gflops": 2.0 * nnz / t / 1e9, "frac_of_8TBs_nominal_per_gpu": B / t / 1e9 / world / NOMINAL_HBM_GBS,
-            "roofline": {"bound": "hbm", "achieved": B / world / t / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": B / world / t / 1e9 / peak, "traffic": None,
-                         "kernel": kernel + " (per rank; step time includes the exchange)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(B / world)},
-            "e2e": {"value": B / (float(ems.item()) * 1e-3 / e2e_steps) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * N,
-                    "d2h_bytes_per_step": 8 * N, "ms_per_step": float(ems.item()) / e2e_steps,
-                    "call": "per rank: pinned x slice -> device, exchange + SpMV, y slice -> pinned host"},
-            "gpu_launches": launches, "clocks": sampler.summary(t0, t1), "x_norm": xnorm,
-        }
-        if single and "ms_per_step" in single:
-            line["single_gpu"] = {"ms_per_step": single["ms_per_step"], "gbs": single["algorithmic_bytes"] / (single["ms_per_step"] * 1e-3) / 1e9,
-                                  "speedup": single["ms_per_step"] / (t * 1e3)}
-        elif single:
-            line["single_gpu"] = single
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
-
-
-# --------------------------------------------------------------------------------------------
-# bench.py --gpus N  (N > 1)
-# --------------------------------------------------------------------------------------------
-
-def bench_main(args) -> int:
-    if getattr(args, "workload", None) == "c4_hyb":
-        return bench_hybrid(args)
-    import torch
-    import torch.distributed as dist
-
-    import spmv_cache_trace_b200 as sp
-    from bench import METRIC, NOMINAL_HBM_GBS, UNIT, ClockSampler, cpu_baseline, measured_peak
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local_rank)
-    sp.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n = int(os.environ.get("SPMV_BENCH_GRID", "512"))
-    N = n ** 3
-    starts = partition_rows_ref(N, world)
-    s, e = int(starts[rank]), int(starts[rank + 1])
-    peak, peak_src = measured_peak()
-
-    # every rank generates only its own rows of the 27-point operator, on its own GPU
-    local = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR, row_begin=s, row_end=e)
-    nnz_local = torch.tensor([local.num_entries], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(nnz_local)
-    nnz = int(nnz_local.item())
-    B = 4 * (N + 1) + 12 * nnz + 16 * N  # matrix_size + x_size + y_size, reference-equivalent (SURVEY 8d)
-
-    # x_(k+1) = A x_k / 52: every eigenvalue of the 27-point operator (26 on the diagonal, -1 off it)
-    # lies within 52 of zero, so the iterates stay finite however many steps are timed.  The scaling
-    # is one tiny elementwise kernel on the rank's slice (8 B/row next to ~330 B/row of matrix).
-    SCALE = 1.0 / 52.0
-    results = {}
-    modes = [args.exchange] if getattr(args, "exchange", None) else ["allgather", "halo"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    marks = {}
-    for mode in modes:
-        eng = DistributedSpMV(sp, torch, dist, local, starts, rank, mode=mode, overlap=True,
-                              spare_ctas=int(os.environ.get("SPMV_SPARE_CTAS", "2")))
-        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-        eng.set_x(torch.rand(e - s, generator=g, dtype=torch.float64) - 0.5)
-        for _ in range(max(args.warmup, 3)):
-            eng.step(scale=SCALE)
-        eng.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        launches0 = sp.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        marks[mode] = [time.perf_counter(), None]
-        ev0.record(eng.compute)
-        for _ in range(args.steps):
-            eng.step(scale=SCALE)
-        ev1.record(eng.compute)
-        torch.cuda.synchronize()
-        marks[mode][1] = time.perf_counter()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
-        t = float(ms.item()) * 1e-3 / args.steps
-        xnorm = float(torch.linalg.vector_norm(eng.x_local()).item())
-        results[mode] = {"ms_per_step": t * 1e3, "gbs": B / t / 1e9, "gflops": 2.0 * nnz / t / 1e9,
-                         "recv_bytes_per_step_per_rank": eng.plan.recv_bytes, "plan": eng.plan.mode,
-                         "row_blocks": [(b, e2, r) for _, b, e2, r in eng.blocks],
-                         "gpu_launches": int(sp.launch_count() - launches0), "x_norm": xnorm,
-                         "kernel": max(eng.blocks, key=lambda t: t[2] - t[1])[0].kernel_name}
-        # end to end: this rank's slice of x from pinned host memory each step, its slice of y back
-        hx = torch.empty(e - s, dtype=torch.float64).pin_memory()
-        hy = torch.empty(e - s, dtype=torch.float64).pin_memory()
-        hx.copy_(torch.rand(e - s, dtype=torch.float64) - 0.5)
-        e2e_steps = max(3, min(args.steps, 10))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ev0.record(eng.compute)
-        for _ in range(e2e_steps):
-            with torch.cuda.stream(eng.compute):
-                eng.x_local().copy_(hx, non_blocking=True)
-            eng.step(scale=SCALE)
-            with torch.cuda.stream(eng.compute):
-                hy.copy_(eng.x_local(), non_blocking=True)
-            eng.compute.synchronize()
-        ev1.record(eng.compute)
-        torch.cuda.synchronize()
-        ems = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        results[mode]["e2e_ms_per_step"] = float(ems.item()) / e2e_steps
-        del eng
-    sampler.stop()
-
-    # one-GPU time of the SAME matrix measured in the same job on rank 0 (strong-scaling reference)
-    single = None
-    if world > 1 and rank == 0 and not getattr(args, "no_single", False):
-        try:
-            full = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR)
-            full.set_option("beta0", 1)  # the same operation the ranks perform: y = alpha*A*x, no exchange
-            full.set_alpha(SCALE)
-            total_ms, _ = sp.time_rotating([full], max(3, min(args.steps, 10)), 3, False)
-            single = total_ms / max(3, min(args.steps, 10))
-            del full
-        except Exception as ex:  # e.g. not enough memory left
-            single = None
-            results["single_gpu_error"] = str(ex)
-    if world > 1:
-        dist.barrier()
-
-    if rank == 0:
-        best = min(results, key=lambda m: results[m]["ms_per_step"] if isinstance(results[m], dict) and "ms_per_step" in results[m] else 1e30)
-        r = results[best]
-        t = r["ms_per_step"] * 1e-3
-        clocks = sampler.summary(*marks[best])
-        per_rank_bytes = B / world
-        line = {
-            "metric": METRIC, "value": r["gbs"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c5_csr_row_partitioned", "description": f"row-partitioned CSR, 3D 27-point {n}^3 "
-                       f"(config 5), x_(k+1) = A x_k, one step = exchange of x + SpMV", "rows": N, "nonzeros": nnz,
-                       "algorithmic_bytes": B, "partition": "reference rule ceil(rows/P) (csr-matrix.cpp:77-83)",
-                       "exchange": best, "overlap": "interior rows run during the exchange",
-                       "l2": "working set per rank far larger than L2"},
-            "gflops": r["gflops"], "frac_of_8TBs_nominal_per_gpu": r["gbs"] / world / NOMINAL_HBM_GBS,
-            "roofline": {"bound": "hbm", "achieved": per_rank_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": per_rank_bytes / t / 1e9 / peak, "traffic": None,
-                         "kernel": r.get("kernel", "csr kernel") + " (per rank; step time includes the exchange)",
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(per_rank_bytes)},
-            "e2e": {"value": B / (r["e2e_ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N, "ms_per_step": r["e2e_ms_per_step"],
-                    "call": "per rank: pinned x slice -> device, exchange + SpMV, y slice -> pinned host"},
-            "gpu_launches": r["gpu_launches"], "clocks": clocks, "exchange_variants": results,
-        }
-        if single:
-            line["single_gpu"] = {"ms_per_step": single, "gbs": B / (single * 1e-3) / 1e9,
-                                  "speedup": single / r["ms_per_step"]}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+def time_steps(engines, steps: int, warmup: int = 3, alpha: float = 1.0):
+    """spmvb200_dist_time over the executors this thread drives; returns per-rank device milliseconds."""
+    n = len(engines)
+    arr = (C.c_void_p * n)(*[e._h for e in engines])
+    ms = np.zeros(n, np.float32)
+    _check(_abi.lib().spmvb200_dist_time(arr, n, warmup, steps, float(alpha), ms.ctypes.data_as(f32p)))
+    return [float(v) for v in ms]

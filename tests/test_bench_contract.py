@@ -28,10 +28,13 @@ def test_reference_arm_runs_on_the_host_cores():
     line = last_json_line(p.stdout)
     assert BASE_KEYS <= set(line) and line["impl"] == "reference"
     assert line["metric"] == "spmv_effective_bandwidth" and line["unit"] == "GB/s" and line["higher_is_better"] is True
-    assert line["config"]["workload"] == "c2_ell" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["config"]["workload"] == "c5_csr" and line["dtype"] == "f64" and line["vs_baseline"] is None
     cb = line["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] > 0
-    assert cb["algorithmic_bytes"] == 209715200  # BASELINE config 2: 176 160 768 + 2 x 16 777 216
+    # config 5 does not fit the reference's int32 sizes: the CPU sample is a 512 x 512 x 24 slab of the same operator,
+    # and the line says so: 12 * 1534^2 * 70 + 4 * (rows + 1) + 16 * rows
+    assert cb["algorithmic_bytes"] == 12 * 1534 * 1534 * 70 + 4 * (512 * 512 * 24 + 1) + 16 * 512 * 512 * 24
+    assert "SLAB" in cb["sample"] and "slab" in line["config"]["sample"].lower()
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

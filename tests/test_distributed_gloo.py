@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle.generators_ref import stencil_entries  # noqa: E402
-from spmv_cache_trace_b200.distributed import (exchange, make_exchange_plan, owner_of,  # noqa: E402
+from spmv_cache_trace_b200.distributed import (exchange, exchange_plan, make_exchange_plan, owner_of,  # noqa: E402
                                                partition_rows_ref, split_rows)
 
 
@@ -205,3 +205,24 @@ def test_plan_arithmetic():
     assert split_rows(3, 20, 25) == [(0, 3, True), (3, 20, False), (20, 25, True)]
     assert split_rows(0, 20, 25) == [(0, 20, False), (20, 25, True)]
     assert split_rows(10, 10, 25) == [(0, 25, True)]
+
+
+def test_library_plan_equals_the_python_restatement():
+    """spmvb200_exchange_plan (the arithmetic the executor below the C ABI runs; host only, no device) against
+    make_exchange_plan above, on random partitions and column ranges."""
+    rng = np.random.default_rng(17)
+    for _ in range(200):
+        P = int(rng.integers(1, 9))
+        n = int(rng.integers(P, 400))
+        cuts = np.sort(rng.integers(0, n + 1, P - 1)) if P > 1 else np.zeros(0, dtype=np.int64)
+        starts = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+        need = []
+        for q in range(P):
+            lo = int(rng.integers(0, n + 1))
+            hi = int(rng.integers(0, n + 1))
+            need.append((lo, hi))  # hi <= lo: the rank references nothing
+        for mode in ("auto", "halo", "allgather"):
+            for rank in range(P):
+                a, b = exchange_plan(starts, need, rank, mode), make_exchange_plan(starts, need, rank, mode)
+                assert a.mode == b.mode and a.recv_bytes == b.recv_bytes
+                assert sorted(a.sends) == sorted(b.sends) and sorted(a.recvs) == sorted(b.recvs), (starts, need, rank, mode)
