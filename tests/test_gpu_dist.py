@@ -75,7 +75,7 @@ def test_stencil_iteration_matches_the_oracle(oracle, P, mode):
         neighbours = (r > 0) + (r < P - 1)
         if plan.mode == "halo":
             assert (inf["n_recvs"], inf["n_sends"]) == (len(plan.recvs), len(plan.sends)) == (neighbours, neighbours)
-            assert 8 * neighbours * nx * ny < plan.recv_bytes <= 8 * neighbours * (nx * ny + nx + 1)  # one grid plane (+ a line)
+            assert 8 * neighbours * nx * ny <= plan.recv_bytes <= 8 * neighbours * (nx * ny + nx + 1)  # one grid plane (+ a line)
         blocks = eng.blocks()
         assert len(blocks) == 1 + neighbours  # interior + one boundary block per neighbour
         assert sum(1 for b in blocks if not b[2]) == 1 and inf["interior_rows"] > 0
