@@ -313,11 +313,18 @@ int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double
  *               lane, one segmented warp scan per 128 entries (default, any entry order), 3 one reduction
  *               per entry, 4 register-staged, striped lanes; "coo.items" 2|4|8 stripes per warp (algo 4);
  *               "coo.threads" 64|128|256; "coo.stages" 2|3|4 and "coo.ctas_per_sm" (algo 1).
+ *               "coo.hot" 1: hot-column kernel (row-sorted entries): the entries are cut into segments, every segment's
+ *               most referenced columns ("coo.hot_slots", default 24576) are gathered from shared memory by a
+ *               persistent grid ("coo.hot_threads" 256|512|1024, "coo.hot_entries" 4|8 per lane, "coo.hot_segments"
+ *               per CTA); off by default: measured slower than the plain kernel.  Experiment switches of
+ *               the plain kernel: "coo.xload" 0 ld.global.nc | 1 ld.global.cg | 2 nc L1::no_allocate | 3 nc L1::evict_last
+ *               | 4 cp.async through shared memory; "coo.carveout" preferred shared-memory carve-out in percent.
  *   host path   "host.zero_copy" (default 1; ELL): spmvb200_spmv_host lets the kernel read and write
  *               pinned host y directly; 2 = y up by DMA in "host.chunks" row chunks, results stored by
  *               the kernel; 0 = copies only ("host.chunks" > 1 pipelines them). */
 int spmvb200_set_option(spmvb200_matrix_t m, const char *key, int64_t value);
-/* Also answers the read-only keys "coo.col_block_log2" (what the builder applied) and
+/* Also answers the read-only keys "coo.col_block_log2" (what the builder applied), "coo.hot_coverage_permille" and
+ * "coo.hot_segments_built" (the hot-column tables, if built), and
  * "last_launch.overlapped" / "last_launch.pdl" (how the library ordered the last kernel of this matrix). */
 int spmvb200_get_option(spmvb200_matrix_t m, const char *key, int64_t *value);
 /* Name of the kernel spmvb200_spmv launches for this matrix. */

@@ -970,7 +970,8 @@ static int launch_format(Matrix * m)
         SPMV_TRY(launch_ell(m, true));
         if (m->coo_n > 0) plan_run(m, false);
         SPMV_TRY(launch_coo(m));
-        m->kernel_name = m->opt_coo_algo == 1 ? "ell_kernel+coo_segmented_kernel" : m->opt_coo_algo == 4 ? "ell_kernel+coo_warp_kernel" : "ell_kernel+coo_warp4_kernel";
+        m->kernel_name = m->opt_coo_algo == 1 ? "ell_kernel+coo_segmented_kernel" : m->opt_coo_algo == 4 ? "ell_kernel+coo_warp_kernel"
+                         : (m->coo_n > 0 && !strcmp(m->kernel_name, "coo_hot_kernel")) ? "ell_kernel+coo_hot_kernel" : "ell_kernel+coo_warp4_kernel";
         return 0;
     }
     return fail(SPMVB200_ERR_INVALID, "unknown format");
@@ -998,9 +999,9 @@ SPMV_ABI_CATCH
 int spmvb200_prepare(spmvb200_matrix_t m)
 try {
     SPMV_TRY(check(m));
-    if (m->format != SPMVB200_CSR) return 0;  // only the CSR kernels keep launch metadata
+    if (m->format == SPMVB200_ELL) return 0;  // the ELL kernel keeps no launch metadata
     m->dry_run = true;
-    const int rc = launch_csr(m);
+    const int rc = m->format == SPMVB200_CSR ? launch_csr(m) : launch_coo(m);  // COO / hybrid tail: hot-column tables
     m->dry_run = false;
     if (rc) return rc;
     SPMV_CUDA(cudaStreamSynchronize(m->stream));
@@ -1257,6 +1258,13 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "coo.ctas_per_sm")) return &m->opt_coo_ctas;
     if (!strcmp(key, "coo.algo")) return &m->opt_coo_algo;
     if (!strcmp(key, "coo.items")) return &m->opt_coo_items;
+    if (!strcmp(key, "coo.xload")) return &m->opt_coo_xload;
+    if (!strcmp(key, "coo.carveout")) return &m->opt_coo_carveout;
+    if (!strcmp(key, "coo.hot")) return &m->opt_coo_hot;
+    if (!strcmp(key, "coo.hot_slots")) return &m->opt_coo_hot_slots;
+    if (!strcmp(key, "coo.hot_threads")) return &m->opt_coo_hot_threads;
+    if (!strcmp(key, "coo.hot_entries")) return &m->opt_coo_hot_entries;
+    if (!strcmp(key, "coo.hot_segments")) return &m->opt_coo_hot_segs;
     if (!strcmp(key, "beta0")) return &m->opt_beta0;
     if (!strcmp(key, "host.chunks")) return &m->opt_host_chunks;
     if (!strcmp(key, "host.zero_copy")) return &m->opt_host_zero_copy;
@@ -1268,6 +1276,19 @@ try {
     if (!m || !key) return fail(SPMVB200_ERR_INVALID, "null argument");
     int64_t * slot = option_slot(m, key);
     if (!slot) return fail(SPMVB200_ERR_INVALID, std::string("unknown option ") + key);
+    if (*slot != value && (slot == &m->opt_coo_hot || slot == &m->opt_coo_hot_slots || slot == &m->opt_coo_hot_threads ||
+                           slot == &m->opt_coo_hot_segs) && m->coo_hot_tried) {
+        // the tables were built for the old shape: drop them, the next launch / prepare rebuilds
+        SPMV_CUDA(cudaSetDevice(m->device));
+        SPMV_CUDA(cudaStreamSynchronize(m->stream));
+        if (m->coo_colh) {
+            const int64_t cap = round_up(m->coo_n, 4096) + kPadEntries;
+            m->device_bytes -= cap * 4 + (int64_t)m->coo_nseg * m->coo_hot_h * 4 + ((int64_t)m->coo_nseg + 1) * 8;
+        }
+        cudaFree(m->coo_colh); cudaFree(m->coo_hot_cols); cudaFree(m->coo_seg);
+        m->coo_colh = nullptr; m->coo_hot_cols = nullptr; m->coo_seg = nullptr;
+        m->coo_hot_tried = false;
+    }
     *slot = value;
     return 0;
 }
@@ -1278,6 +1299,14 @@ try {
     if (!m || !key || !value) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (!strcmp(key, "coo.col_block_log2")) {  // read-only: the column-block size the builder applied (0 = none)
         *value = m->coo_col_shift;
+        return 0;
+    }
+    if (!strcmp(key, "coo.hot_coverage_permille")) {  // read-only: share of the gathers served from the hot-column tables
+        *value = m->coo_colh ? (int64_t)(1000.0 * m->coo_hot_coverage + 0.5) : 0;
+        return 0;
+    }
+    if (!strcmp(key, "coo.hot_segments_built")) {
+        *value = m->coo_colh ? m->coo_nseg : 0;
         return 0;
     }
     if (!strcmp(key, "last_launch.overlapped")) {  // read-only: the last kernel was allowed to skip griddepcontrol.wait

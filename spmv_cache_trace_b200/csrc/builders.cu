@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <atomic>
@@ -81,6 +82,7 @@ void matrix_free(Matrix * m)
     cudaFree(m->rp); cudaFree(m->col); cudaFree(m->val); cudaFree(m->tile_row); cudaFree(m->span_row); cudaFree(m->flat_meta); cudaFree(m->flat_rowmap); cudaFree(m->slice_col); cudaFree(m->slice_val);
     cudaFree(m->ell_col); cudaFree(m->ell_val);
     cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
+    cudaFree(m->coo_colh); cudaFree(m->coo_hot_cols); cudaFree(m->coo_seg);
     if (m->own_x) cudaFree(m->x);
     if (m->own_y) cudaFree(m->y);
     if (m->upload_stream) cudaStreamDestroy(m->upload_stream);
@@ -681,6 +683,207 @@ int coo_column_blocks(Matrix * m)
         m->coo_row = row2; m->coo_col = col2; m->coo_val = val2;
     }
     m->coo_col_shift = shift;
+    return 0;
+}
+
+// ---- hot-column tables for scattered gathers -----------------------------------------------------------------------------
+// On a power-law matrix every lane of a gather hits its own 32 B sector: the COO kernel is bound by the sectors
+// the L1 and the L2 can deliver (ncu: l1tex 86 %, lts 78 %, DRAM 57 % busy on R-MAT 2^24), not by HBM.  But the
+// column popularity is as skewed as the row lengths: inside any stretch of a few hundred thousand entries, the 24 576 most
+// referenced columns receive more than half of the gathers (8 192: a third).  The builder therefore cuts the entries
+// into segments and gives every segment a table of its most referenced columns; the CTA that runs the segment
+// loads their x values into shared memory once (192 KB) and serves those gathers from there -- no sector traffic, and a
+// quarter of the L1 wavefronts of a divergent global load.
+__global__ void hot_sample_spread_kernel(int64_t n, const int32_t * col, int samples, int64_t stride, unsigned int * distinct)
+{
+    // one warp per sampled span of 128 entries: how many distinct 128 B lines of x do they gather from?
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= samples) return;
+    const int64_t base = ((int64_t)w * stride) & ~(int64_t)127;
+    unsigned int count = 0;
+    int lines[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t k = base + 4 * lane + j;
+        lines[j] = k < n ? (col[k] >> 4) : -1 - lane;
+    }
+    // distinct among the 128 values: a value counts if no EARLIER entry of the span has it (O(128) per entry, tiny sample)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bool first = true;
+        for (int src = 0; src < 32; ++src) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int other = __shfl_sync(0xffffffffu, lines[jj], src);
+                if ((src < lane || (src == lane && jj < j)) && other == lines[j]) first = false;
+            }
+        }
+        count += first ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) atomicAdd(distinct, count);
+}
+
+__global__ void hot_scatter_slots_kernel(int h, const int32_t * hot, int32_t * slot_of /* [columns] */, int value_is_slot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < h) slot_of[hot[i]] = value_is_slot ? i : -1;
+}
+
+__global__ void hot_remap_kernel(int64_t lo, int64_t hi, const int32_t * col, const int32_t * slot_of, int32_t * colh,
+                                 unsigned long long * hits)
+{
+    unsigned long long mine = 0;
+    for (int64_t k = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = col[k];
+        const int32_t sl = slot_of[c];
+        colh[k] = sl >= 0 ? (int32_t)(0x80000000u | (uint32_t)sl) : c;
+        mine += sl >= 0 ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(hits, mine);
+}
+
+__global__ void hot_keep_repeated_kernel(int runs, int h, const int32_t * counts_desc, int * kept)
+{
+    // the runs are sorted by count, descending: keep the first h of them, but none that is referenced only once
+    // (its x value would be fetched once either way)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < runs && i < h && counts_desc[i] >= 2 && (i + 1 == runs || i + 1 == h || counts_desc[i + 1] < 2)) *kept = i + 1;
+}
+
+int coo_build_hot(Matrix * m)
+{
+    if (m->coo_hot_tried) return 0;
+    m->coo_hot_tried = true;
+    const int64_t n = m->coo_n;
+    // Opt-in only ("coo.hot" = 1; 2 = with the scattered-gather test below).  Measured on R-MAT 2^24 x 16 it LOSES to
+    // the plain kernel (1.11 ms at best vs 1.04 ms, profiles/r02_sweep_q_coo_hot_columns.log): what bounds the divergent
+    // gather is the number of misses the L1 can hold in flight, which shrinks with every KB of shared memory the tables take
+    // (profiles/r02_sweep_r_coo_gather_paths.log: the plain kernel at 0/25/50/75/100 % carve-out: 1.05/1.09/1.22/1.81/3.46 ms).
+    if (m->opt_coo_hot <= 0 || !m->coo_sorted || n >= ((int64_t)1 << 32)) return 0;
+    cudaStream_t s = m->stream;
+    if (m->opt_coo_hot == 2) {
+        // scattered gathers?  sample 1024 spans of 128 entries: a banded matrix gathers from a handful of lines per
+        // span, a power-law matrix from ~128
+        const int samples = 1024;
+        Scratch<unsigned int> d;
+        SPMV_TRY(d.alloc(1));
+        SPMV_CUDA(cudaMemsetAsync(d.p, 0, sizeof(unsigned int), s));
+        hot_sample_spread_kernel<<<samples / 4, 128, 0, s>>>(n, m->coo_col, samples, std::max<int64_t>(128, n / samples), d.p);
+        SPMV_CUDA(cudaGetLastError());
+        unsigned int distinct = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&distinct, d.p, sizeof distinct, cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        if (distinct < 64u * samples) return 0;  // fewer than 64 distinct lines per 128 gathers: local enough
+    }
+    int h = (int)(m->opt_coo_hot_slots ? m->opt_coo_hot_slots : 24576);
+    h = std::max(1024, std::min(27648, h / 1024 * 1024));
+    const int threads = (int)(m->opt_coo_hot_threads ? m->opt_coo_hot_threads : 1024);
+    const int ctas_per_sm = std::max(1, std::min(2048 / threads, (int)((int64_t)(227 * 1024 - 1024) / ((int64_t)h * 8))));
+    const int per_cta = (int)(m->opt_coo_hot_segs ? m->opt_coo_hot_segs : 4);
+    const int64_t want = (int64_t)m->sm_count * ctas_per_sm * per_cta;
+
+    // ---- segments: equal pieces of every column block, cut at multiples of 128 entries ---------------------------------
+    std::vector<int64_t> block_begin{0, n};
+    if (m->coo_col_shift > 0) {
+        const int64_t nblocks = (m->cols + ((int64_t)1 << m->coo_col_shift) - 1) >> m->coo_col_shift;
+        Scratch<unsigned long long> dh;
+        SPMV_TRY(dh.alloc(256));
+        SPMV_CUDA(cudaMemsetAsync(dh.p, 0, 256 * sizeof(unsigned long long), s));
+        block_hist_kernel<<<grid_for(n, m->sm_count), 256, 0, s>>>(n, m->coo_col, m->coo_col_shift, dh.p);
+        SPMV_CUDA(cudaGetLastError());
+        unsigned long long hist[256];
+        SPMV_CUDA(cudaMemcpyAsync(hist, dh.p, sizeof hist, cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        block_begin.assign(1, 0);
+        for (int64_t b = 0; b < nblocks; b++) block_begin.push_back(block_begin.back() + (int64_t)hist[b]);
+    }
+    std::vector<int64_t> seg{0};
+    const int64_t target = std::max<int64_t>(4096, (n + want - 1) / want);
+    for (size_t b = 0; b + 1 < block_begin.size(); b++) {
+        const int64_t lo = block_begin[b], hi = block_begin[b + 1];
+        if (hi <= lo) continue;
+        const int64_t pieces = std::max<int64_t>(1, (hi - lo + target / 2) / target);
+        for (int64_t q = 1; q < pieces; q++) {
+            const int64_t cut = (lo + (hi - lo) * q / pieces) & ~(int64_t)127;
+            if (cut > seg.back() && cut < hi) seg.push_back(cut);
+        }
+        seg.push_back(hi);
+    }
+    const int nseg = (int)seg.size() - 1;
+    if (nseg < 1) return 0;
+
+    // ---- per segment: the h most referenced columns ---------------------------------------------------------------------
+    int64_t longest = 0;
+    for (int q = 0; q < nseg; q++) longest = std::max(longest, seg[(size_t)q + 1] - seg[(size_t)q]);
+    Scratch<int32_t> keys2, uniq, counts, uniq2, counts2, slot_of;
+    Scratch<int> druns, dkept;
+    Scratch<unsigned long long> dhits;
+    Scratch<unsigned char> tmp;
+    SPMV_TRY(keys2.alloc(longest)); SPMV_TRY(uniq.alloc(longest)); SPMV_TRY(counts.alloc(longest));
+    SPMV_TRY(uniq2.alloc(longest)); SPMV_TRY(counts2.alloc(longest)); SPMV_TRY(slot_of.alloc(m->cols));
+    SPMV_TRY(druns.alloc(1)); SPMV_TRY(dkept.alloc(1)); SPMV_TRY(dhits.alloc(1));
+    size_t tb = 0, t1 = 0, t2 = 0, t3 = 0;
+    const int col_bits = bits_for(m->cols);
+    SPMV_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, t1, (const int32_t *)m->coo_col, keys2.p, longest, 0, col_bits, s));
+    SPMV_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, t2, keys2.p, uniq.p, counts.p, druns.p, longest, s));
+    SPMV_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, t3, counts.p, counts2.p, uniq.p, uniq2.p, longest, 0, 32, s));
+    tb = std::max(t1, std::max(t2, t3));
+    SPMV_TRY(tmp.alloc((int64_t)tb));
+    int32_t *colh = nullptr, *hot = nullptr;
+    int64_t * dseg = nullptr;
+    SPMV_TRY(alloc_streamed(m, &colh, n));
+    m->coo_colh = colh;  // owned from here on (freed with the matrix, or below if the layout is rejected)
+    SPMV_TRY(dev_alloc(m, &hot, (int64_t)nseg * h));
+    m->coo_hot_cols = hot;
+    SPMV_TRY(dev_alloc(m, &dseg, nseg + 1));
+    m->coo_seg = dseg;
+    SPMV_CUDA(cudaMemsetAsync(hot, 0, sizeof(int32_t) * (size_t)nseg * (size_t)h, s));
+    SPMV_CUDA(cudaMemsetAsync(slot_of.p, 0xff, sizeof(int32_t) * (size_t)m->cols, s));
+    SPMV_CUDA(cudaMemsetAsync(dhits.p, 0, sizeof(unsigned long long), s));
+    SPMV_CUDA(cudaMemcpyAsync(dseg, seg.data(), sizeof(int64_t) * seg.size(), cudaMemcpyHostToDevice, s));
+    for (int q = 0; q < nseg; q++) {
+        const int64_t lo = seg[(size_t)q], len = seg[(size_t)q + 1] - lo;
+        int32_t * table = hot + (int64_t)q * h;
+        size_t t = tb;
+        SPMV_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, t, (const int32_t *)(m->coo_col + lo), keys2.p, len, 0, col_bits, s));
+        t = tb;
+        SPMV_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, t, keys2.p, uniq.p, counts.p, druns.p, len, s));
+        int runs = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&runs, druns.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        if (runs <= 0) continue;
+        t = tb;
+        SPMV_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, t, counts.p, counts2.p, uniq.p, uniq2.p, runs, 0, 32, s));
+        SPMV_CUDA(cudaMemsetAsync(dkept.p, 0, sizeof(int), s));
+        hot_keep_repeated_kernel<<<(std::min(runs, h) + 255) / 256, 256, 0, s>>>(runs, h, counts2.p, dkept.p);
+        SPMV_CUDA(cudaGetLastError());
+        int kept = 0;
+        SPMV_CUDA(cudaMemcpyAsync(&kept, dkept.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        if (kept > 0) {
+            SPMV_CUDA(cudaMemcpyAsync(table, uniq2.p, sizeof(int32_t) * (size_t)kept, cudaMemcpyDeviceToDevice, s));
+            hot_scatter_slots_kernel<<<(kept + 255) / 256, 256, 0, s>>>(kept, table, slot_of.p, 1);
+        }
+        hot_remap_kernel<<<grid_for(len, m->sm_count), 256, 0, s>>>(lo, lo + len, m->coo_col, slot_of.p, colh, dhits.p);
+        if (kept > 0) hot_scatter_slots_kernel<<<(kept + 255) / 256, 256, 0, s>>>(kept, table, slot_of.p, 0);
+        SPMV_CUDA(cudaGetLastError());
+    }
+    unsigned long long hits = 0;
+    SPMV_CUDA(cudaMemcpyAsync(&hits, dhits.p, sizeof hits, cudaMemcpyDeviceToHost, s));
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    m->coo_hot_coverage = n > 0 ? (double)hits / (double)n : 0.0;
+    if (m->opt_coo_hot == 2 && m->coo_hot_coverage < 0.15) {  // not worth a persistent kernel with half the warps
+        const int64_t cap = round_up(n, 4096) + kPadEntries;
+        cudaFree(m->coo_colh); cudaFree(m->coo_hot_cols); cudaFree(m->coo_seg);
+        m->coo_colh = nullptr; m->coo_hot_cols = nullptr; m->coo_seg = nullptr;
+        m->device_bytes -= cap * 4 + (int64_t)nseg * h * 4 + (nseg + 1) * 8;
+        return 0;
+    }
+    m->coo_hot_h = h;
+    m->coo_nseg = nseg;
+    m->aux_dirty = true;
     return 0;
 }
 

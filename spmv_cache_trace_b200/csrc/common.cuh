@@ -100,6 +100,16 @@ struct spmvb200_matrix_s {
     int64_t coo_n = 0;
     bool coo_sorted = false;
     int coo_col_shift = 0;  // > 0: entries are partitioned by column block of 2^shift columns, row-sorted inside a block
+    // "hot column" layout of the scattered-gather kernel (coo_hot_kernel): the entries are cut into segments (never
+    // across a column block); every segment has a table of its most referenced columns, whose x values the CTA that
+    // runs the segment keeps in shared memory, and coo_colh = column_index with those columns replaced by
+    // 0x80000000 | slot.  coo_col itself stays as it is (export, conversion and the cache model read it).
+    int32_t * coo_colh = nullptr;
+    int32_t * coo_hot_cols = nullptr;  // [coo_nseg][coo_hot_h] global column of every slot (unused slots: column 0)
+    int64_t * coo_seg = nullptr;       // [coo_nseg + 1] entry offsets
+    int coo_hot_h = 0, coo_nseg = 0;
+    bool coo_hot_tried = false;        // the builder ran (and may have decided against the layout)
+    double coo_hot_coverage = 0.0;     // fraction of the entries whose column is in its segment's table
 
     // optional row range for the next launches (ELL): [range_begin, range_end), range_end <= 0 = all rows
     int64_t range_begin = 0, range_end = 0;
@@ -142,6 +152,13 @@ struct spmvb200_matrix_s {
     int64_t opt_coo_ctas = 0;
     int64_t opt_coo_algo = 0;     // 0 auto, 1 shared-memory staged (coo_segmented_kernel), 2 register-staged (coo_warp_kernel)
     int64_t opt_coo_items = 0;    // stripes of 32 entries per warp of coo_warp_kernel (2, 4, 8), 0 = auto
+    int64_t opt_coo_xload = 0;    // cache path of the x gather (ptx.cuh ld_x): 0 nc, 1 cg (L2 only), 2 nc no_allocate, 3 nc evict_last
+    int64_t opt_coo_carveout = -1;     // >= 0: preferred shared-memory carve-out in percent (experiment: shrinks the L1)
+    int64_t opt_coo_hot = 0;      // hot-column kernel: 0 / -1 off (default: it measured slower), 1 on, 2 on if the gathers are scattered
+    int64_t opt_coo_hot_slots = 0;     // table size per segment (multiple of 1024, <= 27648), 0 = auto
+    int64_t opt_coo_hot_threads = 0;   // threads per CTA (512, 1024), 0 = auto
+    int64_t opt_coo_hot_entries = 0;   // entries per lane (4, 8), 0 = auto
+    int64_t opt_coo_hot_segs = 0;      // segments per CTA, 0 = auto
     int64_t opt_host_zero_copy = 1;  // spmvb200_spmv_host: let the ELL kernel read/write pinned host y directly
     int64_t opt_host_chunks = 0;  // row chunks of the pipelined spmvb200_spmv_host (ELL), 0 = 8, 1 = off
     int64_t opt_beta0 = 0;        // 1: y = A*x (y is cleared first) instead of y += A*x
@@ -267,6 +284,7 @@ int ell_from_csr(const Matrix * src, int skip_padding, bool check_int32, Matrix 
 int hyb_from_csr(const Matrix * src, int skip_padding, bool check_int32, Matrix * dst);
 int coo_from_csr(const Matrix * src, int mode, Matrix * dst);
 int coo_column_blocks(Matrix * m);
+int coo_build_hot(Matrix * m);  // builds (or decides against) the hot-column layout; idempotent
 int coo_row_major_copy(Matrix * m, int32_t * row2, int32_t * col2, double * val2);
 int csr_from_entries_host(int64_t rows, int64_t cols, int64_t n, const int32_t * i, const int32_t * j,
                           const double * a, int32_t row_alignment, Matrix * dst);

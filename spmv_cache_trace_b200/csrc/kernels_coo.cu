@@ -173,7 +173,7 @@ coo_warp_kernel(int64_t n, int independent, const int32_t * __restrict__ row, co
 // warp_segmented_add4 (segreduce.cuh): serially inside a lane, ONE segmented scan across the warp
 // per 128 entries -- a quarter of the shuffles of the striped kernel, whose l1tex/MIO pipe was 70 %
 // busy with gathers + shuffles (profiles/r01_ncu_c3_coo_warp.txt).
-template <int WARPS>
+template <int WARPS, int XPATH = 0>
 __global__ void __launch_bounds__(WARPS * 32)
 coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
                  const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y, double alpha)
@@ -189,10 +189,88 @@ coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, c
     double a[4];
     ldg_stream_d4(val + k0, a);
     if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
-    const double x0 = __ldg(x + c4.x), x1 = __ldg(x + c4.y), x2 = __ldg(x + c4.z), x3 = __ldg(x + c4.w);
+    double x0, x1, x2, x3;
+    if (XPATH == 4) {
+        // experiment: gather through cp.async (LDGSTS.BYPASS): the 16 B pair holding x[c] goes L2 -> shared memory without
+        // passing through an L1 line.  (x must be 16 B aligned.)
+        __shared__ __align__(16) double2 stage[WARPS * 128];
+        double2 * mine = stage + (threadIdx.x >> 5) * 128 + 4 * lane;
+        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(mine + j)), "l"(x + (cc[j] & ~1)) : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        x0 = (cc[0] & 1) ? mine[0].y : mine[0].x;
+        x1 = (cc[1] & 1) ? mine[1].y : mine[1].x;
+        x2 = (cc[2] & 1) ? mine[2].y : mine[2].x;
+        x3 = (cc[3] & 1) ? mine[3].y : mine[3].x;
+    } else {
+        x0 = ld_x<XPATH>(x + c4.x); x1 = ld_x<XPATH>(x + c4.y); x2 = ld_x<XPATH>(x + c4.z); x3 = ld_x<XPATH>(x + c4.w);
+    }
     const int r[4] = {k0 < n ? r4.x : -1, k0 + 1 < n ? r4.y : -1, k0 + 2 < n ? r4.z : -1, k0 + 3 < n ? r4.w : -1};
     const double p[4] = {__dmul_rn(a[0], x0), __dmul_rn(a[1], x1), __dmul_rn(a[2], x2), __dmul_rn(a[3], x3)};
     warp_segmented_add4(lane, r, p, y, alpha);
+}
+
+// Scattered gathers (power-law matrices): the hot-column kernel.  The builder (coo_build_hot, builders.cu) has cut the
+// entries into segments and given every segment a table of its H most referenced columns; colh = column_index with
+// those columns replaced by 0x80000000 | slot.  A persistent grid (CTAs = what fits the SMs with H*8 bytes of shared
+// memory each) takes the segments round-robin.  Per segment the CTA loads the x values of the table into shared memory
+// (one coalesced read of the column list, H gathers) and then runs the blocked segmented reduction of coo_warp4_kernel
+// over the segment's spans of 32*E entries, warps taking spans round-robin; a gather is an LDS for a hot column and a
+// global load otherwise.  More than half of the gathers of an R-MAT matrix are hot (24 576 slots), which removes their
+// L2 -> L1 sector traffic (32 B moved for 8 B used) and most of their L1 wavefronts -- the two pipes the plain kernel
+// saturates (profiles/r01_ncu_c3_coo_final.txt: l1tex 86 %, lts 78 %, DRAM 57 %).
+// MEASURED: slower than the plain kernel for every table size (profiles/r02_sweep_q_coo_hot_columns.log: 1.11 ms with
+// 8 192 slots ... 1.80 ms with 24 576, against 1.04 ms).  The divergent gather is bound by the misses the L1 can hold in
+// flight, and the tables take that capacity away (profiles/r02_sweep_r_coo_gather_paths.log).  Kept as an opt-in
+// ("coo.hot" = 1) because it is the documented negative result, with its tests.
+template <int THREADS, int E>
+__global__ void __launch_bounds__(THREADS, 1)
+coo_hot_kernel(int nseg, int h, const int64_t * __restrict__ seg, const int32_t * __restrict__ hot_cols,
+               const int32_t * __restrict__ row, const int32_t * __restrict__ colh, const double * __restrict__ val,
+               const double * __restrict__ x, double * __restrict__ y, double alpha)
+{
+    extern __shared__ __align__(16) double xs[];
+    constexpr int SPAN = 32 * E, WARPS = THREADS / 32;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol = policy_evict_first();
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the table is made of x values
+    for (int q = blockIdx.x; q < nseg; q += gridDim.x) {
+        const int64_t lo = seg[q], hi = seg[q + 1];
+        __syncthreads();  // everybody is done with the previous segment's table
+        const int32_t * table = hot_cols + (int64_t)q * h;
+        for (int i = threadIdx.x; i < h; i += THREADS) xs[i] = __ldg(x + __ldg(table + i));
+        __syncthreads();
+        const int64_t first = lo & ~(int64_t)(SPAN - 1);
+        for (int64_t kw = first + (int64_t)warp * SPAN; kw < hi; kw += (int64_t)WARPS * SPAN) {
+            const int64_t k0 = kw + E * lane;
+            int r[E], c[E];
+            double a[E];
+#pragma unroll
+            for (int g = 0; g < E / 4; ++g) {
+                const int4 r4 = ldg_stream_i4(row + k0 + 4 * g, pol);
+                const int4 c4 = ldg_stream_i4(colh + k0 + 4 * g, pol);
+                double a4[4];
+                ldg_stream_d4(val + k0 + 4 * g, a4);
+                r[4 * g] = r4.x; r[4 * g + 1] = r4.y; r[4 * g + 2] = r4.z; r[4 * g + 3] = r4.w;
+                c[4 * g] = c4.x; c[4 * g + 1] = c4.y; c[4 * g + 2] = c4.z; c[4 * g + 3] = c4.w;
+                a[4 * g] = a4[0]; a[4 * g + 1] = a4[1]; a[4 * g + 2] = a4[2]; a[4 * g + 3] = a4[3];
+            }
+            double p[E];
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const bool inside = k0 + j >= lo && k0 + j < hi;  // spans are aligned; a segment may start or end inside one
+                if (!inside) { r[j] = -1; c[j] = 0; }
+            }
+#pragma unroll
+            for (int j = 0; j < E; ++j) p[j] = c[j] < 0 ? xs[c[j] & 0x7fffffff] : __ldg(x + c[j]);
+#pragma unroll
+            for (int j = 0; j < E; ++j) p[j] = __dmul_rn(a[j], p[j]);
+            warp_segmented_add<E>(lane, r, p, y, alpha);
+        }
+    }
 }
 
 // Entries in file order: one fp64 reduction per entry, two entries per thread and iteration
@@ -273,7 +351,16 @@ static int launch_coo_warp4_variant(Matrix * m)
     const int64_t grid = (m->coo_n + per_cta - 1) / per_cta;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "COO matrix too large for one launch");
     const RunMode rm = run_mode(m);
-    SPMV_CUDA(launch_kernel(coo_warp4_kernel<WARPS>, (unsigned)grid, (unsigned)(WARPS * 32), 0, m->stream, rm.pdl, m->coo_n,
+    auto kernel = coo_warp4_kernel<WARPS, 0>;
+    if (WARPS == 4) {  // experiment switches: cache path of the x gather, L1 / shared-memory carve-out
+        if (m->opt_coo_xload == 1) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 1 : 0>;
+        else if (m->opt_coo_xload == 2) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 2 : 0>;
+        else if (m->opt_coo_xload == 3) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 3 : 0>;
+        else if (m->opt_coo_xload == 4) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 4 : 0>;
+        if (m->opt_coo_carveout >= 0)
+            SPMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)m->opt_coo_carveout));
+    }
+    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, (unsigned)(WARPS * 32), 0, m->stream, rm.pdl, m->coo_n,
                             rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
                             (const double *)m->coo_val, (const double *)m->x, m->y, m->alpha));
     count_launch();
@@ -304,11 +391,46 @@ static int launch_coo_warp(Matrix * m)
     return fail(SPMVB200_ERR_INVALID, "coo.threads must be 64, 128 or 256");
 }
 
+template <int THREADS, int E>
+static int launch_coo_hot_variant(Matrix * m)
+{
+    auto kernel = coo_hot_kernel<THREADS, E>;
+    const size_t smem = (size_t)m->coo_hot_h * 8;
+    SPMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // (per device, cheap)
+    int occupancy = 0;
+    SPMV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, THREADS, smem));
+    if (occupancy < 1) return fail(SPMVB200_ERR_CUDA, "coo_hot_kernel does not fit on an SM");
+    const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * occupancy, m->coo_nseg);
+    const RunMode rm = run_mode(m);
+    SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, (unsigned)THREADS, smem, m->stream, rm.pdl, m->coo_nseg, m->coo_hot_h,
+                            (const int64_t *)m->coo_seg, (const int32_t *)m->coo_hot_cols, (const int32_t *)m->coo_row,
+                            (const int32_t *)m->coo_colh, (const double *)m->coo_val, (const double *)m->x, m->y, m->alpha));
+    count_launch();
+    return 0;
+}
+
+static int launch_coo_hot(Matrix * m)
+{
+    const int threads = (int)(m->opt_coo_hot_threads ? m->opt_coo_hot_threads : 1024);
+    const int entries = (int)(m->opt_coo_hot_entries ? m->opt_coo_hot_entries : 4);
+    m->kernel_name = "coo_hot_kernel";
+    if (threads == 1024 && entries == 4) return launch_coo_hot_variant<1024, 4>(m);
+    if (threads == 1024 && entries == 8) return launch_coo_hot_variant<1024, 8>(m);
+    if (threads == 512 && entries == 4) return launch_coo_hot_variant<512, 4>(m);
+    if (threads == 512 && entries == 8) return launch_coo_hot_variant<512, 8>(m);
+    if (threads == 256 && entries == 4) return launch_coo_hot_variant<256, 4>(m);
+    if (threads == 256 && entries == 8) return launch_coo_hot_variant<256, 8>(m);
+    return fail(SPMVB200_ERR_INVALID, "coo.hot_threads must be 256, 512 or 1024 and coo.hot_entries 4 or 8");
+}
+
 int launch_coo(Matrix * m)
 {
     if (m->rows == 0) return 0;
+    if (m->coo_n > 0 && m->opt_coo_algo == 0 && m->opt_coo_hot > 0 && !m->coo_hot_tried) SPMV_TRY(coo_build_hot(m));
+    if (m->dry_run) return 0;
     SPMV_TRY(clear_y_for_beta0(m));  // every COO kernel adds partial sums
     if (m->coo_n == 0) return 0;
+    if (m->opt_coo_algo == 0 && m->coo_colh && m->opt_coo_hot > 0) return launch_coo_hot(m);
     if (m->opt_coo_algo == 1 || m->opt_coo_algo == 3 || m->opt_coo_algo == 4) SPMV_TRY(need_unit_alpha(m, "this COO kernel"));
     // coo.algo: 0 automatic, 1 shared-memory staged tiles (sorted entries only), 2 register-staged warp
     // stripes (any order), 3 one reduction per entry

@@ -137,6 +137,20 @@ __device__ __forceinline__ void ldg_stream_d4(const void * p, double (&v)[4])
     v[3] = __longlong_as_double((long long)d);
 }
 
+// Gather of one x value, by cache path (experiment switch of the COO kernels, "coo.xload"):
+//   0 read-only path, cached in L1 (ld.global.nc = __ldg)      1 L2 only (ld.global.cg: no L1 line is allocated)
+//   2 read-only path, L1::no_allocate                           3 read-only path, L1::evict_last
+template <int PATH>
+__device__ __forceinline__ double ld_x(const double * p)
+{
+    double r;
+    if (PATH == 1) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    else if (PATH == 2) asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    else if (PATH == 3) asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    else r = __ldg(p);
+    return r;
+}
+
 // fp64 reduction into global memory without a return value (RED.E.ADD.F64).
 __device__ __forceinline__ void red_add_f64(double * p, double v)
 {

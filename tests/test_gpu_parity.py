@@ -1105,6 +1105,72 @@ def test_csr_spmv_host_zero_copy_for_the_sliced_kernel(oracle):
     assert np.array_equal(yb.array, oracle.csr_spmv(O, x))
 
 
+@pytest.mark.parametrize("threads,entries,slots", [(1024, 4, 1024), (512, 8, 2048), (256, 4, 1024), (1024, 8, 24576)])
+def test_hot_column_coo_kernel(oracle, threads, entries, slots):
+    """coo_hot_kernel: the segments' most referenced columns are gathered from shared memory, everything else from
+    global memory.  Forced here on small matrices (automatic only from 2^22 scattered entries on), with few slots and
+    many segments so that segment edges fall inside spans, with and without the column-blocked order, as COO and as
+    the tail of a hybrid matrix, with alpha and beta0."""
+    scale, ef, seed = 14, 16, 0x5EED0003
+    n = 1 << scale
+    r, c, v = rmat_entries(scale, ef, seed)
+    O = oracle.csr(n, n, r + 1, c + 1, v)
+    rng = np.random.default_rng(41)
+    x = rng.uniform(-1, 1, n)
+    yref, bound = oracle.csr_spmv(O, x), oracle.csr_abs_rowsum(O, x)
+    mm = matrix_market.from_entries(n, n, r + 1, c + 1, v)
+
+    def force(A):
+        for k, val in (("coo.hot", 1), ("coo.hot_slots", slots), ("coo.hot_threads", threads), ("coo.hot_entries", entries),
+                       ("coo.hot_segments", 3)):
+            A.set_option(k, val)
+        return A
+
+    for blocks in (-1, 10):  # never / forced blocks of 2^10 columns (16 of them)
+        sp.set_global_option("coo.col_block_log2", blocks)
+        try:
+            C = force(coo_matrix.from_matrix_market(mm, COO_SEGMENTED))
+            H = force(hybrid_matrix.from_matrix_market(mm))
+        finally:
+            sp.set_global_option("coo.col_block_log2", 0)
+        assert (C.get_option("coo.col_block_log2") > 0) == (blocks > 0)
+        y = C * x
+        assert C.kernel_name == "coo_hot_kernel"
+        assert 0 < C.get_option("coo.hot_coverage_permille") <= 1000 and C.get_option("coo.hot_segments_built") >= 3
+        assert_within(y, yref, bound, f"hot COO, blocks {blocks}")
+        e = C.export()  # the remapped columns live beside the real ones: exports are untouched
+        order = np.lexsort((c, r))
+        assert np.array_equal(e["row_index"], r[order]) and np.array_equal(e["column_index"], c[order])
+        C.set_alpha(0.5)
+        C.set_option("beta0", 1)
+        C.set_y(np.full(n, 1e30))
+        C.spmv()
+        assert_within(C.get_y(), 0.5 * yref, 0.5 * bound, "hot COO, alpha + beta0")
+        yh = H * x
+        assert H.kernel_name == "ell_kernel+coo_hot_kernel"
+        assert_within(yh, yref, bound, f"hot hybrid tail, blocks {blocks}")
+        C.set_alpha(1.0)
+        C.set_option("beta0", 0)
+        C.set_option("coo.hot", -1)  # and back to the plain kernel on the same matrix
+        assert_within(C * x, yref, bound, "plain kernel after hot")
+        assert C.kernel_name == "coo_warp4_kernel"
+    # "coo.hot" = 2 applies the layout only where the gathers are scattered: a banded matrix is left alone
+    S = sp.generators.stencil(sp.STENCIL_3D7, 128, 128, 128, fmt=sp.COO)
+    S.set_option("coo.hot", 2)
+    S.prepare()
+    assert S.get_option("coo.hot_segments_built") == 0
+    S.spmv()
+    assert S.kernel_name == "coo_warp4_kernel"
+    R = sp.generators.rmat(18, 16, 0x5EED0003, fmt=sp.COO)
+    R.set_option("coo.hot", 2)
+    R.prepare()
+    assert R.get_option("coo.hot_segments_built") > 0 and R.get_option("coo.hot_coverage_permille") > 150
+    # the default never builds it (it measured slower, DESIGN.md)
+    R = sp.generators.rmat(18, 16, 0x5EED0003, fmt=sp.COO)
+    R.spmv()
+    assert R.kernel_name == "coo_warp4_kernel" and R.get_option("coo.hot_segments_built") == 0
+
+
 def test_kernels_really_launch():
     before = sp.launch_count()
     A = sp.generators.stencil(sp.STENCIL_2D5, 64, 64, 1)
