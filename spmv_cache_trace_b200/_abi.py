@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspmvb200.so")
+LIB_PATH = os.environ.get("SPMVB200_LIB") or os.path.join(HERE, "lib", "libspmvb200.so")  # SPMVB200_LIB: an experiment build
 
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)

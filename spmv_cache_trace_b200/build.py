@@ -15,9 +15,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+# SPMVB200_VARIANT=name builds an experiment variant next to the product (objects in build_<name>/, library
+# lib/libspmvb200_<name>.so, flags from SPMVB200_CFLAGS); the Python layer loads it when SPMVB200_LIB names it.
+VARIANT = os.environ.get("SPMVB200_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libspmvb200.so")
+LIB = os.path.join(LIBDIR, "libspmvb200" + ("_" + VARIANT if VARIANT else "") + ".so")
 CLI = os.path.join(HERE, "bin", "spmv-b200")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
@@ -90,7 +93,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     plugin = os.path.join(CSRC, "plugin")
     srcs = [os.path.join(plugin, f) for f in ("main.cpp", "cuda_spmv_kernels.cpp")]
     deps = srcs + [os.path.join(plugin, f) for f in ("kernel.hpp", "cuda_spmv_kernels.hpp")] + [LIB]
-    if force or not _newer(CLI, deps):
+    if not VARIANT and (force or not _newer(CLI, deps)):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
         _run([cxx, "-O2", "-std=c++17", "-fopenmp", "-Wall", "-I", INCLUDE, "-o", CLI] + srcs +
              ["-L", LIBDIR, "-lspmvb200", "-Wl,-rpath,$ORIGIN/../lib"], verbose)

@@ -301,7 +301,7 @@ void plan_run(Matrix * m, bool conservative)
     // running.  A launch whose x may have been written by a kernel in flight (an iteration x_{k+1} = A x_k with
     // the buffers swapped by bind_x / bind_y; or anything the record cannot vouch for) is therefore issued without
     // the PDL attribute: ordinary stream serialisation, the whole predecessor retired before the first CTA starts.
-    if (!r.valid || overlaps(x0, x1, r.wlo, r.whi)) m->run_pdl = false;
+    if ((!r.valid || overlaps(x0, x1, r.wlo, r.whi)) && m->opt_pdl != 2) m->run_pdl = false;  // ("pdl" = 2: experiments)
     if (!conservative && m->run_pdl && !m->opt_beta0 && !m->run_beta0 &&
         (m->opt_independent > 0 || (m->opt_independent == 0 && proven))) {
         m->run_independent = true;  // validity of the record is unchanged; its ranges grow

@@ -80,7 +80,7 @@ coo_segmented_kernel(int64_t n, int64_t chunk, int independent, const int32_t * 
             for (int u = 0; u < ITEMS; ++u) {
                 const int k = tid + u * T;
                 a[u] = k < cnt ? pv[k] : 0.0;
-                xv[u] = k < cnt ? __ldg(x + pc[k]) : 0.0;
+                xv[u] = k < cnt ? ldx(x + pc[k]) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < ITEMS; ++u)
@@ -145,7 +145,7 @@ coo_warp_kernel(int64_t n, int independent, const int32_t * __restrict__ row, co
     if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
     double v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = __ldg(x + c[u]);
+    for (int u = 0; u < U; ++u) v[u] = ldx(x + c[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int rr = (k0 + 32 * u < n) ? r[u] : -1;
@@ -241,7 +241,7 @@ coo_hot_kernel(int nseg, int h, const int64_t * __restrict__ seg, const int32_t 
         const int64_t lo = seg[q], hi = seg[q + 1];
         __syncthreads();  // everybody is done with the previous segment's table
         const int32_t * table = hot_cols + (int64_t)q * h;
-        for (int i = threadIdx.x; i < h; i += THREADS) xs[i] = __ldg(x + __ldg(table + i));
+        for (int i = threadIdx.x; i < h; i += THREADS) xs[i] = ldx(x + __ldg(table + i));
         __syncthreads();
         const int64_t first = lo & ~(int64_t)(SPAN - 1);
         for (int64_t kw = first + (int64_t)warp * SPAN; kw < hi; kw += (int64_t)WARPS * SPAN) {
@@ -265,7 +265,7 @@ coo_hot_kernel(int nseg, int h, const int64_t * __restrict__ seg, const int32_t 
                 if (!inside) { r[j] = -1; c[j] = 0; }
             }
 #pragma unroll
-            for (int j = 0; j < E; ++j) p[j] = c[j] < 0 ? xs[c[j] & 0x7fffffff] : __ldg(x + c[j]);
+            for (int j = 0; j < E; ++j) p[j] = c[j] < 0 ? xs[c[j] & 0x7fffffff] : ldx(x + c[j]);
 #pragma unroll
             for (int j = 0; j < E; ++j) p[j] = __dmul_rn(a[j], p[j]);
             warp_segmented_add<E>(lane, r, p, y, alpha);
@@ -287,8 +287,8 @@ coo_atomic_kernel(int64_t n, int independent, const int32_t * __restrict__ row, 
         const int2 r = ldg_stream_i2(row + k, pol);
         const int2 c = ldg_stream_i2(col + k, pol);
         const double2 a = ldg_stream_d2(val + k, pol);
-        red_add_f64(y + r.x, __dmul_rn(a.x, __ldg(x + c.x)));
-        if (k + 1 < n) red_add_f64(y + r.y, __dmul_rn(a.y, __ldg(x + c.y)));
+        red_add_f64(y + r.x, __dmul_rn(a.x, ldx(x + c.x)));
+        if (k + 1 < n) red_add_f64(y + r.y, __dmul_rn(a.y, ldx(x + c.y)));
     }
 }
 

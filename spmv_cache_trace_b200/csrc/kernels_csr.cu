@@ -181,7 +181,7 @@ csr_stream_kernel(int64_t stored, int64_t chunk, int tpc, int independent, const
             for (int u = 0; u < PER; ++u) {
                 const int k = tid + u * T;
                 a[u] = k < n ? pv[k] : 0.0;
-                xv[u] = k < n ? __ldg(x + pc[k]) : 0.0;
+                xv[u] = k < n ? ldx(x + pc[k]) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < PER; ++u)
@@ -219,7 +219,7 @@ csr_stream_kernel(int64_t stored, int64_t chunk, int tpc, int independent, const
                         const int k = kb + g + u * LANES;
                         const bool ok = k < bn;
                         v[u] = ok ? pv[k] : 0.0;
-                        xv[u] = ok ? __ldg(x + pc[k]) : 0.0;
+                        xv[u] = ok ? ldx(x + pc[k]) : 0.0;
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
@@ -247,7 +247,7 @@ csr_stream_kernel(int64_t stored, int64_t chunk, int tpc, int independent, const
                 const int lr = __shfl_sync(0xffffffffu, r, src);
                 double ls = 0.0;
                 if (G > 0) {
-                    for (int k = la + lane; k < lb; k += 32) ls = __dadd_rn(ls, __dmul_rn(pv[k], __ldg(x + pc[k])));
+                    for (int k = la + lane; k < lb; k += 32) ls = __dadd_rn(ls, __dmul_rn(pv[k], ldx(x + pc[k])));
                 } else {
                     for (int k = la + lane; k < lb; k += 32) ls = __dadd_rn(ls, pv[k]);
                 }

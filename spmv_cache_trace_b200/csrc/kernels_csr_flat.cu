@@ -259,7 +259,7 @@ csr_flat_kernel(int64_t rows, int64_t stored, int64_t nspans, int independent, c
     if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
     double p[E];
 #pragma unroll
-    for (int j = 0; j < E; ++j) p[j] = PROBE != 1 ? __ldg(x + c[j]) : 1.0;
+    for (int j = 0; j < E; ++j) p[j] = PROBE != 1 ? ldx(x + c[j]) : 1.0;
 #pragma unroll
     for (int j = 0; j < E; ++j) p[j] = __dmul_rn(a[j], p[j]);
     warp_segmented_add<E>(lane, r, p, y, alpha, MASK ? rowmap : nullptr);

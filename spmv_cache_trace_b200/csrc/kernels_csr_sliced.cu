@@ -138,7 +138,7 @@ csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const 
         }
         double xv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = len > l0 + u ? __ldg(x + c[u]) : 0.0;
+        for (int u = 0; u < U; ++u) xv[u] = len > l0 + u ? ldx(x + c[u]) : 0.0;
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (len > l0 + u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));

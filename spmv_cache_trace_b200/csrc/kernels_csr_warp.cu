@@ -130,7 +130,7 @@ csr_warp_kernel(int64_t stored, int64_t nspans, int independent, const OffT * __
                 const int k = kb + g + u * G;
                 const bool ok = k < bn;
                 pvv[u] = ok ? pv[k] : 0.0;
-                xv[u] = ok ? __ldg(x + pc[k]) : 0.0;
+                xv[u] = ok ? ldx(x + pc[k]) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -148,7 +148,7 @@ csr_warp_kernel(int64_t stored, int64_t nspans, int independent, const OffT * __
             const int lb = __shfl_sync(0xffffffffu, b, src);
             const int lr = __shfl_sync(0xffffffffu, r, src);
             double ls = 0.0;
-            for (int k = la + lane; k < lb; k += 32) ls = __dadd_rn(ls, __dmul_rn(pv[k], __ldg(x + pc[k])));
+            for (int k = la + lane; k < lb; k += 32) ls = __dadd_rn(ls, __dmul_rn(pv[k], ldx(x + pc[k])));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
             if (lane == 0) red_add_f64(y + lr, ls);

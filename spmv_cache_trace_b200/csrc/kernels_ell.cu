@@ -102,7 +102,7 @@ ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int indepen
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (SKIP) live[r] = live[r] && (c[l][r] != INT_MAX);
-                xv[l][r] = (!SKIP || live[r]) ? __ldg(x + c[l][r]) : 0.0;
+                xv[l][r] = (!SKIP || live[r]) ? ldx(x + c[l][r]) : 0.0;
             }
 #pragma unroll
         for (int l = 0; l < W_STATIC; ++l)
@@ -120,7 +120,7 @@ ell_kernel(int64_t row0, int64_t rows, int64_t pitch, int w_runtime, int indepen
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (SKIP) live[r] = live[r] && (c[r] != INT_MAX);
-                if (!SKIP || live[r]) z[r] = __dadd_rn(z[r], __dmul_rn(a[r], __ldg(x + c[r])));
+                if (!SKIP || live[r]) z[r] = __dadd_rn(z[r], __dmul_rn(a[r], ldx(x + c[r])));
             }
         }
     }

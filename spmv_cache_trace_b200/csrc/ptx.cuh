@@ -137,6 +137,22 @@ __device__ __forceinline__ void ldg_stream_d4(const void * p, double (&v)[4])
     v[3] = __longlong_as_double((long long)d);
 }
 
+// Gather of one x value: the read-only path (ld.global.nc, cached in L1).  PTX defines .nc only for data that nothing
+// writes while the kernel runs, which under programmatic dependent launch includes the tail of the PREDECESSOR: the
+// library therefore never launches with the PDL attribute when x may have been written by a kernel in flight
+// (plan_run, abi.cu).  -DSPMVB200_X_COHERENT (experiment build, tools/pdl_probe.py) makes every gather an ordinary
+// coherent load instead, to tell the two explanations of a wrong result under PDL apart.
+__device__ __forceinline__ double ldx(const double * p)
+{
+#ifdef SPMVB200_X_COHERENT
+    double r;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+
 // Gather of one x value, by cache path (experiment switch of the COO kernels, "coo.xload"):
 //   0 read-only path, cached in L1 (ld.global.nc = __ldg)      1 L2 only (ld.global.cg: no L1 line is allocated)
 //   2 read-only path, L1::no_allocate                           3 read-only path, L1::evict_last
