@@ -69,3 +69,42 @@ def test_committed_gpu_lines_carry_the_contract(name):
         assert {f["workload"] for f in line["formats"]} >= {"c1_csr", "c1_ell", "c1_coo", "c1_hyb", "c3_coo", "c4_hyb", "c5_csr"}
     else:
         assert line["scaling"] == "strong" and line["single_gpu"]["speedup"] > 1.0
+
+
+@pytest.mark.parametrize("name", ["r02_bench_n1.json", "r02_bench_n2.json", "r02_bench_n4.json", "r02_bench_n8.json"])
+def test_round2_gpu_lines_are_one_workload_with_parity(name):
+    """Round 2: every GPU count runs BASELINE config 5 (so the driver's 1 -> 8 curve is one workload), every line was
+    preceded by a parity check in the same run, and the multi-GPU lines come from the executor below the C ABI."""
+    line = last_json_line(open(os.path.join(ROOT, "profiles", name)).read())
+    assert BASE_KEYS <= set(line), sorted(BASE_KEYS - set(line))
+    assert line["metric"] == "spmv_effective_bandwidth" and line["unit"] == "GB/s" and line["dtype"] == "f64"
+    assert line["config"]["workload"] == "c5_csr" and line["config"]["algorithmic_bytes"] == 46001250212
+    assert line["scaling"] == "strong" and line["vs_baseline"] is None and "model" not in line["config"]
+    p = line["parity"]
+    assert p["ok"] is True and p["bad_rows"] == 0 and p["rows_checked"] >= 1_000_000
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.5 < r["frac"] < 1.2
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < line["value"]
+    assert line["gpu_launches"] > 0
+    c = line["clocks"]
+    assert c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    n = line["n_gpus"]
+    if n == 1:
+        cb = line["cpu_baseline"]
+        assert cb["kind"] in ("reference", "port") and "SLAB" in cb["sample"]
+        t = line["targets"]
+        for k in ("c1_csr", "c1_ell"):
+            assert t[k]["frac_of_8TBs_pipelined"] >= 0.70  # BASELINE's target, sustained
+            assert t[k]["xy_bytes_in_cycle"] >= 2 * 126e6  # x + y of the rotating copies exceed twice the L2
+            assert t[k]["us_isolated"] > t[k]["us_pipelined"]
+        assert {f["workload"] for f in line["formats"]} >= {"c1_coo", "c1_hyb", "c2_ell", "c2_csr", "c3_coo", "c4_hyb"}
+    else:
+        assert "spmvb200_dist" in line["config"]["executor"]
+        assert line["single_gpu"]["speedup"] > 0.9 * n  # halo plan: 1.98x / 3.95x / 7.83x
+        v = line["exchange_variants"]
+        assert v["halo"]["parity"]["ok"] and v["allgather"]["parity"]["ok"] and v["halo"]["parity"]["ranks"] == n
+        assert v["halo"]["recv_bytes_per_step_per_rank"] in (2 * 512 * 512 * 8, 512 * 512 * 8)
+        if n == 2:
+            h = line["c4_hyb"]
+            assert h["parity"]["ok"] and h["single_gpu"]["speedup"] > 1.5 and h["nonzeros"] == 2103842462
