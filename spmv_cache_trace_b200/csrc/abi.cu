@@ -50,6 +50,7 @@ int gen_stencil(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin,
 int gen_rmat(int scale, int edge_factor, uint64_t seed, double a, double b, double c, int64_t row_begin,
              int64_t row_end, Matrix * csr);
 int launch_csr_sliced(Matrix * m);  // kernels_csr_sliced.cu
+int csr_chunk_colmax(Matrix * m, int64_t rows_per_chunk, int chunks, int * host_out);
 
 __global__ void transpose_to_colmajor_kernel(int64_t rows, int64_t W, int64_t pitch, const int32_t * col_rm,
                                              const double * val_rm, int32_t * ecol, double * eval)
@@ -1086,6 +1087,64 @@ static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chu
     return 0;
 }
 
+// Host-buffer form for the sliced CSR kernel (a lane owns its row, so y is read from and written to pinned host memory by
+// the kernel itself).  What is left to overlap is the upload of x: it goes up in `chunks` pieces, and the rows are run in
+// as many chunks, each launched as soon as the largest column its rows reference has arrived.  For a banded matrix
+// (stencils) chunk c needs x up to piece c + 1, so the kernel starts after 2/chunks of the upload instead of all of it
+// and the whole call costs max(x + y_old up, y_new down) over PCIe; a matrix whose rows reference every column degenerates
+// to upload-then-run.
+static int spmv_host_csr_pipelined(Matrix * m, const double * x, double * y_dev_visible, int chunks)
+{
+    cudaStream_t s = m->stream;
+    if (!m->upload_stream) {
+        SPMV_CUDA(cudaStreamCreateWithFlags(&m->upload_stream, cudaStreamNonBlocking));
+        SPMV_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
+    }
+    for (int c = 0; c < chunks; c++)
+        if (!m->ev_chunk[c]) SPMV_CUDA(cudaEventCreateWithFlags(&m->ev_chunk[c], cudaEventDisableTiming));
+    const int64_t per = round_up((m->rows + chunks - 1) / chunks, 1024);
+    if (m->host_chunks != chunks || m->host_rows_per_chunk != per) {
+        SPMV_TRY(csr_chunk_colmax(m, per, chunks, m->host_colmax));
+        m->host_chunks = chunks;
+        m->host_rows_per_chunk = per;
+    }
+    cudaStream_t up = m->upload_stream;
+    SPMV_CUDA(cudaEventRecord(m->ev_x, s));  // kernels queued earlier may still gather from m->x
+    SPMV_CUDA(cudaStreamWaitEvent(up, m->ev_x, 0));
+    for (int c = 0; c < chunks; c++) {  // x pieces on the same grid as the row chunks (the matrix is square)
+        const int64_t b = (int64_t)c * per, e = std::min<int64_t>(m->cols, b + per);
+        if (e > b) SPMV_CUDA(cudaMemcpyAsync(m->x + b, x + b, sizeof(double) * (size_t)(e - b), cudaMemcpyHostToDevice, up));
+        SPMV_CUDA(cudaEventRecord(m->ev_chunk[c], up));
+    }
+    const int64_t keep = m->opt_beta0;
+    m->host_y_in = keep ? nullptr : (const double *)y_dev_visible;
+    m->host_y_out = y_dev_visible;
+    m->opt_beta0 = 0;
+    int rc = 0, waited = -1;
+    for (int c = 0; c < chunks && rc == 0; c++) {
+        const int64_t b = (int64_t)c * per, e = std::min<int64_t>(m->rows, b + per);
+        if (b >= e) break;
+        const int need = m->host_colmax[c] < 0 ? -1 : (int)std::min<int64_t>(chunks - 1, m->host_colmax[c] / per);
+        if (need > waited) {
+            if (cudaStreamWaitEvent(s, m->ev_chunk[need], 0) != cudaSuccess) { rc = fail(SPMVB200_ERR_CUDA, "cudaStreamWaitEvent"); break; }
+            waited = need;
+        }
+        m->range_begin = b;
+        m->range_end = e;
+        plan_run(m, true);
+        rc = launch_csr_sliced(m);
+    }
+    m->range_begin = m->range_end = 0;
+    m->opt_beta0 = keep;
+    m->host_y_in = nullptr;
+    m->host_y_out = nullptr;
+    if (rc) return rc;
+    SPMV_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[chunks - 1], 0));  // the call owns x until every piece has landed
+    SPMV_CUDA(cudaStreamSynchronize(s));
+    stream_synced(s);
+    return 0;
+}
+
 int spmvb200_spmv_host(spmvb200_matrix_t m, const double * x, double * y)
 try {
     SPMV_TRY(check(m));
@@ -1127,6 +1186,9 @@ try {
             if (rc) return rc;
         }
         if (m->slice_col && cudaPointerGetAttributes(&ay, y) == cudaSuccess && ay.type == cudaMemoryTypeHost && ay.devicePointer) {
+            const int chunks = (int)(m->opt_host_chunks ? std::min<int64_t>(m->opt_host_chunks, 64) : 16);
+            if (chunks > 1 && m->rows >= (int64_t)chunks * 65536 && m->rows == m->cols)
+                return spmv_host_csr_pipelined(m, x, (double *)ay.devicePointer, chunks);
             SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
             m->host_y_in = m->opt_beta0 ? nullptr : (const double *)ay.devicePointer;
             m->host_y_out = (double *)ay.devicePointer;

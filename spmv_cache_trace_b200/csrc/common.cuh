@@ -111,13 +111,17 @@ struct spmvb200_matrix_s {
     bool coo_hot_tried = false;        // the builder ran (and may have decided against the layout)
     double coo_hot_coverage = 0.0;     // fraction of the entries whose column is in its segment's table
 
-    // optional row range for the next launches (ELL): [range_begin, range_end), range_end <= 0 = all rows
+    // pipelined host-buffer path of the sliced CSR kernel: largest column referenced by each of host_chunks row chunks
+    int host_chunks = 0;
+    int64_t host_rows_per_chunk = 0;
+    int host_colmax[64] = {};
+    // optional row range for the next launches (ELL, sliced CSR): [range_begin, range_end), range_end <= 0 = all rows
     int64_t range_begin = 0, range_end = 0;
     const double * host_y_in = nullptr;    // zero-copy host-buffer path (ELL): device-visible host pointers
     double * host_y_out = nullptr;
     cudaStream_t upload_stream = nullptr;  // second stream of the pipelined host-buffer path
     cudaEvent_t ev_x = nullptr;
-    cudaEvent_t ev_chunk[16] = {};
+    cudaEvent_t ev_chunk[64] = {};
 
     // vectors
     double * x = nullptr;

@@ -101,13 +101,14 @@ int csr_ensure_row_major(Matrix * m)
 
 template <typename OffT, int U, int THREADS>
 __global__ void __launch_bounds__(THREADS, (U <= 4 ? 2048 : 1024) / THREADS)
-csr_sliced_kernel(int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
+csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
                   const int32_t * __restrict__ scol, const double * __restrict__ sval, const double * __restrict__ x,
                   double * __restrict__ y, const double * __restrict__ y_in_host, double * __restrict__ y_out_host)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // rows [row0, rows) of the matrix (row0 a multiple of 32: a warp is a slice)
+    const int64_t i = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i - lane >= rows) return;  // whole warp past the end
     const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
     const int len = (int)min(hi - lo, (int64_t)INT_MAX);
@@ -191,20 +192,56 @@ static int csr_build_sliced(Matrix * m)
     return csr_drop_row_major(m);
 }
 
+// Largest column referenced by each of `chunks` equal row chunks (chunk = rows_per_chunk rows, a multiple of 32), from the
+// slot-major copy: a slice's entries are contiguous, [rp[32 s], rp[32 s + 32)).  One warp per slice.
+template <typename OffT>
+__global__ void csr_chunk_colmax_kernel(int64_t rows, int64_t rows_per_chunk, const OffT * __restrict__ rp,
+                                        const int32_t * __restrict__ scol, int * __restrict__ colmax)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t r0 = slice * 32;
+    if (r0 >= rows) return;
+    const int64_t lo = (int64_t)rp[r0], hi = (int64_t)rp[min(r0 + 32, rows)];
+    int best = -1;
+    for (int64_t k = lo + lane; k < hi; k += 32) best = max(best, __ldg(scol + k));
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0 && best >= 0) atomicMax(colmax + r0 / rows_per_chunk, best);
+}
+
+int csr_chunk_colmax(Matrix * m, int64_t rows_per_chunk, int chunks, int * host_out)
+{
+    Scratch<int> d;
+    SPMV_TRY(d.alloc(chunks));
+    SPMV_CUDA(cudaMemsetAsync(d.p, 0xff, sizeof(int) * (size_t)chunks, m->stream));
+    const int64_t warps = (m->rows + 31) / 32;
+    const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+    if (m->off64) csr_chunk_colmax_kernel<int64_t><<<grid, 256, 0, m->stream>>>(m->rows, rows_per_chunk, (const int64_t *)m->rp, m->slice_col, d.p);
+    else csr_chunk_colmax_kernel<uint32_t><<<grid, 256, 0, m->stream>>>(m->rows, rows_per_chunk, (const uint32_t *)m->rp, m->slice_col, d.p);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(cudaMemcpyAsync(host_out, d.p, sizeof(int) * (size_t)chunks, cudaMemcpyDeviceToHost, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
 int launch_csr_sliced(Matrix * m)
 {
     SPMV_TRY(csr_build_sliced(m));
     m->kernel_name = "csr_sliced_kernel";
     if (m->dry_run) return 0;
     const int threads = (int)(m->opt_csr_threads ? m->opt_csr_threads : 128);
-    const int64_t grid = (m->rows + threads - 1) / threads;
+    // optional row range (the pipelined host-buffer path runs the matrix in row chunks)
+    const int64_t row0 = m->range_end > 0 ? m->range_begin : 0;
+    const int64_t row1 = m->range_end > 0 ? m->range_end : m->rows;
+    const int64_t grid = (row1 - row0 + threads - 1) / threads;
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
+    if (grid <= 0) return 0;
     const RunMode rm = run_mode(m);
     const int store = (m->run_beta0 && !m->host_y_out) ? 1 : 0;
     m->run_beta0 = false;
     const int batch = (int)(m->opt_csr_batch ? m->opt_csr_batch : 4);
 #define SPMV_SLICED(OFF, UU, TT)                                                                                          \
-    SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, m->rows,  \
+    SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, row0, row1,  \
                             rm.independent, store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col,          \
                             (const double *)m->slice_val, (const double *)m->x, m->y, (const double *)m->host_y_in,      \
                             m->host_y_out))

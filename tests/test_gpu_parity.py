@@ -1171,6 +1171,50 @@ def test_hot_column_coo_kernel(oracle, threads, entries, slots):
     assert R.kernel_name == "coo_warp4_kernel" and R.get_option("coo.hot_segments_built") == 0
 
 
+def test_csr_spmv_host_pipelined_upload(oracle):
+    """From 2^20 rows on, the host-buffer call of the sliced CSR kernel uploads x in pieces and launches each row chunk as
+    soon as the largest column it references has arrived.  A banded matrix starts after two pieces; a matrix whose first
+    rows reference the last columns must wait for the whole vector -- both must give the reference's numbers."""
+    n = 104
+    N = n ** 3
+    i, j, a = stencil_entries(2, n, n, n)
+    O = oracle.csr(N, N, i, j, a)
+    x = 1.0 + (np.arange(N) % 7) / 8.0  # exact data
+    y0 = (np.arange(N) % 5) / 4.0
+    ref = oracle.csr_spmv(O, x, y0)
+    A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+    xb, yb = sp.PinnedBuffer(N), sp.PinnedBuffer(N)
+    for chunks in (16, 5, 1):
+        A.set_option("host.chunks", chunks)
+        xb.array[:] = x
+        yb.array[:] = y0
+        before = sp.launch_count()
+        A.spmv_host(xb.array, yb.array)
+        assert sp.launch_count() - before == (chunks if chunks > 1 else 1) and A.kernel_name == "csr_sliced_kernel"
+        assert np.array_equal(yb.array, ref), f"{chunks} chunks"
+        A.spmv()  # an asynchronous launch in flight when the next host call starts uploading
+    # wrap-around columns: row r references (r + 97 k) mod N, k = 0..11, so the last rows reference the first columns
+    # and the first chunk's largest column lies in the last piece only for the LAST rows -- the spans must be per chunk
+    N2 = 16 * 65536 + 4096
+    k = np.arange(12, dtype=np.int64)
+    rows = np.repeat(np.arange(N2, dtype=np.int64), 12)
+    cols = (rows + np.tile(97 * 9001 * k, N2)) % N2
+    vals = 1.0 + (np.arange(rows.size) % 3) / 2.0
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    rp = np.arange(N2 + 1, dtype=np.int64) * 12
+    B = sp.csr_matrix.Matrix(N2, N2, rows.size, 1, rp, cols.astype(np.int32), vals)
+    x2 = 1.0 + (np.arange(N2) % 9) / 8.0
+    want = np.add.reduceat(vals * x2[cols], rp[:-1])  # exact data: any order
+    xb2, yb2 = sp.PinnedBuffer(N2), sp.PinnedBuffer(N2)
+    xb2.array[:] = x2
+    yb2.array[:] = 0.0
+    before = sp.launch_count()
+    B.spmv_host(xb2.array, yb2.array)
+    assert B.kernel_name == "csr_sliced_kernel" and sp.launch_count() - before == 16
+    assert np.array_equal(yb2.array, want)
+
+
 def test_kernels_really_launch():
     before = sp.launch_count()
     A = sp.generators.stencil(sp.STENCIL_2D5, 64, 64, 1)
