@@ -600,12 +600,15 @@ def measure_c5_partitioned(args, sp, D, comm, rank, world, sampler):
     # x_(k+1) = A x_k / 52: every eigenvalue of the 27-point operator (26 on the diagonal, -1 off it) lies within 52 of
     # zero, so the iterates stay finite however many steps are timed.
     SCALE = 1.0 / 52.0
-    modes = [args.exchange] if getattr(args, "exchange", None) else ["allgather", "halo"]
+    plans = [args.exchange] if getattr(args, "exchange", None) else ["allgather", "halo"]
+    # every plan with both transports: NCCL kernels, and copy-engine pulls out of the owners' IPC-mapped buffers ("_peer")
+    transports = [False, True] if world > 1 and os.environ.get("SPMV_PEER_COPY", "1") != "0" else [False]
     results, marks = {}, {}
-    for mode in modes:
+    for mode, peer in [(m, t) for m in plans for t in transports]:
+        label = mode + ("_peer" if peer else "")
         # every rank generates only its own rows of the 27-point operator, on its own GPU
         local = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR, row_begin=s, row_end=e)
-        eng = D.DistributedSpMV(comm, local, starts, mode=mode, consume_local=True)
+        eng = D.DistributedSpMV(comm, local, starts, mode=mode, consume_local=True, peer_copy=peer)
         # parity before timing: one step from x_j = 1 + (j mod 7)/8, alpha = 1, every rank checks its rows exactly
         eng.set_x(x_pattern(np.arange(s, e)))
         eng.step(1.0)
@@ -616,28 +619,30 @@ def measure_c5_partitioned(args, sp, D, comm, rank, world, sampler):
         par["ok"] = par["bad_rows"] == 0
         par["ranks"] = world
         if not par["ok"]:
-            results[mode] = {"parity": par}
+            results[label] = {"parity": par}
+            eng.destroy()
             continue
         eng.set_x(np.random.default_rng(1234 + rank).random(e - s) - 0.5)
         launches0 = sp.launch_count()
-        marks[mode] = [time.perf_counter(), None]
+        marks[label] = [time.perf_counter(), None]
         ms = eng.time(args.steps, max(args.warmup, 3), SCALE)
-        marks[mode][1] = time.perf_counter()
+        marks[label][1] = time.perf_counter()
         ms = comm.allreduce(ms, "max")  # device time, max over ranks
         t = ms * 1e-3 / args.steps
         inf = eng.info
         xnorm = math.sqrt(comm.allreduce(float(np.sum(eng.get_x() ** 2)), "sum"))
-        results[mode] = {"ms_per_step": t * 1e3, "gbs": B / t / 1e9, "gflops": 2.0 * nnz / t / 1e9,
+        results[label] = {"ms_per_step": t * 1e3, "gbs": B / t / 1e9, "gflops": 2.0 * nnz / t / 1e9,
                          "recv_bytes_per_step_per_rank": inf["recv_bytes_per_step"], "plan": inf["exchange"],
+                         "transport": "copy-engine pulls from IPC-mapped peer buffers" if peer else "NCCL",
                          "row_blocks": eng.blocks(), "interior_rows": inf["interior_rows"],
                          "gpu_launches": int(sp.launch_count() - launches0), "launches_per_step": inf["launches_per_step"],
                          "resident_bytes_rank0": inf["device_bytes"], "x_norm": xnorm, "parity": par,
                          "kernel": max(eng.blocks(), key=lambda b: b[1] - b[0])[3]}
         e2e_steps = max(4, min(args.steps, 10))
         e2e_ms, ymax = _e2e_host(sp, eng, e - s, e2e_steps, SCALE)
-        results[mode]["e2e_ms_per_step"] = comm.allreduce(e2e_ms, "max")
-        results[mode]["e2e_steps"] = e2e_steps
-        results[mode]["e2e_max_abs_y"] = ymax
+        results[label]["e2e_ms_per_step"] = comm.allreduce(e2e_ms, "max")
+        results[label]["e2e_steps"] = e2e_steps
+        results[label]["e2e_max_abs_y"] = ymax
         eng.destroy()
         del eng, local
     return {"results": results, "marks": marks, "B": B, "N": N, "nnz": nnz, "grid": n, "scale": SCALE}
@@ -673,8 +678,9 @@ def measure_c4_partitioned(args, sp, D, comm, rank, world):
     B = sum(p[0] for p in per_rank) + 16 * N
     ALPHA = 1.0 / 8192.0  # keeps x_(k+1) = alpha A x_k finite: hub rows of the R-MAT matrix sum ~10^6 entries
     split = os.environ.get("SPMV_COLUMN_SPLIT", "1") != "0" and world > 1
+    peer = world > 1 and os.environ.get("SPMV_PEER_COPY", "1") != "0" and os.environ.get("SPMV_C4_PEER", "1") != "0"
     eng = D.DistributedSpMV(comm, block, starts, mode="allgather", fmt=sp.HYB, column_split=split, overlap=False,
-                            consume_local=True)
+                            consume_local=True, peer_copy=peer)
     eng.set_x(x_pattern(np.arange(s, e)))
     eng.step(1.0)
     y = eng.get_x()
@@ -687,7 +693,8 @@ def measure_c4_partitioned(args, sp, D, comm, rank, world):
            "against": "numpy row products of sampled CSR rows, |err| <= 1e-12 * sum|a_ij x_j| per row"}
     par["ok"] = par["bad_rows"] == 0
     out = {"parity": par, "B": B, "N": N, "nnz": int(nnz), "starts": [int(v) for v in starts], "per_rank": per_rank,
-           "split": split, "scale_log2": scale_log2, "ef": ef, "alpha": ALPHA}
+           "split": split, "scale_log2": scale_log2, "ef": ef, "alpha": ALPHA,
+           "transport": "copy-engine pulls from IPC-mapped peer buffers" if peer else "NCCL"}
     if not par["ok"]:
         return out
     eng.set_x(np.random.default_rng(99 + rank).random(e - s) - 0.5)
@@ -731,7 +738,7 @@ def c4_summary(c4, world, peak):
          "frac_of_8TBs_nominal_per_gpu": B / t / 1e9 / world / NOMINAL_HBM_GBS, "frac_of_measured_peak_per_gpu": B / t / 1e9 / world / peak,
          "algorithmic_bytes": int(B), "nonzeros": c4["nnz"], "partition": "balanced non-zeros (spmvb200_partition_rows_nnz)",
          "row_starts": c4["starts"], "per_rank": [{"matrix_size": p[0], "num_coo_entries": p[1], "ell_row_length": p[2]} for p in c4["per_rank"]],
-         "exchange": "allgather", "recv_bytes_per_step_per_rank": c4["recv_bytes"],
+         "exchange": "allgather", "transport": c4["transport"], "recv_bytes_per_step_per_rank": c4["recv_bytes"],
          "overlap": "column split: the entries that reference the rank's own slice of x run during the all-gather" if c4["split"] else "none",
          "rank0_pieces": c4["pieces"], "gpu_launches": c4["gpu_launches"], "x_norm": c4["x_norm"], "parity": c4["parity"],
          "e2e_ms_per_step": c4["e2e_ms_per_step"]}
@@ -788,7 +795,8 @@ def run_multi_gpu(args):
                 "config": {"workload": "c5_csr", "description": f"row-partitioned CSR, 3D 27-point {n}^3 (config 5), "
                            f"x_(k+1) = A x_k / 52, one step = exchange of x + SpMV", "rows": N, "nonzeros": nnz,
                            "algorithmic_bytes": B, "partition": "reference rule ceil(rows/P) (csr-matrix.cpp:77-83)",
-                           "exchange": best, "executor": "spmvb200_dist_* (C ABI, NCCL loaded at run time)",
+                           "exchange": best, "executor": "spmvb200_dist_* (C ABI; transports: NCCL loaded at run time, or copy-engine "
+                                                         "pulls over NVLink out of IPC-mapped peer buffers = the *_peer variants)",
                            "overlap": "interior rows run during the exchange; boundary rows on their own stream as soon as the halo arrives",
                            "l2": "working set per rank far larger than L2"},
                 "gflops": r["gflops"], "frac_of_8TBs_nominal_per_gpu": r["gbs"] / world / NOMINAL_HBM_GBS,

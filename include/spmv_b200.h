@@ -396,6 +396,9 @@ typedef enum {
 #define SPMVB200_DIST_COLUMN_SPLIT 2  /* cut the block by COLUMNS (own slice of x / the rest) instead of by rows: for
                                          matrices without a band (power law); all-gather exchange */
 #define SPMVB200_DIST_NO_OVERLAP 4    /* one block per rank, run after the exchange */
+#define SPMVB200_DIST_PEER_COPY 8     /* NCCL communicators: move x with copy-engine pulls out of the owners' IPC-mapped
+                                         buffers over NVLink instead of NCCL kernels (no SM taken from the SpMV, no
+                                         rendezvous); spmvb200_dist_set_x and _destroy become collective */
 
 /* The exchange plan, as plain arithmetic (no device, no communicator): rank `rank` of `parts` owns columns
  * [starts[rank], starts[rank+1]) of x; need_lo/need_hi[q] = the column range rank q's rows reference (hi exclusive).

@@ -28,10 +28,22 @@
 //               the slice (write-after-read across ranks).
 //   NCCL        one process per rank: ncclSend/ncclRecv of exactly the needed ranges in one group ("halo"), or
 //               ncclAllGather / grouped ncclBroadcast of the slices ("all-gather").  libnccl.so.2 is dlopen'ed.
+//   peer copy   one process per rank, flag SPMVB200_DIST_PEER_COPY: the in-process scheme across processes.  Every rank
+//               exports its x buffers (cudaIpcGetMemHandle) and its "x_k is ready" / "my pulls of step k are done" events
+//               (interprocess events); a rank pulls its ranges straight out of the owners' buffers with cudaMemcpyAsync on
+//               the peer-mapped pointers -- the copy engines move the data over NVLink, no SM is taken from the SpMV, no
+//               rendezvous with the sender.  An interprocess event can only be waited on once its record has been ISSUED,
+//               so the ranks publish their host progress (steps whose events are recorded) in a small POSIX shared-memory
+//               block and a waiter spins on the HOST until the owner's counter says the record exists; nothing spins on
+//               the device.  NCCL is used only while the executor is set up (handle exchange, barriers).
 #include "common.cuh"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -199,6 +211,8 @@ struct spmvb200_comm_s {
     ncclComm_t nccl = nullptr;
     cudaStream_t stream = nullptr;
     double * scratch = nullptr;  // a few doubles of device memory for the plumbing collectives
+    uint64_t id_hash = 0;        // names the shared-memory block of the peer-copy transport
+    int executors = 0;           // executors created on this communicator so far (part of that name)
 };
 
 struct DistBlock {
@@ -228,6 +242,20 @@ struct spmvb200_dist_s {
     int64_t k = 0;  // steps issued
     int64_t x_bytes = 0;
     bool equal_slices = false;
+    // peer-copy transport (one process per rank)
+    bool peer = false;
+    cudaEvent_t e_xready[kRing] = {};        // interprocess: "this rank's slice of x_k is complete", slot k % kRing
+    std::vector<double *> peer_X[2];         // [buffer][rank] peer-mapped x buffers (own rank: the local pointer)
+    std::vector<cudaEvent_t> peer_xready[kRing], peer_exch[kRing];  // [slot][rank] opened interprocess events
+    struct PeerCounters * shm = nullptr;     // [P] host progress of every rank, in POSIX shared memory
+    size_t shm_bytes = 0;
+};
+
+// Host progress a rank publishes for the others: events up to these step indices have been RECORDED (issued).
+struct PeerCounters {
+    volatile int64_t xready_issued;  // e_xready[k] exists for all k < xready_issued
+    volatile int64_t exch_issued;    // e_exch[k]   exists for all k < exch_issued
+    char pad[48];
 };
 
 namespace {
@@ -288,6 +316,21 @@ int dist_free(spmvb200_dist_t d)
             d->comm->group->need_set[(size_t)d->rank] = 0;
         }
     }
+    if (d->peer) {
+        for (int q = 0; q < d->P; q++) {
+            if (q == d->rank) continue;
+            for (int b = 0; b < 2; b++)
+                if ((size_t)q < d->peer_X[b].size() && d->peer_X[b][(size_t)q]) cudaIpcCloseMemHandle(d->peer_X[b][(size_t)q]);
+            for (int i = 0; i < kRing; i++) {
+                if ((size_t)q < d->peer_xready[i].size() && d->peer_xready[i][(size_t)q]) cudaEventDestroy(d->peer_xready[i][(size_t)q]);
+                if ((size_t)q < d->peer_exch[i].size() && d->peer_exch[i][(size_t)q]) cudaEventDestroy(d->peer_exch[i][(size_t)q]);
+            }
+        }
+        if (d->comm && !d->comm->local && d->P > 1) spmvb200_comm_barrier(d->comm);  // nobody frees a buffer a peer still maps
+    }
+    if (d->shm) munmap((void *)d->shm, d->shm_bytes);
+    for (int i = 0; i < kRing; i++)
+        if (d->e_xready[i]) cudaEventDestroy(d->e_xready[i]);
     for (auto & b : d->blocks)
         if (b.owned && b.A) spmvb200_destroy(b.A);
     for (double * p : {d->X[0], d->X[1], d->Yh[0], d->Yh[1]})
@@ -311,6 +354,103 @@ struct DistGuard {
 
 inline int slot(int64_t k) { return (int)(((k % kRing) + kRing) % kRing); }
 
+// ---- peer-copy transport: host progress counters, handle exchange ------------------------------------------------
+inline void publish(volatile int64_t * ctr, int64_t v)
+{
+    if (__atomic_load_n(ctr, __ATOMIC_RELAXED) < v) __atomic_store_n(ctr, v, __ATOMIC_RELEASE);
+}
+
+// Wait on the HOST until rank `who` has issued the record of the event we are about to wait on.
+int spin_until(volatile int64_t * ctr, int64_t target, const char * what)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int64_t it = 0; __atomic_load_n(ctr, __ATOMIC_ACQUIRE) < target; ++it) {
+        if ((it & 1023) == 1023) {
+            sched_yield();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+                return fail(SPMVB200_ERR_CUDA, std::string("peer-copy exchange: timed out waiting for a peer rank to issue ") + what);
+        }
+    }
+    return 0;
+}
+
+struct PeerExport {
+    cudaIpcMemHandle_t x[2];
+    cudaIpcEventHandle_t xready[kRing], exch[kRing];
+};
+
+int setup_peer(spmvb200_dist_t d)
+{
+    NcclApi * nc = nccl_api();
+    spmvb200_comm_t c = d->comm;
+    const int P = d->P, rank = d->rank;
+    // interprocess twins of the two event families the other ranks wait on
+    for (int i = 0; i < kRing; i++) {
+        if (d->e_exch[i]) cudaEventDestroy(d->e_exch[i]);
+        SPMV_CUDA(cudaEventCreateWithFlags(&d->e_exch[i], cudaEventDisableTiming | cudaEventInterprocess));
+        SPMV_CUDA(cudaEventCreateWithFlags(&d->e_xready[i], cudaEventDisableTiming | cudaEventInterprocess));
+    }
+    PeerExport mine;
+    memset(&mine, 0, sizeof mine);
+    for (int b = 0; b < 2; b++) SPMV_CUDA(cudaIpcGetMemHandle(&mine.x[b], d->X[b]));
+    for (int i = 0; i < kRing; i++) {
+        SPMV_CUDA(cudaIpcGetEventHandle(&mine.xready[i], d->e_xready[i]));
+        SPMV_CUDA(cudaIpcGetEventHandle(&mine.exch[i], d->e_exch[i]));
+    }
+    std::vector<PeerExport> all((size_t)P);
+    char * dbuf = nullptr;
+    SPMV_CUDA(cudaMalloc((void **)&dbuf, sizeof(PeerExport) * (size_t)P));
+    SPMV_CUDA(cudaMemcpyAsync(dbuf + sizeof(PeerExport) * (size_t)rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = nc->AllGather(dbuf + sizeof(PeerExport) * (size_t)rank, dbuf, sizeof(PeerExport), ncclChar, c->nccl, c->stream);
+    if (r != ncclSuccess) { cudaFree(dbuf); return nccl_fail(r, "ncclAllGather(peer handles)"); }
+    SPMV_CUDA(cudaMemcpyAsync(all.data(), dbuf, sizeof(PeerExport) * (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+    SPMV_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(dbuf);
+    for (int b = 0; b < 2; b++) d->peer_X[b].assign((size_t)P, nullptr);
+    for (int i = 0; i < kRing; i++) { d->peer_xready[i].assign((size_t)P, nullptr); d->peer_exch[i].assign((size_t)P, nullptr); }
+    // open only what this rank touches: the owners it pulls from (their buffers and readiness) and the ranks that pull
+    // from it (their "pulls done" events)
+    std::vector<char> pull_from((size_t)P, 0), pulled_by((size_t)P, 0);
+    for (const Range & t : d->plan.recvs) pull_from[(size_t)t.peer] = 1;
+    for (const Range & t : d->plan.sends) pulled_by[(size_t)t.peer] = 1;
+    for (int q = 0; q < P; q++) {
+        if (q == rank) {
+            for (int b = 0; b < 2; b++) d->peer_X[b][(size_t)q] = d->X[b];
+            continue;
+        }
+        if (pull_from[(size_t)q]) {
+            for (int b = 0; b < 2; b++)
+                SPMV_CUDA(cudaIpcOpenMemHandle((void **)&d->peer_X[b][(size_t)q], all[(size_t)q].x[b], cudaIpcMemLazyEnablePeerAccess));
+            for (int i = 0; i < kRing; i++) SPMV_CUDA(cudaIpcOpenEventHandle(&d->peer_xready[i][(size_t)q], all[(size_t)q].xready[i]));
+        }
+        if (pulled_by[(size_t)q])
+            for (int i = 0; i < kRing; i++) SPMV_CUDA(cudaIpcOpenEventHandle(&d->peer_exch[i][(size_t)q], all[(size_t)q].exch[i]));
+    }
+    // the host progress counters: rank 0 creates the block, the others open it
+    char name[64];
+    snprintf(name, sizeof name, "/spmvb200_%016llx_%d", (unsigned long long)c->id_hash, c->executors);
+    d->shm_bytes = sizeof(PeerCounters) * (size_t)P;
+    int fd = -1;
+    if (rank == 0) {
+        shm_unlink(name);
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)d->shm_bytes) != 0) return fail(SPMVB200_ERR_IO, std::string("shm_open(") + name + ") failed");
+    }
+    SPMV_TRY(spmvb200_comm_barrier(c));  // the block exists (and is zero: ftruncate)
+    if (rank != 0) {
+        fd = shm_open(name, O_RDWR, 0600);
+        if (fd < 0) return fail(SPMVB200_ERR_IO, std::string("shm_open(") + name + ") failed");
+    }
+    void * map = mmap(nullptr, d->shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return fail(SPMVB200_ERR_IO, "mmap of the peer-copy progress block failed");
+    d->shm = static_cast<PeerCounters *>(map);
+    SPMV_TRY(spmvb200_comm_barrier(c));  // everybody has it mapped
+    if (rank == 0) shm_unlink(name);
+    d->peer = true;
+    return 0;
+}
+
 // ---- the exchange of step k (x_k lives in buffer `buf`), enqueued on d->s_comm ------------------------------------
 // "The owner's slice of this x is complete" is e_int/e_bnd of step k-1 in the iteration (the kernels that produced
 // it) and e_up of step k in run_host (the upload).  `lag`: how many steps ago the buffer was last in use (1 or 2).
@@ -332,11 +472,20 @@ int enqueue_exchange(spmvb200_dist_t d, int buf, int64_t k, Ready ready, int lag
     cudaStream_t cs = d->s_comm;
     if (d->P == 1 || (d->plan.recvs.empty() && d->plan.sends.empty())) {
         SPMV_CUDA(cudaEventRecord(d->e_exch[slot(k)], cs));
+        if (d->peer) publish(&d->shm[d->rank].exch_issued, k + 1);
         return 0;
     }
     // the remote ranges of this buffer were last read by this rank's remote blocks `lag` steps ago
     SPMV_CUDA(cudaStreamWaitEvent(cs, d->e_bnd[slot(k - lag)], 0));
-    if (d->comm->local) {
+    if (d->peer) {
+        for (const Range & r : d->plan.recvs) {
+            // the owner has issued the record of "its slice of x_k is complete" (or set the slice synchronously)
+            SPMV_TRY(spin_until(&d->shm[r.peer].xready_issued, k + 1, "the readiness of its slice of x"));
+            SPMV_CUDA(cudaStreamWaitEvent(cs, d->peer_xready[slot(k)][(size_t)r.peer], 0));
+            SPMV_CUDA(cudaMemcpyAsync(d->X[buf] + r.lo, d->peer_X[buf][(size_t)r.peer] + r.lo, sizeof(double) * (size_t)(r.hi - r.lo),
+                                      cudaMemcpyDeviceToDevice, cs));
+        }
+    } else if (d->comm->local) {
         LocalGroup & g = *d->comm->group;
         for (const Range & r : d->plan.recvs) {
             spmvb200_dist_t o = nullptr;
@@ -371,6 +520,7 @@ int enqueue_exchange(spmvb200_dist_t d, int buf, int64_t k, Ready ready, int lag
         }
     }
     SPMV_CUDA(cudaEventRecord(d->e_exch[slot(k)], cs));
+    if (d->peer) publish(&d->shm[d->rank].exch_issued, k + 1);
     return 0;
 }
 
@@ -381,6 +531,17 @@ int wait_slice_readers(spmvb200_dist_t d, cudaStream_t s, int64_t k_prev_exchang
 {
     if (d->P == 1) return 0;
     const int sl = slot(k_prev_exchange);
+    if (d->peer) {
+        if (k_prev_exchange < 0) return 0;
+        int last = -1;
+        for (const Range & r : d->plan.sends) {  // the ranks that pull from this one
+            if (r.peer == last) continue;
+            last = r.peer;
+            SPMV_TRY(spin_until(&d->shm[r.peer].exch_issued, k_prev_exchange + 1, "its pulls of the previous step"));
+            SPMV_CUDA(cudaStreamWaitEvent(s, d->peer_exch[sl][(size_t)r.peer], 0));
+        }
+        return 0;
+    }
     if (!d->comm->local) {
         SPMV_CUDA(cudaStreamWaitEvent(s, d->e_exch[sl], 0));
         return 0;
@@ -443,6 +604,11 @@ int step(spmvb200_dist_t d, double alpha)
     if (d->any_accumulate) SPMV_CUDA(cudaStreamWaitEvent(d->s_bnd, d->e_int[slot(k)], 0));
     SPMV_TRY(launch_blocks(d, true, d->X[cur], d->X[nxt] + d->s, alpha));
     SPMV_CUDA(cudaEventRecord(d->e_bnd[slot(k)], d->s_bnd));
+    if (d->peer) {  // "this rank's slice of x_(k+1) is complete", for the ranks that will pull from it
+        SPMV_CUDA(cudaStreamWaitEvent(d->s_bnd, d->e_int[slot(k)], 0));
+        SPMV_CUDA(cudaEventRecord(d->e_xready[slot(k + 1)], d->s_bnd));
+        publish(&d->shm[d->rank].xready_issued, k + 2);
+    }
     d->k = k + 1;
     return 0;
 }
@@ -545,6 +711,7 @@ try {
     SPMV_CUDA(cudaGetDevice(&c->device));
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
+    for (size_t i = 0; i < sizeof u; i++) c->id_hash = c->id_hash * 1099511628211ull + (unsigned char)u.internal[i] + 1;
     SPMV_NCCL(nc->CommInitRank(&c->nccl, nranks, u, rank));
     SPMV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SPMV_CUDA(cudaMalloc((void **)&c->scratch, 64 * sizeof(double)));
@@ -732,6 +899,8 @@ try {
         std::vector<int64_t> lo((size_t)P), hi((size_t)P);
         for (int q = 0; q < P; q++) { lo[(size_t)q] = all[(size_t)2 * q]; hi[(size_t)q] = all[(size_t)2 * q + 1]; }
         finalize_plan(d, lo.data(), hi.data());
+        if (flags & SPMVB200_DIST_PEER_COPY) SPMV_TRY(setup_peer(d));
+        comm->executors++;
     }
     *out = guard.release();
     return 0;
@@ -745,6 +914,12 @@ try {
     SPMV_TRY(sync_all(d));
     if (d->rows > 0)
         SPMV_CUDA(cudaMemcpy(d->X[d->k & 1] + d->s, x, sizeof(double) * (size_t)d->rows, cudaMemcpyHostToDevice));
+    if (d->peer) {
+        // the other ranks pull this slice without asking: nobody may proceed before every slice is in place
+        // (spmvb200_dist_set_x is collective with the peer-copy transport)
+        publish(&d->shm[d->rank].xready_issued, d->k + 1);
+        SPMV_TRY(spmvb200_comm_barrier(d->comm));
+    }
     return 0;
 }
 SPMV_ABI_CATCH
@@ -851,6 +1026,10 @@ try {
         SPMV_TRY(wait_slice_readers(d, d->s_h2d, k - 2));
         if (d->rows > 0) SPMV_CUDA(cudaMemcpyAsync(d->X[buf] + d->s, xs[i], bytes, cudaMemcpyHostToDevice, d->s_h2d));
         SPMV_CUDA(cudaEventRecord(d->e_up[slot(k)], d->s_h2d));
+        if (d->peer) {
+            SPMV_CUDA(cudaEventRecord(d->e_xready[slot(k)], d->s_h2d));
+            publish(&d->shm[d->rank].xready_issued, k + 1);
+        }
         if (threads_meet) group_reduce(*d->comm->group, d->rank, 0.0, 1);  // every rank's e_up of this step is recorded
         SPMV_TRY(enqueue_exchange(d, buf, k, Ready::Upload, 2));
         SPMV_CUDA(cudaStreamWaitEvent(d->s_int, d->e_up[slot(k)], 0));
