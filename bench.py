@@ -710,6 +710,12 @@ def measure_c4_partitioned(args, sp, D, comm, rank, world):
     e2e_steps = max(4, min(args.steps, 10))
     e2e_ms, _ = _e2e_host(sp, eng, e - s, e2e_steps, ALPHA)
     out["e2e_ms_per_step"] = comm.allreduce(e2e_ms, "max")
+    # diagnostic: every rank's pieces timed alone, without the exchange (how well the equal-non-zeros cut balances the TIME)
+    mine = 0.0
+    for b in range(inf["n_blocks"]):
+        total_ms, _ = sp.time_rotating([eng.block_matrix(b)], 5, 2, False)
+        mine += total_ms / 5
+    out["rank_compute_ms"] = [comm.allreduce(mine if q == rank else 0.0, "sum") for q in range(world)]
     eng.destroy()
     del eng
     single = None
@@ -741,7 +747,7 @@ def c4_summary(c4, world, peak):
          "exchange": "allgather", "transport": c4["transport"], "recv_bytes_per_step_per_rank": c4["recv_bytes"],
          "overlap": "column split: the entries that reference the rank's own slice of x run during the all-gather" if c4["split"] else "none",
          "rank0_pieces": c4["pieces"], "gpu_launches": c4["gpu_launches"], "x_norm": c4["x_norm"], "parity": c4["parity"],
-         "e2e_ms_per_step": c4["e2e_ms_per_step"]}
+         "e2e_ms_per_step": c4["e2e_ms_per_step"], "rank_compute_ms_without_exchange": c4.get("rank_compute_ms")}
     single = c4.get("single")
     if single and "ms_per_step" in single:
         d["single_gpu"] = {"ms_per_step": single["ms_per_step"], "gbs": single["algorithmic_bytes"] / (single["ms_per_step"] * 1e-3) / 1e9,

@@ -222,6 +222,7 @@ struct DistBlock {
 };
 
 constexpr int kRing = 4;  // event slots: step k uses slot k % kRing
+constexpr int kPullStreams = 4;  // peer-copy transport: pulls in flight at once (one copy engine each)
 
 struct spmvb200_dist_s {
     spmvb200_comm_t comm = nullptr;
@@ -247,6 +248,8 @@ struct spmvb200_dist_s {
     cudaEvent_t e_xready[kRing] = {};        // interprocess: "this rank's slice of x_k is complete", slot k % kRing
     std::vector<double *> peer_X[2];         // [buffer][rank] peer-mapped x buffers (own rank: the local pointer)
     std::vector<cudaEvent_t> peer_xready[kRing], peer_exch[kRing];  // [slot][rank] opened interprocess events
+    cudaStream_t s_pull[kPullStreams] = {};  // extra streams of the all-gather pulls
+    cudaEvent_t e_fork = nullptr, e_join[kPullStreams] = {};
     struct PeerCounters * shm = nullptr;     // [P] host progress of every rank, in POSIX shared memory
     size_t shm_bytes = 0;
 };
@@ -329,6 +332,11 @@ int dist_free(spmvb200_dist_t d)
         if (d->comm && !d->comm->local && d->P > 1) spmvb200_comm_barrier(d->comm);  // nobody frees a buffer a peer still maps
     }
     if (d->shm) munmap((void *)d->shm, d->shm_bytes);
+    for (int l = 0; l < kPullStreams; l++) {
+        if (d->s_pull[l]) { cudaStreamSynchronize(d->s_pull[l]); cudaStreamDestroy(d->s_pull[l]); }
+        if (d->e_join[l]) cudaEventDestroy(d->e_join[l]);
+    }
+    if (d->e_fork) cudaEventDestroy(d->e_fork);
     for (int i = 0; i < kRing; i++)
         if (d->e_xready[i]) cudaEventDestroy(d->e_xready[i]);
     for (auto & b : d->blocks)
@@ -389,6 +397,13 @@ int setup_peer(spmvb200_dist_t d)
         if (d->e_exch[i]) cudaEventDestroy(d->e_exch[i]);
         SPMV_CUDA(cudaEventCreateWithFlags(&d->e_exch[i], cudaEventDisableTiming | cudaEventInterprocess));
         SPMV_CUDA(cudaEventCreateWithFlags(&d->e_xready[i], cudaEventDisableTiming | cudaEventInterprocess));
+    }
+    int lo_prio = 0, hi_prio = 0;
+    SPMV_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    SPMV_CUDA(cudaEventCreateWithFlags(&d->e_fork, cudaEventDisableTiming));
+    for (int l = 0; l < kPullStreams; l++) {
+        SPMV_CUDA(cudaStreamCreateWithPriority(&d->s_pull[l], cudaStreamNonBlocking, hi_prio));
+        SPMV_CUDA(cudaEventCreateWithFlags(&d->e_join[l], cudaEventDisableTiming));
     }
     PeerExport mine;
     memset(&mine, 0, sizeof mine);
@@ -478,13 +493,30 @@ int enqueue_exchange(spmvb200_dist_t d, int buf, int64_t k, Ready ready, int lag
     // the remote ranges of this buffer were last read by this rank's remote blocks `lag` steps ago
     SPMV_CUDA(cudaStreamWaitEvent(cs, d->e_bnd[slot(k - lag)], 0));
     if (d->peer) {
-        for (const Range & r : d->plan.recvs) {
+        // One copy engine moves ~280 GB/s over NVLink; several pulls in flight on different streams use several engines.
+        // The owners are visited starting behind this rank, so that at any time every owner serves different pullers.
+        const size_t nr = d->plan.recvs.size();
+        const int lanes = nr >= 3 ? kPullStreams : 1;
+        size_t first = 0;
+        while (first < nr && d->plan.recvs[first].peer < d->rank) first++;
+        if (lanes > 1) {
+            SPMV_CUDA(cudaEventRecord(d->e_fork, cs));  // carries the wait on e_bnd above to the pull streams
+            for (int l = 0; l < lanes; l++) SPMV_CUDA(cudaStreamWaitEvent(d->s_pull[l], d->e_fork, 0));
+        }
+        for (size_t i = 0; i < nr; i++) {
+            const Range & r = d->plan.recvs[(first + i) % nr];
+            cudaStream_t ps = lanes > 1 ? d->s_pull[i % (size_t)lanes] : cs;
             // the owner has issued the record of "its slice of x_k is complete" (or set the slice synchronously)
             SPMV_TRY(spin_until(&d->shm[r.peer].xready_issued, k + 1, "the readiness of its slice of x"));
-            SPMV_CUDA(cudaStreamWaitEvent(cs, d->peer_xready[slot(k)][(size_t)r.peer], 0));
+            SPMV_CUDA(cudaStreamWaitEvent(ps, d->peer_xready[slot(k)][(size_t)r.peer], 0));
             SPMV_CUDA(cudaMemcpyAsync(d->X[buf] + r.lo, d->peer_X[buf][(size_t)r.peer] + r.lo, sizeof(double) * (size_t)(r.hi - r.lo),
-                                      cudaMemcpyDeviceToDevice, cs));
+                                      cudaMemcpyDeviceToDevice, ps));
         }
+        if (lanes > 1)
+            for (int l = 0; l < lanes; l++) {
+                SPMV_CUDA(cudaEventRecord(d->e_join[l], d->s_pull[l]));
+                SPMV_CUDA(cudaStreamWaitEvent(cs, d->e_join[l], 0));
+            }
     } else if (d->comm->local) {
         LocalGroup & g = *d->comm->group;
         for (const Range & r : d->plan.recvs) {
@@ -822,7 +854,6 @@ try {
     d->need_lo = col_max < 0 ? 0 : col_min;
     d->need_hi = col_max < 0 ? 0 : col_max + 1;
     d->wanted_mode = exchange;
-    bool local_used = false;
     auto add = [&](spmvb200_matrix_t A, int64_t b, int64_t e, bool remote, bool accumulate, bool owned) -> int {
         if (format != SPMVB200_CSR) {
             spmvb200_info bi;
@@ -830,7 +861,7 @@ try {
             if (bi.format == SPMVB200_CSR) {
                 spmvb200_matrix_t conv = nullptr;
                 SPMV_TRY(spmvb200_convert(A, format, 0, &conv));
-                if (owned) spmvb200_destroy(A); else if (A == local) local_used = false;
+                if (owned) spmvb200_destroy(A);
                 A = conv; owned = true;
             }
         }
@@ -848,8 +879,7 @@ try {
         SPMV_TRY(add(outside, 0, d->rows, true, true, true));
         d->any_accumulate = true;
     } else if (!overlap || !csr || lo_end >= hi_begin) {
-        local_used = true;
-        SPMV_TRY(add(local, 0, d->rows, P > 1, false, consume));
+        SPMV_TRY(add(local, 0, d->rows, P > 1, false, false));
     } else {
         struct Cut { int64_t b, e; bool remote; };
         std::vector<Cut> cuts;
@@ -858,8 +888,7 @@ try {
         if (hi_begin < d->rows) cuts.push_back({hi_begin, d->rows, true});
         for (auto & c : cuts) {
             if (c.b == 0 && c.e == d->rows) {
-                local_used = true;
-                SPMV_TRY(add(local, 0, d->rows, c.remote, false, consume));
+                SPMV_TRY(add(local, 0, d->rows, c.remote, false, false));
             } else {
                 spmvb200_matrix_t blk = nullptr;
                 SPMV_TRY(spmvb200_csr_row_block(local, c.b, c.e, &blk));
@@ -867,7 +896,6 @@ try {
             }
         }
     }
-    if (consume && !local_used) spmvb200_destroy(local);
     for (auto & b : d->blocks) {
         SPMV_TRY(spmvb200_set_stream(b.A, b.remote ? d->s_bnd : d->s_int));
         SPMV_TRY(spmvb200_set_option(b.A, "beta0", b.accumulate ? 0 : 1));
@@ -901,6 +929,13 @@ try {
         finalize_plan(d, lo.data(), hi.data());
         if (flags & SPMVB200_DIST_PEER_COPY) SPMV_TRY(setup_peer(d));
         comm->executors++;
+    }
+    // `local` changes hands only now that nothing can fail any more: until here a failure leaves it with the caller
+    if (consume) {
+        bool used = false;
+        for (auto & b : d->blocks)
+            if (b.A == local) { b.owned = true; used = true; }
+        if (!used) spmvb200_destroy(local);
     }
     *out = guard.release();
     return 0;
