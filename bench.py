@@ -46,6 +46,7 @@ if ROOT not in sys.path:
 METRIC = "spmv_effective_bandwidth"
 UNIT = "GB/s"
 NOMINAL_HBM_GBS = 8000.0  # the "8 TB/s HBM3e roofline" BASELINE.json's metric is normalised to
+C4_ROW_WEIGHT = 0.0       # per-row cost (in entries) of the configs[3] partition; see measure_c4_partitioned
 
 
 def measured_peak():
@@ -239,14 +240,16 @@ def parity_stencil(kind, nx, ny, nz, row_begin, y_local, seed=7):
 def parity_csr_rows(rp, col, val, y_rows):
     """|y - sum a_ij x_j| <= 1e-12 * sum |a_ij x_j| per row (BASELINE tolerance) for CSR rows held on the host."""
     p = val * x_pattern(col)
-    starts = rp[:-1].astype(np.int64)
+    rp = np.asarray(rp, dtype=np.int64)
     nonempty = rp[1:] > rp[:-1]
     ref = np.zeros(len(rp) - 1)
     bound = np.zeros(len(rp) - 1)
     if len(p):
-        idx = np.minimum(starts, len(p) - 1)
-        ref = np.where(nonempty, np.add.reduceat(p, idx), 0.0)
-        bound = np.where(nonempty, np.add.reduceat(np.abs(p), idx), 0.0)
+        # reduceat over the starts of the NON-EMPTY rows only (strictly increasing, the last one sums to the end): with
+        # empty rows in the index list reduceat would cut the preceding row short
+        idx = rp[:-1][nonempty]
+        ref[nonempty] = np.add.reduceat(p, idx)
+        bound[nonempty] = np.add.reduceat(np.abs(p), idx)
     err = np.abs(y_rows - ref)
     bad = int(np.count_nonzero(err > 1e-12 * bound))
     rel = float(np.max(err / np.maximum(bound, 1e-300))) if len(err) else 0.0
@@ -658,7 +661,11 @@ def measure_c4_partitioned(args, sp, D, comm, rank, world):
     seed = 0x5EED0004
     N = 1 << scale_log2
     full = sp.generators.rmat(scale_log2, ef, seed, fmt=sp.CSR)  # every rank: the partition needs the global row_ptr
-    starts = sp.partition.rows_nnz(full, world)
+    # balanced COST: a row costs its entries + ROW_WEIGHT entries of per-row work (y traffic of two pieces, ELL padding, one
+    # reduction per run); 0 = balanced non-zeros.  R-MAT's long rows come first, so with equal non-zeros the last rank holds
+    # six times the rows of the first and is the slower one (`rank_compute_ms_without_exchange`).
+    row_weight = float(os.environ.get("SPMV_C4_ROW_WEIGHT", str(C4_ROW_WEIGHT)))
+    starts = sp.partition.rows_weighted(full, world, row_weight)
     s, e = int(starts[rank]), int(starts[rank + 1])
     block = full.row_block(s, e)
     nnz = full.num_entries
@@ -693,7 +700,7 @@ def measure_c4_partitioned(args, sp, D, comm, rank, world):
            "against": "numpy row products of sampled CSR rows, |err| <= 1e-12 * sum|a_ij x_j| per row"}
     par["ok"] = par["bad_rows"] == 0
     out = {"parity": par, "B": B, "N": N, "nnz": int(nnz), "starts": [int(v) for v in starts], "per_rank": per_rank,
-           "split": split, "scale_log2": scale_log2, "ef": ef, "alpha": ALPHA,
+           "split": split, "scale_log2": scale_log2, "ef": ef, "alpha": ALPHA, "row_weight": row_weight,
            "transport": "copy-engine pulls from IPC-mapped peer buffers" if peer else "NCCL"}
     if not par["ok"]:
         return out
@@ -742,7 +749,8 @@ def c4_summary(c4, world, peak):
          "x_(k+1) = alpha A x_k, one step = all-gather of x + ELL kernel + COO kernel per piece",
          "ms_per_step": c4["ms_per_step"], "gbs": B / t / 1e9, "gflops": 2.0 * c4["nnz"] / t / 1e9,
          "frac_of_8TBs_nominal_per_gpu": B / t / 1e9 / world / NOMINAL_HBM_GBS, "frac_of_measured_peak_per_gpu": B / t / 1e9 / world / peak,
-         "algorithmic_bytes": int(B), "nonzeros": c4["nnz"], "partition": "balanced non-zeros (spmvb200_partition_rows_nnz)",
+         "algorithmic_bytes": int(B), "nonzeros": c4["nnz"],
+         "partition": f"balanced cost, row = its entries + {c4['row_weight']:g} (spmvb200_partition_rows_weighted; 0 = balanced non-zeros)",
          "row_starts": c4["starts"], "per_rank": [{"matrix_size": p[0], "num_coo_entries": p[1], "ell_row_length": p[2]} for p in c4["per_rank"]],
          "exchange": "allgather", "transport": c4["transport"], "recv_bytes_per_step_per_rank": c4["recv_bytes"],
          "overlap": "column split: the entries that reference the rank's own slice of x run during the all-gather" if c4["split"] else "none",

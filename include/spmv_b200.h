@@ -338,6 +338,13 @@ int spmvb200_destroy(spmvb200_matrix_t m);
 int spmvb200_partition_rows_ref(int64_t rows, int32_t parts, int64_t *starts /* parts+1 */);
 /* Balanced non-zeros: start_p = first row r with row_ptr[r] >= floor(p*nnz/P). CSR only. */
 int spmvb200_partition_rows_nnz(spmvb200_matrix_t m, int32_t parts, int64_t *starts /* parts+1 */);
+/* Balanced COST, where a row costs its entries plus row_weight_q10/1024 entries of per-row work (its y traffic, its ELL
+ * padding, one reduction per run -- what makes a block of many short rows slower than a block of few long ones with the
+ * same non-zeros): start_p = first row r with 1024*row_ptr[r] + w*r >= floor(p*(1024*nnz + w*rows)/P).  w = 0 is the
+ * cut of spmvb200_partition_rows_nnz (up to one row: the targets round differently); a very large w tends to equal rows.
+ * CSR only.  (Measured on configs[3] at two GPUs, profiles/r02_sweep_s_c4_row_weight.log: w = 0 / 4 / 12 / 32 -> 4.90 / 4.90 /
+ * 5.15 / 6.06 ms: equal non-zeros IS the balanced cut for that matrix.) */
+int spmvb200_partition_rows_weighted(spmvb200_matrix_t m, int32_t parts, int64_t row_weight_q10, int64_t *starts /* parts+1 */);
 /* New matrix holding rows [row_begin, row_end) of a CSR matrix (global columns). */
 int spmvb200_csr_row_block(spmvb200_matrix_t m, int64_t row_begin, int64_t row_end,
                            spmvb200_matrix_t *out);

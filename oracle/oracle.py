@@ -393,6 +393,13 @@ class Oracle:
                                         C.c_int(P), out.ctypes.data_as(C.POINTER(C.c_int64)))
         return out
 
+    def partition_rows_weighted(self, row_ptr, P, row_weight: float):
+        rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        out = np.zeros(P + 1, dtype=np.int64)
+        self.lib.orc_partition_rows_weighted(C.c_int64(len(rp) - 1), rp.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(P),
+                                             C.c_int64(int(round(1024 * row_weight))), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
+
 
 class RefError(RuntimeError):
     pass

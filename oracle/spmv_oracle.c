@@ -770,6 +770,25 @@ void orc_partition_rows_nnz(int64_t rows, const int64_t *row_ptr, int P, int64_t
     starts[P] = rows;
 }
 
+/* P_weighted: start_p = first r with 1024*row_ptr[r] + w*r >= floor(p*(1024*nnz + w*rows)/P) (our design). */
+void orc_partition_rows_weighted(int64_t rows, const int64_t *row_ptr, int P, int64_t w, int64_t *starts)
+{
+    const unsigned __int128 total = (unsigned __int128)1024 * (uint64_t)row_ptr[rows] + (unsigned __int128)w * (uint64_t)rows;
+    int p;
+    starts[0] = 0;
+    for (p = 1; p < P; p++) {
+        const unsigned __int128 target = total * (unsigned)p / (unsigned)P;
+        int64_t lo = 0, hi = rows;
+        while (lo < hi) {
+            int64_t mid = lo + (hi - lo) / 2;
+            const unsigned __int128 c = (unsigned __int128)1024 * (uint64_t)row_ptr[mid] + (unsigned __int128)w * (uint64_t)mid;
+            if (c >= target) hi = mid; else lo = mid + 1;
+        }
+        starts[p] = lo;
+    }
+    starts[P] = rows;
+}
+
 /* ======================================================================== */
 /* R-MAT edges of the synthetic power-law matrices (BASELINE configs 3, 4)   */
 /* ======================================================================== */

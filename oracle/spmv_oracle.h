@@ -178,6 +178,8 @@ void orc_partition_rows_ref(int64_t rows, int P, int64_t *starts /* P+1 */);
 /* P_nnz: start_p = first row r with row_ptr[r] >= floor(p*nnz/P); start_0 = 0, start_P = rows. */
 void orc_partition_rows_nnz(int64_t rows, const int64_t *row_ptr, int P, int64_t *starts /* P+1 */);
 
+void orc_partition_rows_weighted(int64_t rows, const int64_t *row_ptr, int P, int64_t row_weight_q10, int64_t *starts /* P+1 */);
+
 /* ---- R-MAT edges: C twin of OUR device generator (generators.cu), for the full-size parity tests ----------- */
 void orc_rmat_keys(int scale, uint64_t seed, double a, double b, double c, uint64_t e0, uint64_t e1, uint64_t *keys);
 void orc_rmat_unpack(int64_t n, const uint64_t *keys, int32_t *col, double *val);

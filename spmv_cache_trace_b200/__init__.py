@@ -641,6 +641,14 @@ class partition:
         return out
 
 
+    @staticmethod
+    def rows_weighted(A: DeviceMatrix, parts: int, row_weight: float):
+        """Balanced cost, a row costing its entries + row_weight (in entries): spmvb200_partition_rows_weighted."""
+        out = np.zeros(parts + 1, np.int64)
+        _check(_abi.lib().spmvb200_partition_rows_weighted(A._h, parts, int(round(1024 * row_weight)), _p(out, i64p)))
+        return out
+
+
 class cache_model:
     """The reference's LRU cache model (cache-simulation/lru.cpp, cache-trace.cpp:92-161) over the SpMV
     reference string, with per-array attribution and an arbitrary partition (include/spmv_b200.h).

@@ -133,6 +133,7 @@ SIGNATURES = {
     "spmvb200_destroy": (C.c_int, [vp]),
     "spmvb200_partition_rows_ref": (C.c_int, [C.c_int64, C.c_int32, i64p]),
     "spmvb200_partition_rows_nnz": (C.c_int, [vp, C.c_int32, i64p]),
+    "spmvb200_partition_rows_weighted": (C.c_int, [vp, C.c_int32, C.c_int64, i64p]),
     "spmvb200_csr_row_block": (C.c_int, [vp, C.c_int64, C.c_int64, vpp]),
     "spmvb200_csr_column_split": (C.c_int, [vp, C.c_int64, C.c_int64, vpp, vpp]),
     "spmvb200_csr_column_span": (C.c_int, [vp, C.c_int64, C.c_int64, i64p, i64p, i64p, i64p]),

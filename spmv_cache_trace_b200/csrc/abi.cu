@@ -100,6 +100,26 @@ __global__ void partition_nnz_kernel(int64_t rows, const OffT * rp, int parts, i
     starts[p] = lo;
 }
 
+// Weighted variant: a row costs its entries plus row_weight_q10 / 1024 "entries" of per-row work (y traffic, padding, a
+// reduction per run): start_p = first r with 1024*rp[r] + w*r >= floor(p * (1024*nnz + w*rows) / P).
+template <typename OffT>
+__global__ void partition_weighted_kernel(int64_t rows, const OffT * rp, int parts, int64_t w, int64_t * starts)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > parts) return;
+    if (p == 0) { starts[0] = 0; return; }
+    if (p == parts) { starts[p] = rows; return; }
+    const unsigned __int128 total = (unsigned __int128)1024 * (unsigned long long)rp[rows] + (unsigned __int128)w * (unsigned long long)rows;
+    const unsigned __int128 target = total * (unsigned)p / (unsigned)parts;
+    int64_t lo = 0, hi = rows;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        const unsigned __int128 c = (unsigned __int128)1024 * (unsigned long long)rp[mid] + (unsigned __int128)w * (unsigned long long)mid;
+        if (c >= target) hi = mid; else lo = mid + 1;
+    }
+    starts[p] = lo;
+}
+
 template <typename OffT>
 __global__ void rebase_offsets_kernel(int64_t n, const OffT * rp, int64_t first, int64_t * out)
 {
@@ -1415,6 +1435,23 @@ try {
     const unsigned grid = (unsigned)((parts + 1 + 63) / 64);
     if (m->off64) partition_nnz_kernel<int64_t><<<grid, 64, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, parts, d.p);
     else partition_nnz_kernel<uint32_t><<<grid, 64, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, parts, d.p);
+    SPMV_CUDA(cudaGetLastError());
+    SPMV_CUDA(cudaMemcpyAsync(starts, d.p, sizeof(int64_t) * (size_t)(parts + 1), cudaMemcpyDeviceToHost, m->stream));
+    SPMV_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+SPMV_ABI_CATCH
+
+int spmvb200_partition_rows_weighted(spmvb200_matrix_t m, int32_t parts, int64_t row_weight_q10, int64_t * starts)
+try {
+    SPMV_TRY(check(m));
+    if (m->format != SPMVB200_CSR || parts < 1 || !starts || row_weight_q10 < 0 || row_weight_q10 > ((int64_t)1 << 30))
+        return fail(SPMVB200_ERR_INVALID, "bad argument");
+    Scratch<int64_t> d;
+    SPMV_TRY(d.alloc(parts + 1));
+    const unsigned grid = (unsigned)((parts + 1 + 63) / 64);
+    if (m->off64) partition_weighted_kernel<int64_t><<<grid, 64, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, parts, row_weight_q10, d.p);
+    else partition_weighted_kernel<uint32_t><<<grid, 64, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, parts, row_weight_q10, d.p);
     SPMV_CUDA(cudaGetLastError());
     SPMV_CUDA(cudaMemcpyAsync(starts, d.p, sizeof(int64_t) * (size_t)(parts + 1), cudaMemcpyDeviceToHost, m->stream));
     SPMV_CUDA(cudaStreamSynchronize(m->stream));

@@ -796,6 +796,24 @@ def test_row_partition_concatenates_to_the_full_product(oracle, P):
         assert csr_matrix.spmv_nonzeros_per_thread(A, t, P) == oracle.csr_nonzeros_per_thread(O.row_ptr, N, t, P)
 
 
+def test_weighted_row_partition(oracle):
+    """spmvb200_partition_rows_weighted: bit-exact against the oracle; weight 0 is the balanced-nnz cut, and a heavy
+    per-row weight moves rows from the block of many short rows to the block of few long ones."""
+    scale, ef, seed = 13, 16, 0x5EED0004
+    A = sp.generators.rmat(scale, ef, seed)
+    rp = A.export()["row_ptr"]
+    for P in (1, 2, 3, 8):
+        for w in (0.0, 0.5, 4.0, 37.25, 1e5):
+            got = sp.partition.rows_weighted(A, P, w)
+            assert np.array_equal(got, oracle.partition_rows_weighted(rp, P, w)), (P, w)
+            assert got[0] == 0 and got[-1] == A.rows and np.all(np.diff(got) >= 0)
+        # weight 0 is the balanced-nnz cut up to the rounding of its targets (floor(1024 t) vs 1024 floor(t)): one row at most
+        assert np.all(np.abs(sp.partition.rows_weighted(A, P, 0.0) - sp.partition.rows_nnz(A, P)) <= 1)
+    s0 = sp.partition.rows_weighted(A, 2, 0.0)[1]
+    s8 = sp.partition.rows_weighted(A, 2, 8.0)[1]
+    assert s8 > s0  # R-MAT's long rows come first: the first block takes more rows when rows cost something
+
+
 @pytest.mark.parametrize("empty_every", [0, 5])
 def test_csr_traffic_probes(oracle, empty_every):
     """spmv_regular_traffic / spmv_irregular_traffic (csr-matrix-spmv.cpp:35-61): values only / gather only."""
