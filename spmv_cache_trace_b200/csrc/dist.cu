@@ -48,6 +48,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -249,6 +250,7 @@ struct spmvb200_dist_s {
     std::vector<double *> peer_X[2];         // [buffer][rank] peer-mapped x buffers (own rank: the local pointer)
     std::vector<cudaEvent_t> peer_xready[kRing], peer_exch[kRing];  // [slot][rank] opened interprocess events
     cudaStream_t s_pull[kPullStreams] = {};  // extra streams of the all-gather pulls
+    int pull_lanes = 1;                      // how many of them are used (SPMVB200_PULL_LANES, 1..kPullStreams)
     cudaEvent_t e_fork = nullptr, e_join[kPullStreams] = {};
     struct PeerCounters * shm = nullptr;     // [P] host progress of every rank, in POSIX shared memory
     size_t shm_bytes = 0;
@@ -400,6 +402,7 @@ int setup_peer(spmvb200_dist_t d)
     }
     int lo_prio = 0, hi_prio = 0;
     SPMV_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    if (const char * env = getenv("SPMVB200_PULL_LANES")) d->pull_lanes = std::max(1, std::min(kPullStreams, atoi(env)));
     SPMV_CUDA(cudaEventCreateWithFlags(&d->e_fork, cudaEventDisableTiming));
     for (int l = 0; l < kPullStreams; l++) {
         SPMV_CUDA(cudaStreamCreateWithPriority(&d->s_pull[l], cudaStreamNonBlocking, hi_prio));
@@ -496,7 +499,7 @@ int enqueue_exchange(spmvb200_dist_t d, int buf, int64_t k, Ready ready, int lag
         // One copy engine moves ~280 GB/s over NVLink; several pulls in flight on different streams use several engines.
         // The owners are visited starting behind this rank, so that at any time every owner serves different pullers.
         const size_t nr = d->plan.recvs.size();
-        const int lanes = nr >= 3 ? kPullStreams : 1;
+        const int lanes = nr >= 3 ? d->pull_lanes : 1;
         size_t first = 0;
         while (first < nr && d->plan.recvs[first].peer < d->rank) first++;
         if (lanes > 1) {
