@@ -607,15 +607,33 @@ def measure_c5_partitioned(args, sp, D, comm, rank, world, sampler):
     # every plan with both transports: NCCL kernels, and copy-engine pulls out of the owners' IPC-mapped buffers ("_peer")
     transports = [False, True] if world > 1 and os.environ.get("SPMV_PEER_COPY", "1") != "0" else [False]
     results, marks = {}, {}
-    for mode, peer in [(m, t) for m in plans for t in transports]:
-        label = mode + ("_peer" if peer else "")
+    x3_first = None
+    variants = [(m, t, False) for m in plans for t in transports]
+    if len(transports) > 1 and "halo" in plans:
+        variants.append(("halo", True, True))  # "_push": the kernels store the halo rows straight into the neighbours' buffers
+    for mode, peer, push in variants:
+        label = mode + ("_push" if push else "_peer" if peer else "")
         # every rank generates only its own rows of the 27-point operator, on its own GPU
         local = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR, row_begin=s, row_end=e)
-        eng = D.DistributedSpMV(comm, local, starts, mode=mode, consume_local=True, peer_copy=peer)
+        eng = D.DistributedSpMV(comm, local, starts, mode=mode, consume_local=True, peer_copy=peer, peer_push=push)
         # parity before timing: one step from x_j = 1 + (j mod 7)/8, alpha = 1, every rank checks its rows exactly
         eng.set_x(x_pattern(np.arange(s, e)))
         eng.step(1.0)
         par = parity_stencil(2, n, n, n, s, eng.get_x(), seed=11 + rank)
+        # ... and three steps back to back on the same exact data (multiples of 1/8 below 2^19: exact in any order), so that
+        # steps 2 and 3 consume the halo the previous step delivered (copied, or stored by the fused push): every variant
+        # must reproduce the first one's rows bit for bit
+        eng.set_x(x_pattern(np.arange(s, e)))
+        for _ in range(3):
+            eng.step(1.0)
+        x3 = eng.get_x()
+        if x3_first is None:
+            x3_first = x3
+            par["three_steps"] = "reference variant"
+        else:
+            diff = int(np.count_nonzero(x3 != x3_first))
+            par["bad_rows"] += diff
+            par["three_steps"] = "identical to the first variant" if diff == 0 else f"{diff} rows differ from the first variant"
         par["bad_rows"] = int(comm.allreduce(par["bad_rows"], "sum"))
         par["rows_checked"] = int(comm.allreduce(par["rows_checked"], "sum"))
         par["max_rel"] = comm.allreduce(par["max_rel"], "max")
@@ -636,7 +654,8 @@ def measure_c5_partitioned(args, sp, D, comm, rank, world, sampler):
         xnorm = math.sqrt(comm.allreduce(float(np.sum(eng.get_x() ** 2)), "sum"))
         results[label] = {"ms_per_step": t * 1e3, "gbs": B / t / 1e9, "gflops": 2.0 * nnz / t / 1e9,
                          "recv_bytes_per_step_per_rank": inf["recv_bytes_per_step"], "plan": inf["exchange"],
-                         "transport": "copy-engine pulls from IPC-mapped peer buffers" if peer else "NCCL",
+                         "transport": ("halo rows stored into the neighbours' IPC-mapped buffers by the SpMV kernel itself (fused push)"
+                                       if push and inf["halo_push"] else "copy-engine pulls from IPC-mapped peer buffers" if peer else "NCCL"),
                          "row_blocks": eng.blocks(), "interior_rows": inf["interior_rows"],
                          "gpu_launches": int(sp.launch_count() - launches0), "launches_per_step": inf["launches_per_step"],
                          "resident_bytes_rank0": inf["device_bytes"], "x_norm": xnorm, "parity": par,

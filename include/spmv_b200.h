@@ -444,6 +444,10 @@ int spmvb200_dist_time(const spmvb200_dist_t *ds, int n, int warmup, int steps, 
  * copy streams while step i computes.  ms (may be NULL) = device time of the whole sequence.  Synchronises. */
 int spmvb200_dist_run_host(spmvb200_dist_t d, int steps, const double *const *x_local_host, double *const *y_local_host,
                            double alpha, float *ms);
+#define SPMVB200_DIST_PEER_PUSH 16    /* PEER_COPY plus the fused form of the halo plan: the kernel that computes the rows a
+                                         neighbouring rank references stores them into that rank's x buffer as well (peer-
+                                         mapped pointer, the stores travel over NVLink), so the next exchange has nothing to
+                                         copy; used when every rank's sending blocks run the sliced CSR kernel */
 typedef struct {
     int32_t rank, nranks;
     int32_t exchange;             /* the mode in use (spmvb200_exchange)                         */
@@ -457,6 +461,7 @@ typedef struct {
     int64_t device_bytes;         /* matrices + x buffers resident on this rank's GPU             */
     int64_t launches_per_step;
     int64_t steps_done;
+    int64_t halo_push;            /* 1: the halo is stored by the senders' kernels (SPMVB200_DIST_PEER_PUSH in effect) */
 } spmvb200_dist_info_t;
 int spmvb200_dist_info(spmvb200_dist_t d, spmvb200_dist_info_t *info);
 /* Block b of the executor (0 <= b < n_blocks): its row range inside the rank, whether it needs remote x, and the

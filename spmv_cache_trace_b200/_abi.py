@@ -58,7 +58,7 @@ class DistInfo(C.Structure):
         ("n_sends", C.c_int32), ("n_recvs", C.c_int32),
         ("recv_bytes_per_step", C.c_int64), ("send_bytes_per_step", C.c_int64),
         ("rows", C.c_int64), ("row_begin", C.c_int64), ("num_entries", C.c_int64), ("interior_rows", C.c_int64),
-        ("device_bytes", C.c_int64), ("launches_per_step", C.c_int64), ("steps_done", C.c_int64),
+        ("device_bytes", C.c_int64), ("launches_per_step", C.c_int64), ("steps_done", C.c_int64), ("halo_push", C.c_int64),
     ]
 
 

@@ -115,6 +115,10 @@ struct spmvb200_matrix_s {
     int host_chunks = 0;
     int64_t host_rows_per_chunk = 0;
     int host_colmax[64] = {};
+    // fused compute + halo push (row-partitioned executor, sliced CSR kernel in store mode): rows [push_lo, push_hi) of the
+    // next launch are ALSO stored at push_y[..][row] -- a peer GPU's x buffer, mapped over NVLink
+    double * push_y[2] = {nullptr, nullptr};
+    int64_t push_lo[2] = {0, 0}, push_hi[2] = {0, 0};
     // optional row range for the next launches (ELL, sliced CSR): [range_begin, range_end), range_end <= 0 = all rows
     int64_t range_begin = 0, range_end = 0;
     const double * host_y_in = nullptr;    // zero-copy host-buffer path (ELL): device-visible host pointers

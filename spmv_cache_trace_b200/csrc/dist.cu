@@ -252,6 +252,11 @@ struct spmvb200_dist_s {
     cudaStream_t s_pull[kPullStreams] = {};  // extra streams of the all-gather pulls
     int pull_lanes = 1;                      // how many of them are used (SPMVB200_PULL_LANES, 1..kPullStreams)
     cudaEvent_t e_fork = nullptr, e_join[kPullStreams] = {};
+    // fused halo push: the kernels that compute the rows a neighbour references store them into the neighbour's buffer
+    struct PushRange { int peer; int64_t lo, hi; };          // block-local rows [lo, hi) go to rank `peer`
+    std::vector<std::vector<PushRange>> push;                // per block
+    bool want_push = false, push_active = false;
+    int64_t halo_by_push = -1;               // the halo of x_k (k = this value) was delivered by the senders' kernels
     struct PeerCounters * shm = nullptr;     // [P] host progress of every rank, in POSIX shared memory
     size_t shm_bytes = 0;
 };
@@ -436,7 +441,7 @@ int setup_peer(spmvb200_dist_t d)
             for (int b = 0; b < 2; b++) d->peer_X[b][(size_t)q] = d->X[b];
             continue;
         }
-        if (pull_from[(size_t)q]) {
+        if (pull_from[(size_t)q] || pulled_by[(size_t)q]) {  // (the push form writes into the buffers of the ranks that would pull)
             for (int b = 0; b < 2; b++)
                 SPMV_CUDA(cudaIpcOpenMemHandle((void **)&d->peer_X[b][(size_t)q], all[(size_t)q].x[b], cudaIpcMemLazyEnablePeerAccess));
             for (int i = 0; i < kRing; i++) SPMV_CUDA(cudaIpcOpenEventHandle(&d->peer_xready[i][(size_t)q], all[(size_t)q].xready[i]));
@@ -466,6 +471,35 @@ int setup_peer(spmvb200_dist_t d)
     SPMV_TRY(spmvb200_comm_barrier(c));  // everybody has it mapped
     if (rank == 0) shm_unlink(name);
     d->peer = true;
+    return 0;
+}
+
+// Fused compute + halo push (flag SPMVB200_DIST_PEER_PUSH, halo plan, peer transport): every send range of the plan is cut
+// at the block boundaries; a block may push to at most two ranks and must run the sliced CSR kernel in store mode.  All
+// ranks must agree (a receiver that expects a push must get one), hence the reduction at the end.
+bool build_push_lists(spmvb200_dist_t d)
+{
+    bool ok = d->plan.mode == SPMVB200_EXCHANGE_HALO && !d->any_accumulate;
+    d->push.assign(d->blocks.size(), {});
+    for (size_t bi = 0; ok && bi < d->blocks.size(); bi++) {
+        const DistBlock & b = d->blocks[bi];
+        for (const Range & t : d->plan.sends) {
+            const int64_t lo = std::max<int64_t>(t.lo - d->s, b.b), hi = std::min<int64_t>(t.hi - d->s, b.e);
+            if (hi <= lo) continue;
+            d->push[bi].push_back({t.peer, lo - b.b, hi - b.b});
+        }
+        if (d->push[bi].empty()) continue;
+        if (d->push[bi].size() > 2 || !csr_uses_sliced_kernel(b.A) || b.A->opt_csr_threads != 0 || b.A->opt_csr_batch != 0) ok = false;
+    }
+    return ok;
+}
+
+int setup_push(spmvb200_dist_t d)
+{
+    double all_ok = (d->peer && build_push_lists(d)) ? 1.0 : 0.0;
+    SPMV_TRY(spmvb200_comm_allreduce(d->comm, &all_ok, 2));
+    d->push_active = all_ok > 0.5;
+    if (!d->push_active) d->push.clear();
     return 0;
 }
 
@@ -512,6 +546,7 @@ int enqueue_exchange(spmvb200_dist_t d, int buf, int64_t k, Ready ready, int lag
             // the owner has issued the record of "its slice of x_k is complete" (or set the slice synchronously)
             SPMV_TRY(spin_until(&d->shm[r.peer].xready_issued, k + 1, "the readiness of its slice of x"));
             SPMV_CUDA(cudaStreamWaitEvent(ps, d->peer_xready[slot(k)][(size_t)r.peer], 0));
+            if (d->halo_by_push == k && ready == Ready::Iteration) continue;  // the owner's kernels stored it here already
             SPMV_CUDA(cudaMemcpyAsync(d->X[buf] + r.lo, d->peer_X[buf][(size_t)r.peer] + r.lo, sizeof(double) * (size_t)(r.hi - r.lo),
                                       cudaMemcpyDeviceToDevice, ps));
         }
@@ -530,6 +565,7 @@ int enqueue_exchange(spmvb200_dist_t d, int buf, int64_t k, Ready ready, int lag
             }
             if (!o) return fail(SPMVB200_ERR_INVALID, "in-process exchange: a peer rank has no executor");
             SPMV_TRY(wait_ready(cs, o, ready, k));
+            if (ready == Ready::Iteration && o->push_active && o->halo_by_push == k) continue;  // the owner's kernels stored it here
             SPMV_CUDA(cudaMemcpyPeerAsync(d->X[buf] + r.lo, d->device, o->X[buf] + r.lo, o->device,
                                           sizeof(double) * (size_t)(r.hi - r.lo), cs));
         }
@@ -596,14 +632,47 @@ int wait_slice_readers(spmvb200_dist_t d, cudaStream_t s, int64_t k_prev_exchang
     return 0;
 }
 
-int launch_blocks(spmvb200_dist_t d, bool remote, const double * x, double * y_base, double alpha)
+// push_buf >= 0: iteration step k whose results also go to the neighbours' buffer `push_buf` (their X[(k+1) % 2]).
+int launch_blocks(spmvb200_dist_t d, bool remote, const double * x, double * y_base, double alpha, int push_buf = -1,
+                  int64_t k = 0)
 {
-    for (auto & b : d->blocks) {
+    for (size_t bi = 0; bi < d->blocks.size(); bi++) {
+        DistBlock & b = d->blocks[bi];
         if (b.remote != remote) continue;
         SPMV_TRY(spmvb200_bind_x(b.A, (void *)x));
         SPMV_TRY(spmvb200_bind_y(b.A, (void *)(y_base + b.b)));
         SPMV_TRY(spmvb200_set_alpha(b.A, alpha));
-        SPMV_TRY(spmvb200_spmv(b.A));
+        for (int t = 0; t < 2; t++) { b.A->push_y[t] = nullptr; b.A->push_lo[t] = b.A->push_hi[t] = 0; }
+        if (push_buf >= 0 && d->push_active) {
+            int t = 0;
+            for (const auto & pr : d->push[bi]) {
+                // the target's buffer still holds x_(k-1), which its boundary kernels of step k-1 read: they are behind
+                // its "x_k is ready" event
+                cudaStream_t bs = remote ? d->s_bnd : d->s_int;
+                double * target = nullptr;
+                if (d->comm->local) {
+                    spmvb200_dist_t q = nullptr;
+                    {
+                        std::lock_guard<std::mutex> lk(d->comm->group->mu);
+                        q = d->comm->group->dist[(size_t)pr.peer];
+                    }
+                    if (!q) return fail(SPMVB200_ERR_INVALID, "in-process halo push: a peer rank has no executor");
+                    SPMV_TRY(wait_ready(bs, q, Ready::Iteration, k));
+                    target = q->X[push_buf];
+                } else {
+                    SPMV_TRY(spin_until(&d->shm[pr.peer].xready_issued, k + 1, "its previous step (halo push)"));
+                    SPMV_CUDA(cudaStreamWaitEvent(bs, d->peer_xready[slot(k)][(size_t)pr.peer], 0));
+                    target = d->peer_X[push_buf][(size_t)pr.peer];
+                }
+                b.A->push_y[t] = target + d->s + b.b;  // same global index in the peer's buffer
+                b.A->push_lo[t] = pr.lo;
+                b.A->push_hi[t] = pr.hi;
+                t++;
+            }
+        }
+        const int rc = spmvb200_spmv(b.A);
+        for (int t = 0; t < 2; t++) { b.A->push_y[t] = nullptr; b.A->push_lo[t] = b.A->push_hi[t] = 0; }
+        SPMV_TRY(rc);
     }
     return 0;
 }
@@ -617,6 +686,10 @@ int ensure_plan(spmvb200_dist_t d)
     for (int q = 0; q < g.nranks; q++)
         if (!g.need_set[(size_t)q]) return fail(SPMVB200_ERR_INVALID, "in-process communicator: create the executor of every rank before the first step");
     finalize_plan(d, g.need_lo.data(), g.need_hi.data());
+    if (d->want_push) {
+        d->push_active = build_push_lists(d);
+        if (!d->push_active) d->push.clear();
+    }
     return 0;
 }
 
@@ -630,15 +703,17 @@ int step(spmvb200_dist_t d, double alpha)
     // blocks that need no remote x
     SPMV_CUDA(cudaStreamWaitEvent(d->s_int, d->e_bnd[slot(k - 1)], 0));
     SPMV_TRY(wait_slice_readers(d, d->s_int, k - 1));
-    SPMV_TRY(launch_blocks(d, false, d->X[cur], d->X[nxt] + d->s, alpha));
+    const int push_buf = d->push_active ? nxt : -1;
+    SPMV_TRY(launch_blocks(d, false, d->X[cur], d->X[nxt] + d->s, alpha, push_buf, k));
     SPMV_CUDA(cudaEventRecord(d->e_int[slot(k)], d->s_int));
     // blocks that do
     SPMV_CUDA(cudaStreamWaitEvent(d->s_bnd, d->e_exch[slot(k)], 0));
     SPMV_CUDA(cudaStreamWaitEvent(d->s_bnd, d->e_int[slot(k - 1)], 0));
     SPMV_TRY(wait_slice_readers(d, d->s_bnd, k - 1));
     if (d->any_accumulate) SPMV_CUDA(cudaStreamWaitEvent(d->s_bnd, d->e_int[slot(k)], 0));
-    SPMV_TRY(launch_blocks(d, true, d->X[cur], d->X[nxt] + d->s, alpha));
+    SPMV_TRY(launch_blocks(d, true, d->X[cur], d->X[nxt] + d->s, alpha, push_buf, k));
     SPMV_CUDA(cudaEventRecord(d->e_bnd[slot(k)], d->s_bnd));
+    if (d->push_active) d->halo_by_push = k + 1;  // the neighbours hold their halo of x_(k+1) once their wait on e_xready passes
     if (d->peer) {  // "this rank's slice of x_(k+1) is complete", for the ranks that will pull from it
         SPMV_CUDA(cudaStreamWaitEvent(d->s_bnd, d->e_int[slot(k)], 0));
         SPMV_CUDA(cudaEventRecord(d->e_xready[slot(k + 1)], d->s_bnd));
@@ -857,6 +932,7 @@ try {
     d->need_lo = col_max < 0 ? 0 : col_min;
     d->need_hi = col_max < 0 ? 0 : col_max + 1;
     d->wanted_mode = exchange;
+    d->want_push = (flags & SPMVB200_DIST_PEER_PUSH) != 0 && P > 1;
     auto add = [&](spmvb200_matrix_t A, int64_t b, int64_t e, bool remote, bool accumulate, bool owned) -> int {
         if (format != SPMVB200_CSR) {
             spmvb200_info bi;
@@ -930,7 +1006,8 @@ try {
         std::vector<int64_t> lo((size_t)P), hi((size_t)P);
         for (int q = 0; q < P; q++) { lo[(size_t)q] = all[(size_t)2 * q]; hi[(size_t)q] = all[(size_t)2 * q + 1]; }
         finalize_plan(d, lo.data(), hi.data());
-        if (flags & SPMVB200_DIST_PEER_COPY) SPMV_TRY(setup_peer(d));
+        if (flags & (SPMVB200_DIST_PEER_COPY | SPMVB200_DIST_PEER_PUSH)) SPMV_TRY(setup_peer(d));
+        if (flags & SPMVB200_DIST_PEER_PUSH) SPMV_TRY(setup_push(d));
         comm->executors++;
     }
     // `local` changes hands only now that nothing can fail any more: until here a failure leaves it with the caller
@@ -952,6 +1029,7 @@ try {
     SPMV_TRY(sync_all(d));
     if (d->rows > 0)
         SPMV_CUDA(cudaMemcpy(d->X[d->k & 1] + d->s, x, sizeof(double) * (size_t)d->rows, cudaMemcpyHostToDevice));
+    d->halo_by_push = -1;  // this x did not come out of the kernels: the next exchange copies
     if (d->peer) {
         // the other ranks pull this slice without asking: nobody may proceed before every slice is in place
         // (spmvb200_dist_set_x is collective with the peer-copy transport)
@@ -1050,6 +1128,7 @@ try {
         }
     }
     SPMV_TRY(sync_all(d));
+    d->halo_by_push = -1;
     const bool threads_meet = d->comm->local && d->P > 1;  // one host thread per rank: they meet once per step
     if (d->P > 1) SPMV_TRY(spmvb200_comm_barrier(d->comm));
     SPMV_CUDA(cudaEventRecord(d->t0, d->s_h2d));
@@ -1117,6 +1196,7 @@ try {
     info->device_bytes = dev;
     info->launches_per_step = launches;
     info->steps_done = d->k;
+    info->halo_push = d->push_active ? 1 : 0;
     return 0;
 }
 SPMV_ABI_CATCH

@@ -99,11 +99,12 @@ int csr_ensure_row_major(Matrix * m)
     return 0;
 }
 
-template <typename OffT, int U, int THREADS>
+template <typename OffT, int U, int THREADS, bool PUSH = false>
 __global__ void __launch_bounds__(THREADS, (U <= 4 ? 2048 : 1024) / THREADS)
 csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
                   const int32_t * __restrict__ scol, const double * __restrict__ sval, const double * __restrict__ x,
-                  double * __restrict__ y, const double * __restrict__ y_in_host, double * __restrict__ y_out_host)
+                  double * __restrict__ y, const double * __restrict__ y_in_host, double * __restrict__ y_out_host,
+                  double * push0, int64_t push0_lo, int64_t push0_hi, double * push1, int64_t push1_lo, int64_t push1_hi)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
@@ -156,7 +157,19 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
         return;
     }
     // a lane owns its whole row: y = alpha*A*x is a plain store (no clearing pass, no read of y)
-    if (store) { if (i < rows) y[i] = __dmul_rn(alpha, z); }
+    if (store) {
+        if (i < rows) {
+            const double v = __dmul_rn(alpha, z);
+            y[i] = v;
+            // Fused halo push of the row-partitioned mode: the rows a neighbouring rank's rows reference are stored into
+            // that rank's x buffer as well -- a peer-mapped pointer, the store travels over NVLink -- so the exchange of
+            // the next step has nothing left to copy.  Consecutive lanes write consecutive addresses (256 B per warp).
+            if (PUSH) {
+                if (i >= push0_lo && i < push0_hi) push0[i] = v;
+                if (i >= push1_lo && i < push1_hi) push1[i] = v;
+            }
+        }
+    }
     else if (len > 0) red_add_f64(y + i, __dmul_rn(alpha, z));
 }
 
@@ -244,13 +257,24 @@ int launch_csr_sliced(Matrix * m)
     SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, row0, row1,  \
                             rm.independent, store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col,          \
                             (const double *)m->slice_val, (const double *)m->x, m->y, (const double *)m->host_y_in,      \
-                            m->host_y_out))
+                            m->host_y_out, m->push_y[0], m->push_lo[0], m->push_hi[0], m->push_y[1], m->push_lo[1],       \
+                            m->push_hi[1]))
+#define SPMV_SLICED_P(OFF)                                                                                                 \
+    SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, 4, 128, true>, (unsigned)grid, 128u, 0, m->stream, rm.pdl, row0, row1,  \
+                            rm.independent, store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col,          \
+                            (const double *)m->slice_val, (const double *)m->x, m->y, (const double *)m->host_y_in,      \
+                            m->host_y_out, m->push_y[0], m->push_lo[0], m->push_hi[0], m->push_y[1], m->push_lo[1],       \
+                            m->push_hi[1]))
 #define SPMV_SLICED_T(UU, TT)                                             \
     do {                                                                  \
         if (m->off64) SPMV_SLICED(int64_t, UU, TT);                       \
         else SPMV_SLICED(uint32_t, UU, TT);                               \
     } while (0)
-    if (threads == 128) {
+    if (m->push_y[0] || m->push_y[1]) {  // fused halo push: its own instantiation, so that the plain kernel keeps its 32 registers
+        if (threads != 128 || batch != 4 || !store) return fail(SPMVB200_ERR_UNSUPPORTED, "halo push needs the default sliced kernel in store mode");
+        if (m->off64) SPMV_SLICED_P(int64_t);
+        else SPMV_SLICED_P(uint32_t);
+    } else if (threads == 128) {
         if (batch == 4) SPMV_SLICED_T(4, 128);
         else if (batch == 8) SPMV_SLICED_T(8, 128);
         else if (batch == 2) SPMV_SLICED_T(2, 128);
@@ -263,6 +287,7 @@ int launch_csr_sliced(Matrix * m)
         return fail(SPMVB200_ERR_INVALID, "sliced kernel: csr.threads 128 (csr.batch 2|4|8) or 256|512 (csr.batch 4)");
     }
 #undef SPMV_SLICED_T
+#undef SPMV_SLICED_P
 #undef SPMV_SLICED
     count_launch();
     return 0;

@@ -142,7 +142,7 @@ def split_rows(lo_end: int, hi_begin: int, rows: int):
 
 EXCHANGE = {"auto": 0, "allgather": 1, "halo": 2}
 EXCHANGE_NAMES = {v: k for k, v in EXCHANGE.items()}
-CONSUME_LOCAL, COLUMN_SPLIT, NO_OVERLAP, PEER_COPY = 1, 2, 4, 8
+CONSUME_LOCAL, COLUMN_SPLIT, NO_OVERLAP, PEER_COPY, PEER_PUSH = 1, 2, 4, 8, 16
 
 
 def _check(rc: int) -> None:
@@ -246,11 +246,11 @@ class DistributedSpMV:
     """spmvb200_dist_t: iterated x <- alpha A x on this rank's row block (see include/spmv_b200.h)."""
 
     def __init__(self, comm: Comm, local, starts, mode: str = "auto", fmt: int = 0, column_split: bool = False,
-                 overlap: bool = True, consume_local: bool = False, peer_copy: bool = False):
+                 overlap: bool = True, consume_local: bool = False, peer_copy: bool = False, peer_push: bool = False):
         self.comm = comm
         self.starts = np.ascontiguousarray(starts, dtype=np.int64)
         flags = ((CONSUME_LOCAL if consume_local else 0) | (COLUMN_SPLIT if column_split else 0) | (0 if overlap else NO_OVERLAP)
-                 | (PEER_COPY if peer_copy else 0))
+                 | (PEER_COPY if peer_copy else 0) | (PEER_PUSH if peer_push else 0))
         h = C.c_void_p()
         _check(_abi.lib().spmvb200_dist_create(comm._h, local._h, self.starts.ctypes.data_as(i64p), EXCHANGE[mode], int(fmt),
                                                flags, C.byref(h)))

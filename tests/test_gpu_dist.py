@@ -85,6 +85,53 @@ def test_stencil_iteration_matches_the_oracle(oracle, P, mode):
     assert np.array_equal(got, oracle.csr_spmv(O, oracle.csr_spmv(O, xp)))
 
 
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_fused_halo_push(oracle, P):
+    """SPMVB200_DIST_PEER_PUSH: the sliced CSR kernel that computes the rows a neighbour references stores them into the
+    neighbour's x buffer as well, so from the second step on the exchange copies nothing.  Same numbers as the copying
+    exchange, bit for bit on exact data, over many steps (every step consumes the halo the previous one pushed)."""
+    nx, ny, nz = 12, 10, 4 * max(P, 2) + 3
+    N = nx * ny * nz
+    i, j, a = stencil_entries(2, nx, ny, nz)
+    O = oracle.csr(N, N, i, j, a)
+    starts = D.partition_rows_ref(N, P)
+
+    def engines(push):
+        comms = D.Comm.local(P, [0] * P)
+        out = []
+        for r in range(P):
+            local = sp.generators.stencil(sp.STENCIL_3D27, nx, ny, nz, fmt=sp.CSR, row_begin=int(starts[r]), row_end=int(starts[r + 1]))
+            out.append(D.DistributedSpMV(comms[r], local, starts, mode="halo", consume_local=True, peer_push=push))
+        return out
+
+    pushers, copiers = engines(True), engines(False)
+    xp = 1.0 + (np.arange(N) % 7) / 8.0
+    steps = 6
+    got = run_iteration(pushers, xp, starts, steps, 1.0 / 4.0)  # powers of two: still exact
+    want = run_iteration(copiers, xp, starts, steps, 1.0 / 4.0)
+    assert all(e.info["halo_push"] == 1 for e in pushers) and all(e.info["halo_push"] == 0 for e in copiers)
+    ref = xp
+    for _ in range(steps):
+        ref = 0.25 * oracle.csr_spmv(O, ref)
+    assert np.array_equal(want, ref) and np.array_equal(got, ref)
+    # set_x in between: the next exchange copies again, then the pushes take over
+    x0 = np.random.default_rng(3).uniform(-1, 1, N)
+    got = run_iteration(pushers, x0, starts, 5, 1.0 / 52.0)
+    ref, bound = iterate_oracle(oracle, O, x0, 5, 1.0 / 52.0)
+    assert np.all(np.abs(got - ref) <= TOL * 6 * bound)
+    # a block that is not CSR cannot push: the flag is ignored, the copies stay
+    comms = D.Comm.local(2, [0, 0])
+    s2 = D.partition_rows_ref(N, 2)
+    ell = [D.DistributedSpMV(comms[r], sp.generators.stencil(sp.STENCIL_3D27, nx, ny, nz, fmt=sp.CSR, row_begin=int(s2[r]), row_end=int(s2[r + 1])),
+                             s2, mode="halo", fmt=sp.ELL, consume_local=True, peer_push=True) for r in range(2)]
+    got = run_iteration(ell, xp, s2, 3, 0.25)
+    assert all(e.info["halo_push"] == 0 for e in ell)
+    ref = xp
+    for _ in range(3):
+        ref = 0.25 * oracle.csr_spmv(O, ref)
+    assert np.array_equal(got, ref)
+
+
 def test_uneven_partition_and_unstructured_rows(oracle):
     """Balanced-nnz cut of a ragged matrix: no band, so no interior rows; automatic mode picks the all-gather."""
     rng = np.random.default_rng(21)

@@ -72,22 +72,25 @@ def main():
     ref_exact = full * (full * xp)
     absA = 52.0  # row sums of |A| are at most 52
     tol = 1e-12 * (args.iters + 1) * np.abs(x0).max()
-    for mode in ("halo", "allgather"):
-        for peer in (False, True):
-            local = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR, row_begin=s, row_end=e)
-            eng = D.DistributedSpMV(comm, local, starts, mode=mode, consume_local=True, peer_copy=peer)
-            eng.set_x(x0[s:e])
-            for _ in range(args.iters):
-                eng.step(alpha)
-            got = gather(comm, eng.get_x(), starts, rank, world)
-            err = float(np.abs(got - ref).max())
-            report(f"27-point {n}^3, {mode}, {'peer copy' if peer else 'NCCL'}, {args.iters} steps", err <= tol, f"max|err|={err:.3e}")
-            eng.set_x(xp[s:e])
-            eng.step(1.0)
-            eng.step(1.0)
-            got = gather(comm, eng.get_x(), starts, rank, world)
-            report(f"27-point {n}^3, {mode}, {'peer copy' if peer else 'NCCL'}, exact data", bool(np.array_equal(got, ref_exact)))
-            eng.destroy()
+    for mode, peer, push in (("halo", False, False), ("halo", True, False), ("halo", True, True), ("allgather", False, False),
+                             ("allgather", True, False)):
+        local = sp.generators.stencil(sp.STENCIL_3D27, n, n, n, fmt=sp.CSR, row_begin=s, row_end=e)
+        eng = D.DistributedSpMV(comm, local, starts, mode=mode, consume_local=True, peer_copy=peer, peer_push=push)
+        how = "fused push" if push else "peer copy" if peer else "NCCL"
+        if push:
+            report(f"27-point {n}^3, halo push is in effect", eng.info["halo_push"] == 1)
+        eng.set_x(x0[s:e])
+        for _ in range(args.iters):
+            eng.step(alpha)
+        got = gather(comm, eng.get_x(), starts, rank, world)
+        err = float(np.abs(got - ref).max())
+        report(f"27-point {n}^3, {mode}, {how}, {args.iters} steps", err <= tol, f"max|err|={err:.3e}")
+        eng.set_x(xp[s:e])
+        eng.step(1.0)
+        eng.step(1.0)
+        got = gather(comm, eng.get_x(), starts, rank, world)
+        report(f"27-point {n}^3, {mode}, {how}, exact data", bool(np.array_equal(got, ref_exact)))
+        eng.destroy()
     del full
 
     # ---- R-MAT row blocks of equal non-zeros -----------------------------------------------------------------------------
