@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPMVB200_VERSION 100 /* 0.1.0 */
+#define SPMVB200_VERSION 200 /* 0.2.0: + spmvb200_comm_*, spmvb200_dist_*, spmvb200_exchange_plan, spmvb200_partition_rows_weighted */
 
 typedef enum {
     SPMVB200_OK = 0,
