@@ -541,6 +541,16 @@ def run_single_gpu(args):
                     "target": "BASELINE: >= 0.70 of 8 TB/s"}
             except Exception as e:
                 targets[name] = {"error": str(e)}
+        # the yardstick for the isolated figures: the same event-pair protocol around a plain device-to-device copy that
+        # moves the same 80 MB of DRAM traffic (40 MB read + 40 MB written), L2-cold -- no kernel of ours involved
+        try:
+            cp = sp.time_copy(40_000_000, copies=8, reps=300, warmup=30)
+            targets["isolated_copy_yardstick"] = {
+                "what": "cudaMemcpyAsync device-to-device of 40 MB (80 MB of DRAM traffic, like one config-1 SpMV), event pair per copy, "
+                        "rotating over 8 buffer pairs", "us_median": float(np.median(cp)) * 1e3, "us_min": float(np.min(cp)) * 1e3,
+                "frac_of_8TBs": 80e6 / (float(np.median(cp)) * 1e-3) / 1e9 / NOMINAL_HBM_GBS}
+        except Exception as e:
+            targets["isolated_copy_yardstick"] = {"error": str(e)}
         line["targets"] = targets
         extra = []
         for name in ("c1_coo", "c1_hyb", "c2_ell", "c2_csr", "c3_coo", "c3_coo_atomic", "c4_hyb"):

@@ -282,6 +282,9 @@ int spmvb200_time_rotating(const spmvb200_matrix_t *ms, int n, int warmup, int s
  * D2H y, synchronise), k round-robin; total_ms = CUDA-event time around all `steps` steps. */
 int spmvb200_time_host_rotating(const spmvb200_matrix_t *ms, int n, const double *const *xs,
                                 double *const *ys, int warmup, int steps, float *total_ms);
+/* Yardstick for the isolated-launch figures: the event-pair protocol of spmvb200_time around a plain device-to-device
+ * cudaMemcpyAsync of `bytes` (2 * bytes of DRAM traffic), rotating over `copies` buffer pairs (L2-cold); ms[r] per copy. */
+int spmvb200_time_copy(int64_t bytes, int copies, int warmup, int reps, float *ms);
 /* Options (0 = automatic unless noted):
  *   semantics   "beta0" 1: y = A*x instead of y += A*x.
  *               "independent_launches": y is updated with reductions, so two launches need ordering only

@@ -612,6 +612,13 @@ def time_rotating(mats, steps: int, warmup: int = 3, per_launch: bool = False):
     return float(total.value), per
 
 
+def time_copy(nbytes: int, copies: int = 8, reps: int = 200, warmup: int = 20):
+    """Per-copy milliseconds of an isolated device-to-device cudaMemcpyAsync of `nbytes` (event pair per copy, L2-cold)."""
+    ms = np.zeros(reps, np.float32)
+    _check(_abi.lib().spmvb200_time_copy(int(nbytes), int(copies), int(warmup), int(reps), _p(ms, f32p)))
+    return ms
+
+
 def time_host_rotating(mats, xs, ys, steps: int, warmup: int = 1) -> float:
     """End-to-end steps with host buffers (H2D x, y; kernel; D2H y); returns total milliseconds."""
     n = len(mats)

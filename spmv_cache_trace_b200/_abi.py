@@ -124,6 +124,7 @@ SIGNATURES = {
     "spmvb200_sync": (C.c_int, [vp]),
     "spmvb200_spmv_host": (C.c_int, [vp, f64p, f64p]),
     "spmvb200_time": (C.c_int, [vp, C.c_int, C.c_int, f32p]),
+    "spmvb200_time_copy": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, f32p]),
     "spmvb200_time_rotating": (C.c_int, [vpp, C.c_int, C.c_int, C.c_int, f32p, f32p]),
     "spmvb200_time_host_rotating": (C.c_int, [vpp, C.c_int, C.POINTER(f64p), C.POINTER(f64p), C.c_int, C.c_int,
                                               f32p]),

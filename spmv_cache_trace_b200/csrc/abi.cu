@@ -1317,6 +1317,51 @@ try {
 }
 SPMV_ABI_CATCH
 
+// Yardstick for "isolated launch" figures: the same event-pair protocol around a plain device-to-device cudaMemcpyAsync
+// that moves `bytes` (read + write = 2 * bytes of DRAM traffic), rotating over `copies` source/destination pairs so that
+// nothing is found in L2.  What this takes is what the protocol + one DRAM round trip cost with no kernel of ours involved.
+int spmvb200_time_copy(int64_t bytes, int copies, int warmup, int reps, float * ms)
+try {
+    if (bytes < 1 || copies < 1 || warmup < 0 || reps < 1 || !ms) return fail(SPMVB200_ERR_INVALID, "bad argument");
+    std::vector<char *> src((size_t)copies, nullptr), dst((size_t)copies, nullptr);
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
+    auto cleanup = [&] {
+        for (char * p : src) if (p) cudaFree(p);
+        for (char * p : dst) if (p) cudaFree(p);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (s) cudaStreamDestroy(s);
+    };
+    auto run = [&]() -> int {
+        SPMV_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        SPMV_CUDA(cudaEventCreate(&e0));
+        SPMV_CUDA(cudaEventCreate(&e1));
+        for (int c = 0; c < copies; c++) {
+            SPMV_CUDA(cudaMalloc((void **)&src[(size_t)c], (size_t)bytes));
+            SPMV_CUDA(cudaMalloc((void **)&dst[(size_t)c], (size_t)bytes));
+            SPMV_CUDA(cudaMemsetAsync(src[(size_t)c], 1, (size_t)bytes, s));
+        }
+        for (int w = 0; w < warmup; w++)
+            SPMV_CUDA(cudaMemcpyAsync(dst[(size_t)(w % copies)], src[(size_t)(w % copies)], (size_t)bytes, cudaMemcpyDeviceToDevice, s));
+        SPMV_CUDA(cudaStreamSynchronize(s));
+        for (int r = 0; r < reps; r++) {
+            const size_t c = (size_t)((warmup + r) % copies);
+            SPMV_CUDA(cudaEventRecord(e0, s));
+            SPMV_CUDA(cudaMemcpyAsync(dst[c], src[c], (size_t)bytes, cudaMemcpyDeviceToDevice, s));
+            SPMV_CUDA(cudaEventRecord(e1, s));
+            SPMV_CUDA(cudaEventSynchronize(e1));
+            SPMV_CUDA(cudaEventElapsedTime(&ms[r], e0, e1));
+        }
+        return 0;
+    };
+    rc = run();
+    cleanup();
+    return rc;
+}
+SPMV_ABI_CATCH
+
 static int64_t * option_slot(Matrix * m, const char * key)
 {
     if (!strcmp(key, "csr.tile")) return &m->opt_csr_tile;
