@@ -320,11 +320,25 @@ int dist_free(spmvb200_dist_t d)
     for (cudaStream_t s : {d->s_int, d->s_bnd, d->s_comm, d->s_h2d, d->s_d2h})
         if (s) cudaStreamSynchronize(s);
     if (d->comm && d->comm->local && d->comm->group) {
-        std::lock_guard<std::mutex> lk(d->comm->group->mu);
-        if ((size_t)d->rank < d->comm->group->dist.size() && d->comm->group->dist[(size_t)d->rank] == d) {
-            d->comm->group->dist[(size_t)d->rank] = nullptr;
-            d->comm->group->need_set[(size_t)d->rank] = 0;
+        // the other ranks of the process pull from (and, with the fused push, store into) this rank's buffers: whatever
+        // they have queued must be done before the buffers go away
+        std::vector<spmvb200_dist_t> others;
+        {
+            std::lock_guard<std::mutex> lk(d->comm->group->mu);
+            for (spmvb200_dist_t o : d->comm->group->dist)
+                if (o && o != d) others.push_back(o);
+            if ((size_t)d->rank < d->comm->group->dist.size() && d->comm->group->dist[(size_t)d->rank] == d) {
+                d->comm->group->dist[(size_t)d->rank] = nullptr;
+                d->comm->group->need_set[(size_t)d->rank] = 0;
+            }
+            if (others.empty()) d->comm->group->wanted_mode = -1;  // the last executor of this generation
         }
+        for (spmvb200_dist_t o : others) {
+            cudaSetDevice(o->device);
+            for (cudaStream_t s : {o->s_comm, o->s_int, o->s_bnd})
+                if (s) cudaStreamSynchronize(s);
+        }
+        cudaSetDevice(d->device);
     }
     if (d->peer) {
         for (int q = 0; q < d->P; q++) {
@@ -685,6 +699,7 @@ int ensure_plan(spmvb200_dist_t d)
     std::lock_guard<std::mutex> lk(g.mu);
     for (int q = 0; q < g.nranks; q++)
         if (!g.need_set[(size_t)q]) return fail(SPMVB200_ERR_INVALID, "in-process communicator: create the executor of every rank before the first step");
+    if (g.wanted_mode == SPMVB200_EXCHANGE_ALLGATHER) d->wanted_mode = SPMVB200_EXCHANGE_ALLGATHER;  // one plan for all ranks
     finalize_plan(d, g.need_lo.data(), g.need_hi.data());
     if (d->want_push) {
         d->push_active = build_push_lists(d);
@@ -993,18 +1008,26 @@ try {
         g.need_lo[(size_t)rank] = d->need_lo;
         g.need_hi[(size_t)rank] = d->need_hi;
         g.need_set[(size_t)rank] = 1;
+        if (d->wanted_mode == SPMVB200_EXCHANGE_ALLGATHER || g.wanted_mode < 0) g.wanted_mode = d->wanted_mode;
     } else {
         NcclApi * nc = nccl_api();
-        std::vector<int64_t> all((size_t)2 * P);
-        int64_t * dbuf = reinterpret_cast<int64_t *>(comm->scratch);  // 64 doubles: up to 32 ranks
-        if (P > 32) return fail(SPMVB200_ERR_UNSUPPORTED, "more than 32 ranks");
-        const int64_t mine[2] = {d->need_lo, d->need_hi};
-        SPMV_CUDA(cudaMemcpyAsync(dbuf + 2 * rank, mine, sizeof mine, cudaMemcpyHostToDevice, comm->stream));
-        SPMV_NCCL(nc->AllGather(dbuf + 2 * rank, dbuf, 2, ncclInt64, comm->nccl, comm->stream));
+        std::vector<int64_t> all((size_t)3 * P);
+        int64_t * dbuf = reinterpret_cast<int64_t *>(comm->scratch);  // 64 doubles: up to 21 ranks
+        if (3 * P > 64) return fail(SPMVB200_ERR_UNSUPPORTED, "more than 21 ranks");
+        const int64_t mine[3] = {d->need_lo, d->need_hi, d->wanted_mode};
+        SPMV_CUDA(cudaMemcpyAsync(dbuf + 3 * rank, mine, sizeof mine, cudaMemcpyHostToDevice, comm->stream));
+        SPMV_NCCL(nc->AllGather(dbuf + 3 * rank, dbuf, 3, ncclInt64, comm->nccl, comm->stream));
         SPMV_CUDA(cudaMemcpyAsync(all.data(), dbuf, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, comm->stream));
         SPMV_CUDA(cudaStreamSynchronize(comm->stream));
         std::vector<int64_t> lo((size_t)P), hi((size_t)P);
-        for (int q = 0; q < P; q++) { lo[(size_t)q] = all[(size_t)2 * q]; hi[(size_t)q] = all[(size_t)2 * q + 1]; }
+        for (int q = 0; q < P; q++) {
+            lo[(size_t)q] = all[(size_t)3 * q]; hi[(size_t)q] = all[(size_t)3 * q + 1];
+            // every rank must run the same plan: a rank whose block allows no column analysis (all-gather) decides for all
+            if (all[(size_t)3 * q + 2] == SPMVB200_EXCHANGE_ALLGATHER) d->wanted_mode = SPMVB200_EXCHANGE_ALLGATHER;
+        }
+        for (int q = 0; q < P; q++)
+            if (d->wanted_mode != SPMVB200_EXCHANGE_ALLGATHER && all[(size_t)3 * q + 2] != d->wanted_mode)
+                return fail(SPMVB200_ERR_INVALID, "the ranks ask for different exchange modes");
         finalize_plan(d, lo.data(), hi.data());
         if (flags & (SPMVB200_DIST_PEER_COPY | SPMVB200_DIST_PEER_PUSH)) SPMV_TRY(setup_peer(d));
         if (flags & SPMVB200_DIST_PEER_PUSH) SPMV_TRY(setup_push(d));
