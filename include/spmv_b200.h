@@ -303,7 +303,9 @@ int spmvb200_time_copy(int64_t bytes, int copies, int warmup, int reps, float *m
  *               rows rebuild the row numbers from row_ptr instead of the row map), 5 sliced (lane per row on a slot-major copy of
  *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" (default 1) = free the row-major
  *               column_index/value once that copy exists, so the matrix is resident once -- they are rebuilt on
- *               demand by export, convert, row_block, column_span and the other kernels; 0 = keep both copies); "csr.probe" 1 = regular traffic
+ *               demand by export, convert, row_block, column_span and the other kernels; 0 = keep both copies); "csr.rmw" (sliced kernel, y += A*x): the lane that owns a row adds to y
+ *               with a plain load and store instead of a reduction -- the launches are then ordered; 1 = on (default off:
+ *               measured slower); "csr.probe" 1 = regular traffic
  *               (y_i += sum a_k, values streamed, no gather), 2 = irregular traffic (y_i += sum x[j_k], the
  *               gather alone): spmv_regular_traffic / spmv_irregular_traffic of the reference
  *               (csr-matrix-spmv.cpp:35-61, 119-146); "csr.algo" 0 = automatic: sliced when the mean row has

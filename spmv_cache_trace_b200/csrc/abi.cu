@@ -323,7 +323,7 @@ void plan_run(Matrix * m, bool conservative)
     // the buffers swapped by bind_x / bind_y; or anything the record cannot vouch for) is therefore issued without
     // the PDL attribute: ordinary stream serialisation, the whole predecessor retired before the first CTA starts.
     if ((!r.valid || overlaps(x0, x1, r.wlo, r.whi)) && m->opt_pdl != 2) m->run_pdl = false;  // ("pdl" = 2: experiments)
-    if (!conservative && m->run_pdl && !m->opt_beta0 && !m->run_beta0 &&
+    if (!conservative && m->run_pdl && !m->opt_beta0 && !m->run_beta0 && !m->run_rmw &&
         (m->opt_independent > 0 || (m->opt_independent == 0 && proven))) {
         m->run_independent = true;  // validity of the record is unchanged; its ranges grow
         r.wlo = r.whi > r.wlo ? std::min(r.wlo, y0) : y0;
@@ -338,7 +338,7 @@ void plan_run(Matrix * m, bool conservative)
     r = StreamRec{};
     r.valid = !conservative;
     r.wlo = y0; r.whi = y1; r.rlo = x0; r.rhi = x1;
-    if (m->run_beta0 || m->opt_beta0) { r.slo = y0; r.shi = y1; }
+    if (m->run_beta0 || m->opt_beta0 || m->run_rmw) { r.slo = y0; r.shi = y1; }  // plain stores: reductions must not overtake them
 }
 
 // Entry check of every API call that is not an SpMV launch: whatever it enqueues is unknown to the record.
@@ -1003,9 +1003,15 @@ static int launch_format(Matrix * m)
 static int launch(Matrix * m)
 {
     m->run_beta0 = m->opt_beta0 != 0;
+    // "csr.rmw" = 1: y += A*x with the sliced CSR kernel, the lane that owns a row adds to y with a plain load and store
+    // instead of a reduction (the reductions make L2 write every y sector back twice: 1.97 GB written for 1.07 GB of y on
+    // config 5); such launches must be ordered.  Opt-in: it measured SLOWER (config 5: 7.69 vs 7.41 ms; 27-point 256^3:
+    // 0.929 vs 0.908 ms) -- the load of y_old sits at the end of every lane's dependency chain, the reduction does not.
+    m->run_rmw = !m->run_beta0 && m->format == SPMVB200_CSR && m->opt_csr_rmw > 0 && csr_uses_sliced_kernel(m);
     plan_run(m, false);
     const int rc = launch_format(m);
     m->run_beta0 = false;
+    m->run_rmw = false;
     return rc;
 }
 
@@ -1375,6 +1381,7 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.spare_ctas")) return &m->opt_csr_spare;
     if (!strcmp(key, "csr.batch")) return &m->opt_csr_batch;
     if (!strcmp(key, "csr.probe")) return &m->opt_csr_probe;
+    if (!strcmp(key, "csr.rmw")) return &m->opt_csr_rmw;
     if (!strcmp(key, "csr.entries")) return &m->opt_csr_entries;
     if (!strcmp(key, "csr.rowptr_path")) return &m->opt_csr_rowptr_path;
     if (!strcmp(key, "csr.drop_row_major")) return &m->opt_csr_drop;

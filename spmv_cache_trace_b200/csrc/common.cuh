@@ -150,6 +150,8 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_batch = 0;    // sliced kernel: slots in flight per lane (2, 4, 8), 0 = auto
     int64_t opt_csr_rowptr_path = 0;  // flat kernel, matrices with empty rows: 1 = rebuild row numbers from row_ptr (MASK = false path)
     int64_t opt_csr_entries = 0;  // flat kernel: entries per lane (4, 8), 0 = auto
+    int64_t opt_csr_rmw = 0;      // sliced kernel, y += A*x: 1 = the owning lane updates y with a plain read-modify-write instead of a
+                                  // reduction (needs the launches ordered); off by default: measured slower
     int64_t opt_csr_probe = 0;    // 1 regular traffic (values only), 2 irregular traffic (x gather only): csr-matrix-spmv.cpp:35-61
     int64_t opt_csr_drop = 1;     // sliced kernel: free the row-major column_index/value once the slot-major copy exists (0 = keep both)
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
@@ -173,6 +175,7 @@ struct spmvb200_matrix_s {
     // per-launch decisions of plan_run() (abi.cu): launch attribute and whether the kernel may skip
     // griddepcontrol.wait because nothing in flight on its stream writes its x or reads its y
     bool run_pdl = true, run_independent = false;
+    bool run_rmw = false;         // this launch updates y with plain loads and stores by the lanes that own the rows (sliced CSR)
     bool run_beta0 = false;       // this launch computes y = alpha*A*x: kernels that own whole rows store, the others clear y first
     double alpha = 1.0;           // y += alpha*A*x (spmvb200_set_alpha); 1.0 is exact, the reference's semantics
     bool aux_dirty = false;       // an auxiliary table was just (re)built on the stream: serialise the next launch

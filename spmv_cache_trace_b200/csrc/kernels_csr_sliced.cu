@@ -157,7 +157,7 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
         return;
     }
     // a lane owns its whole row: y = alpha*A*x is a plain store (no clearing pass, no read of y)
-    if (store) {
+    if (store == 1) {
         if (i < rows) {
             const double v = __dmul_rn(alpha, z);
             y[i] = v;
@@ -169,6 +169,9 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
                 if (i >= push1_lo && i < push1_hi) push1[i] = v;
             }
         }
+    }
+    else if (store == 2) {  // y += ...: plain read-modify-write by the lane that owns the row (the launch is ordered)
+        if (len > 0) y[i] = __dadd_rn(y[i], __dmul_rn(alpha, z));
     }
     else if (len > 0) red_add_f64(y + i, __dmul_rn(alpha, z));
 }
@@ -250,7 +253,7 @@ int launch_csr_sliced(Matrix * m)
     if (grid > INT_MAX) return fail(SPMVB200_ERR_OVERFLOW, "CSR matrix too large for one launch");
     if (grid <= 0) return 0;
     const RunMode rm = run_mode(m);
-    const int store = (m->run_beta0 && !m->host_y_out) ? 1 : 0;
+    const int store = (m->run_beta0 && !m->host_y_out) ? 1 : (m->run_rmw && !m->host_y_out && !rm.independent) ? 2 : 0;
     m->run_beta0 = false;
     const int batch = (int)(m->opt_csr_batch ? m->opt_csr_batch : 4);
 #define SPMV_SLICED(OFF, UU, TT)                                                                                          \
@@ -271,7 +274,7 @@ int launch_csr_sliced(Matrix * m)
         else SPMV_SLICED(uint32_t, UU, TT);                               \
     } while (0)
     if (m->push_y[0] || m->push_y[1]) {  // fused halo push: its own instantiation, so that the plain kernel keeps its 32 registers
-        if (threads != 128 || batch != 4 || !store) return fail(SPMVB200_ERR_UNSUPPORTED, "halo push needs the default sliced kernel in store mode");
+        if (threads != 128 || batch != 4 || store != 1) return fail(SPMVB200_ERR_UNSUPPORTED, "halo push needs the default sliced kernel in store mode");
         if (m->off64) SPMV_SLICED_P(int64_t);
         else SPMV_SLICED_P(uint32_t);
     } else if (threads == 128) {

@@ -132,6 +132,29 @@ def test_fused_halo_push(oracle, P):
     assert np.array_equal(got, ref)
 
 
+def test_all_ranks_run_one_plan(oracle):
+    """A rank whose block allows no column analysis (here: an ELL block) needs the all-gather; the ranks that asked for
+    the halo plan must follow, or the exchange would not match."""
+    nx, ny, nz = 10, 9, 12
+    N = nx * ny * nz
+    i, j, a = stencil_entries(2, nx, ny, nz)
+    O = oracle.csr(N, N, i, j, a)
+    starts = D.partition_rows_ref(N, 3)
+    comms = D.Comm.local(3, [0, 0, 0])
+    engines = []
+    for r in range(3):
+        fmt = sp.ELL if r == 1 else sp.CSR
+        local = sp.generators.stencil(sp.STENCIL_3D27, nx, ny, nz, fmt=fmt, row_begin=int(starts[r]), row_end=int(starts[r + 1]))
+        engines.append(D.DistributedSpMV(comms[r], local, starts, mode="halo", consume_local=True))
+    xp = 1.0 + (np.arange(N) % 7) / 8.0
+    got = run_iteration(engines, xp, starts, 3, 0.5)
+    ref = xp
+    for _ in range(3):
+        ref = 0.5 * oracle.csr_spmv(O, ref)
+    assert np.array_equal(got, ref)
+    assert [e.info["exchange"] for e in engines] == ["allgather"] * 3
+
+
 def test_uneven_partition_and_unstructured_rows(oracle):
     """Balanced-nnz cut of a ragged matrix: no band, so no interior rows; automatic mode picks the all-gather."""
     rng = np.random.default_rng(21)

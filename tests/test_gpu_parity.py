@@ -1189,6 +1189,37 @@ def test_hot_column_coo_kernel(oracle, threads, entries, slots):
     assert R.kernel_name == "coo_warp4_kernel" and R.get_option("coo.hot_segments_built") == 0
 
 
+def test_sliced_csr_read_modify_write_accumulate(oracle):
+    """csr.rmw = 1: y += A*x with plain loads and stores by the lanes that own the rows (opt-in: it measured slower than the
+    reductions).  Such launches are ordered -- never overlapped -- and give the reference's numbers bit for bit."""
+    n = 40
+    i, j, a = stencil_entries(2, n, n, n)
+    N = n ** 3
+    O = oracle.csr(N, N, i, j, a)
+    rng = np.random.default_rng(12)
+    x, y0 = rng.uniform(-1, 1, N), rng.uniform(-1, 1, N)
+    ref = y0.copy()
+    for _ in range(4):
+        ref = oracle.csr_spmv(O, x, ref)
+    for rmw in (1, -1):
+        A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
+        A.set_option("csr.rmw", rmw)
+        A.set_x(x)
+        A.set_y(y0)
+        for k in range(4):
+            A.spmv()
+            if k > 0:
+                assert A.get_option("last_launch.overlapped") == (0 if rmw == 1 else 1)
+        assert A.kernel_name == "csr_sliced_kernel"
+        assert np.array_equal(A.get_y(), ref), f"csr.rmw {rmw}"  # one rounding of y_old + row sum either way
+    # alpha, and a reduction-based launch of another matrix on the same y must not overtake the plain stores
+    A.set_option("csr.rmw", 1)
+    A.set_alpha(0.5)
+    A.set_y(y0)
+    A.spmv()
+    assert_within(A.get_y(), y0 + 0.5 * oracle.csr_spmv(O, x), 0.5 * oracle.csr_abs_rowsum(O, x) + np.abs(y0), "rmw with alpha")
+
+
 def test_csr_spmv_host_pipelined_upload(oracle):
     """From 2^20 rows on, the host-buffer call of the sliced CSR kernel uploads x in pieces and launches each row chunk as
     soon as the largest column it references has arrived.  A banded matrix starts after two pieces; a matrix whose first
