@@ -83,6 +83,7 @@ void matrix_free(Matrix * m)
     cudaFree(m->ell_col); cudaFree(m->ell_val);
     cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
     cudaFree(m->coo_colh); cudaFree(m->coo_hot_cols); cudaFree(m->coo_seg);
+    if (m->x_tex) cudaDestroyTextureObject(m->x_tex);
     if (m->own_x) cudaFree(m->x);
     if (m->own_y) cudaFree(m->y);
     if (m->upload_stream) cudaStreamDestroy(m->upload_stream);

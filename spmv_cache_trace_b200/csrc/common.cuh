@@ -110,6 +110,8 @@ struct spmvb200_matrix_s {
     int coo_hot_h = 0, coo_nseg = 0;
     bool coo_hot_tried = false;        // the builder ran (and may have decided against the layout)
     double coo_hot_coverage = 0.0;     // fraction of the entries whose column is in its segment's table
+    cudaTextureObject_t x_tex = 0;     // (experiment "coo.xload" = 5 / 6) x as a linear texture, for the pointer below
+    const double * x_tex_ptr = nullptr;
 
     // pipelined host-buffer path of the sliced CSR kernel: largest column referenced by each of host_chunks row chunks
     int host_chunks = 0;
@@ -162,7 +164,7 @@ struct spmvb200_matrix_s {
     int64_t opt_coo_ctas = 0;
     int64_t opt_coo_algo = 0;     // 0 auto, 1 shared-memory staged (coo_segmented_kernel), 2 register-staged (coo_warp_kernel)
     int64_t opt_coo_items = 0;    // stripes of 32 entries per warp of coo_warp_kernel (2, 4, 8), 0 = auto
-    int64_t opt_coo_xload = 0;    // cache path of the x gather (ptx.cuh ld_x): 0 nc, 1 cg (L2 only), 2 nc no_allocate, 3 nc evict_last
+    int64_t opt_coo_xload = 0;    // cache path of the x gather (ptx.cuh ld_x): 0 nc, 1 cg (L2 only), 2 nc no_allocate, 3 nc evict_last, 4 cp.async, 5 texture, 6 texture + nc
     int64_t opt_coo_carveout = -1;     // >= 0: preferred shared-memory carve-out in percent (experiment: shrinks the L1)
     int64_t opt_coo_hot = 0;      // hot-column kernel: 0 / -1 off (default: it measured slower), 1 on, 2 on if the gathers are scattered
     int64_t opt_coo_hot_slots = 0;     // table size per segment (multiple of 1024, <= 27648), 0 = auto

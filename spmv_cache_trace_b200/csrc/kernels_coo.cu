@@ -176,7 +176,8 @@ coo_warp_kernel(int64_t n, int independent, const int32_t * __restrict__ row, co
 template <int WARPS, int XPATH = 0>
 __global__ void __launch_bounds__(WARPS * 32)
 coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, const int32_t * __restrict__ col,
-                 const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y, double alpha)
+                 const double * __restrict__ val, const double * __restrict__ x, double * __restrict__ y, double alpha,
+                 cudaTextureObject_t xtex)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
@@ -204,6 +205,18 @@ coo_warp4_kernel(int64_t n, int independent, const int32_t * __restrict__ row, c
         x1 = (cc[1] & 1) ? mine[1].y : mine[1].x;
         x2 = (cc[2] & 1) ? mine[2].y : mine[2].x;
         x3 = (cc[3] & 1) ? mine[3].y : mine[3].x;
+    } else if (XPATH == 5) {
+        // experiment: gather through the texture pipe (TEX.LL / TLD in SASS): x as a linear texture of int2 texels.  The
+        // texture path has its own input stage in L1TEX; does it also have its own divergent-address rate?
+        const int2 t0 = tex1Dfetch<int2>(xtex, c4.x), t1 = tex1Dfetch<int2>(xtex, c4.y);
+        const int2 t2 = tex1Dfetch<int2>(xtex, c4.z), t3 = tex1Dfetch<int2>(xtex, c4.w);
+        x0 = __hiloint2double(t0.y, t0.x); x1 = __hiloint2double(t1.y, t1.x);
+        x2 = __hiloint2double(t2.y, t2.x); x3 = __hiloint2double(t3.y, t3.x);
+    } else if (XPATH == 6) {
+        // experiment: half of the gathers through the texture pipe, half through the LSU
+        const int2 t0 = tex1Dfetch<int2>(xtex, c4.x), t2 = tex1Dfetch<int2>(xtex, c4.z);
+        x1 = __ldg(x + c4.y); x3 = __ldg(x + c4.w);
+        x0 = __hiloint2double(t0.y, t0.x); x2 = __hiloint2double(t2.y, t2.x);
     } else {
         x0 = ld_x<XPATH>(x + c4.x); x1 = ld_x<XPATH>(x + c4.y); x2 = ld_x<XPATH>(x + c4.z); x3 = ld_x<XPATH>(x + c4.w);
     }
@@ -344,6 +357,24 @@ static int launch_coo_warp_variant(Matrix * m)
     return 0;
 }
 
+// (experiment, "coo.xload" = 5 / 6) x as a linear texture of 8-byte texels, rebuilt when x was rebound
+static int x_texture(Matrix * m)
+{
+    if (m->x_tex && m->x_tex_ptr == m->x) return 0;
+    if (m->x_tex) cudaDestroyTextureObject(m->x_tex);
+    m->x_tex = 0;
+    cudaResourceDesc res = {};
+    res.resType = cudaResourceTypeLinear;
+    res.res.linear.devPtr = m->x;
+    res.res.linear.desc = cudaCreateChannelDesc<int2>();
+    res.res.linear.sizeInBytes = sizeof(double) * (size_t)m->cols;
+    cudaTextureDesc tex = {};
+    tex.readMode = cudaReadModeElementType;
+    SPMV_CUDA(cudaCreateTextureObject(&m->x_tex, &res, &tex, nullptr));
+    m->x_tex_ptr = m->x;
+    return 0;
+}
+
 template <int WARPS>
 static int launch_coo_warp4_variant(Matrix * m)
 {
@@ -357,12 +388,15 @@ static int launch_coo_warp4_variant(Matrix * m)
         else if (m->opt_coo_xload == 2) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 2 : 0>;
         else if (m->opt_coo_xload == 3) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 3 : 0>;
         else if (m->opt_coo_xload == 4) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 4 : 0>;
+        else if (m->opt_coo_xload == 5) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 5 : 0>;
+        else if (m->opt_coo_xload == 6) kernel = coo_warp4_kernel<WARPS == 4 ? 4 : WARPS, WARPS == 4 ? 6 : 0>;
+        if (m->opt_coo_xload == 5 || m->opt_coo_xload == 6) SPMV_TRY(x_texture(m));
         if (m->opt_coo_carveout >= 0)
             SPMV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)m->opt_coo_carveout));
     }
     SPMV_CUDA(launch_kernel(kernel, (unsigned)grid, (unsigned)(WARPS * 32), 0, m->stream, rm.pdl, m->coo_n,
                             rm.independent, (const int32_t *)m->coo_row, (const int32_t *)m->coo_col,
-                            (const double *)m->coo_val, (const double *)m->x, m->y, m->alpha));
+                            (const double *)m->coo_val, (const double *)m->x, m->y, m->alpha, m->x_tex));
     count_launch();
     return 0;
 }

@@ -422,6 +422,34 @@ def test_column_blocked_coo_layout(oracle):
     assert m_block["x_references"] == m_plain["x_references"]
 
 
+def test_coo_gather_path_experiments_agree(oracle):
+    """"coo.xload" 0..6: the cache paths the scattered gather was measured on (read-only, L2-only, no-allocate,
+    evict-last, cp.async, texture, texture + read-only) are switches of ONE kernel: same products whatever the path,
+    also after x was rebound (the texture object follows the pointer)."""
+    rng = np.random.default_rng(77)
+    rows, cols = 4000, 6001
+    i, j, a = ragged_matrix(rng, rows, cols, long_rows=(7, 900), long_len=2500, short_max=9, empty_every=13)
+    x = rng.uniform(-1, 1, cols)
+    O = oracle.csr(rows, cols, i, j, a)
+    yref, bound = oracle.csr_spmv(O, x), oracle.csr_abs_rowsum(O, x)
+    mm = matrix_market.from_entries(rows, cols, i, j, a)
+    for mode in (COO_SEGMENTED, COO_ATOMIC):
+        C = coo_matrix.from_matrix_market(mm, mode)
+        for path in range(7):
+            C.set_option("coo.xload", path)
+            assert_within(C * x, yref, bound, f"coo.xload={path} mode={mode}")
+            assert C.kernel_name == "coo_warp4_kernel"
+    D = coo_matrix.from_matrix_market(mm, COO_ATOMIC)  # lends its x buffer
+    D.set_x(2.0 * x)
+    D.sync()
+    C.set_option("coo.xload", 5)
+    C.bind_x(D.x_device())
+    C.fill_y(0.0)
+    C.spmv()
+    C.sync()
+    assert_within(C.get_y(), 2.0 * yref, 2.0 * bound, "texture path after bind_x")
+
+
 def test_forced_64bit_offsets(oracle):
     rng = np.random.default_rng(5)
     i, j, a = ragged_matrix(rng, 3000, 5000, long_rows=(10,), long_len=4000, short_max=12)
