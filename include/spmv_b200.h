@@ -323,10 +323,16 @@ int spmvb200_time_copy(int64_t bytes, int copies, int warmup, int reps, float *m
  *               persistent grid ("coo.hot_threads" 256|512|1024, "coo.hot_entries" 4|8 per lane, "coo.hot_segments"
  *               per CTA); off by default: measured slower than the plain kernel.  Experiment switches of
  *               the plain kernel: "coo.xload" 0 ld.global.nc | 1 ld.global.cg | 2 nc L1::no_allocate | 3 nc L1::evict_last
- *               | 4 cp.async through shared memory; "coo.carveout" preferred shared-memory carve-out in percent.
- *   host path   "host.zero_copy" (default 1; ELL): spmvb200_spmv_host lets the kernel read and write
+ *               | 4 cp.async through shared memory | 5 texture fetch | 6 texture + read-only path, half each;
+ *               "coo.carveout" preferred shared-memory carve-out in percent.
+ *   host path   "host.zero_copy" (default 1): ELL: spmvb200_spmv_host lets the kernel read and write
  *               pinned host y directly; 2 = y up by DMA in "host.chunks" row chunks, results stored by
- *               the kernel; 0 = copies only ("host.chunks" > 1 pipelines them). */
+ *               the kernel; 0 = copies only ("host.chunks" > 1 pipelines them).  CSR (sliced kernel,
+ *               square matrices of >= 2^20 rows, x uploaded in "host.chunks" pieces and every row chunk
+ *               launched when the columns it references have arrived): 1 = automatic = 3; 3 = y_old up
+ *               and y_new down by the copy engines, chunk by chunk; 2 = y_old up by DMA, y_new stored
+ *               into the pinned buffer by the kernel; 4 = the kernel reads y_old from and stores y_new
+ *               to the pinned buffer. */
 int spmvb200_set_option(spmvb200_matrix_t m, const char *key, int64_t value);
 /* Also answers the read-only keys "coo.col_block_log2" (what the builder applied), "coo.hot_coverage_permille" and
  * "coo.hot_segments_built" (the hot-column tables, if built), and

@@ -1119,14 +1119,15 @@ static int spmv_host_pipelined(Matrix * m, const double * x, double * y, int chu
 // (stencils) chunk c needs x up to piece c + 1, so the kernel starts after 2/chunks of the upload instead of all of it
 // and the whole call costs max(x + y_old up, y_new down) over PCIe; a matrix whose rows reference every column degenerates
 // to upload-then-run.
-static int spmv_host_csr_pipelined(Matrix * m, const double * x, double * y_dev_visible, int chunks)
+static int spmv_host_csr_pipelined(Matrix * m, const double * x, double * y_dev_visible, int chunks, const double * y_dma,
+                                   double * y_back)
 {
     cudaStream_t s = m->stream;
     if (!m->upload_stream) {
         SPMV_CUDA(cudaStreamCreateWithFlags(&m->upload_stream, cudaStreamNonBlocking));
         SPMV_CUDA(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
     }
-    for (int c = 0; c < chunks; c++)
+    for (int c = 0; c < 2 * chunks; c++)  // [0, chunks): x pieces; [chunks, 2 chunks): y chunks of the DMA form
         if (!m->ev_chunk[c]) SPMV_CUDA(cudaEventCreateWithFlags(&m->ev_chunk[c], cudaEventDisableTiming));
     const int64_t per = round_up((m->rows + chunks - 1) / chunks, 1024);
     if (m->host_chunks != chunks || m->host_rows_per_chunk != per) {
@@ -1137,20 +1138,44 @@ static int spmv_host_csr_pipelined(Matrix * m, const double * x, double * y_dev_
     cudaStream_t up = m->upload_stream;
     SPMV_CUDA(cudaEventRecord(m->ev_x, s));  // kernels queued earlier may still gather from m->x
     SPMV_CUDA(cudaStreamWaitEvent(up, m->ev_x, 0));
+    const int64_t keep = m->opt_beta0;
+    // "host.zero_copy" = 2 (y_dma): y_old goes up with the copy engine as well -- chunk c right behind the x piece its rows
+    // wait for -- and the kernel adds onto the uploaded chunk; only y_new is written by the kernel.  One DMA queue then
+    // carries everything that goes up, in the order the kernels need it.
+    const bool dma = y_dma && !keep;
+    std::vector<int> need_of((size_t)chunks, -1);
+    for (int c = 0; c < chunks; c++)
+        need_of[(size_t)c] = m->host_colmax[c] < 0 ? -1 : (int)std::min<int64_t>(chunks - 1, m->host_colmax[c] / per);
+    int next_y = 0;  // next y chunk to send up
+    auto send_y_upto = [&](int piece) -> int {  // every y chunk whose rows need no x piece beyond `piece`
+        while (dma && next_y < chunks && need_of[(size_t)next_y] <= piece) {
+            const int64_t b = (int64_t)next_y * per, e = std::min<int64_t>(m->rows, b + per);
+            if (e > b) SPMV_CUDA(cudaMemcpyAsync(m->y + b, y_dma + b, sizeof(double) * (size_t)(e - b), cudaMemcpyHostToDevice, up));
+            SPMV_CUDA(cudaEventRecord(m->ev_chunk[chunks + next_y], up));
+            ++next_y;
+        }
+        return 0;
+    };
     for (int c = 0; c < chunks; c++) {  // x pieces on the same grid as the row chunks (the matrix is square)
         const int64_t b = (int64_t)c * per, e = std::min<int64_t>(m->cols, b + per);
         if (e > b) SPMV_CUDA(cudaMemcpyAsync(m->x + b, x + b, sizeof(double) * (size_t)(e - b), cudaMemcpyHostToDevice, up));
         SPMV_CUDA(cudaEventRecord(m->ev_chunk[c], up));
+        SPMV_TRY(send_y_upto(c));
     }
-    const int64_t keep = m->opt_beta0;
-    m->host_y_in = keep ? nullptr : (const double *)y_dev_visible;
-    m->host_y_out = y_dev_visible;
+    SPMV_TRY(send_y_upto(chunks));
+    // "host.zero_copy" = 3 (y_back): the result comes down with the copy engine too; the kernel works on device memory only
+    const bool back = dma && y_back;
+    m->host_y_in = back || keep ? nullptr : dma ? (const double *)m->y : (const double *)y_dev_visible;
+    m->host_y_out = back ? nullptr : y_dev_visible;
     m->opt_beta0 = 0;
     int rc = 0, waited = -1;
     for (int c = 0; c < chunks && rc == 0; c++) {
         const int64_t b = (int64_t)c * per, e = std::min<int64_t>(m->rows, b + per);
         if (b >= e) break;
-        const int need = m->host_colmax[c] < 0 ? -1 : (int)std::min<int64_t>(chunks - 1, m->host_colmax[c] / per);
+        const int need = need_of[(size_t)c];
+        if (dma) {  // the chunk's y went up behind the x piece it needs: one wait covers both
+            if (cudaStreamWaitEvent(s, m->ev_chunk[chunks + c], 0) != cudaSuccess) { rc = fail(SPMVB200_ERR_CUDA, "cudaStreamWaitEvent"); break; }
+        } else
         if (need > waited) {
             if (cudaStreamWaitEvent(s, m->ev_chunk[need], 0) != cudaSuccess) { rc = fail(SPMVB200_ERR_CUDA, "cudaStreamWaitEvent"); break; }
             waited = need;
@@ -1159,6 +1184,9 @@ static int spmv_host_csr_pipelined(Matrix * m, const double * x, double * y_dev_
         m->range_end = e;
         plan_run(m, true);
         rc = launch_csr_sliced(m);
+        if (back && rc == 0 &&
+            cudaMemcpyAsync(y_back + b, m->y + b, sizeof(double) * (size_t)(e - b), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            rc = fail(SPMVB200_ERR_CUDA, "cudaMemcpyAsync(y chunk)");
     }
     m->range_begin = m->range_end = 0;
     m->opt_beta0 = keep;
@@ -1212,9 +1240,14 @@ try {
             if (rc) return rc;
         }
         if (m->slice_col && cudaPointerGetAttributes(&ay, y) == cudaSuccess && ay.type == cudaMemoryTypeHost && ay.devicePointer) {
-            const int chunks = (int)(m->opt_host_chunks ? std::min<int64_t>(m->opt_host_chunks, 64) : 16);
+            const int chunks = (int)(m->opt_host_chunks ? std::min<int64_t>(m->opt_host_chunks, 32) : m->rows >= 32 * (int64_t)65536 ? 32 : 16);
+            // form of the pipelined call: 1 = automatic = 3, everything by copy engines (config 5: 43.6 ms against 44.8 ms for
+            // form 4, where the kernel reads y_old from and writes y_new to the pinned buffer); 2 = y_old up by DMA, y_new
+            // stored by the kernel
+            const int64_t form = m->opt_host_zero_copy == 1 ? 3 : m->opt_host_zero_copy;
             if (chunks > 1 && m->rows >= (int64_t)chunks * 65536 && m->rows == m->cols)
-                return spmv_host_csr_pipelined(m, x, (double *)ay.devicePointer, chunks);
+                return spmv_host_csr_pipelined(m, x, (double *)ay.devicePointer, chunks, form == 2 || form == 3 ? y : nullptr,
+                                               form == 3 ? y : nullptr);
             SPMV_CUDA(cudaMemcpyAsync(m->x, x, sizeof(double) * (size_t)m->cols, cudaMemcpyHostToDevice, s));
             m->host_y_in = m->opt_beta0 ? nullptr : (const double *)ay.devicePointer;
             m->host_y_out = (double *)ay.devicePointer;

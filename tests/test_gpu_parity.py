@@ -1261,15 +1261,19 @@ def test_csr_spmv_host_pipelined_upload(oracle):
     ref = oracle.csr_spmv(O, x, y0)
     A = sp.generators.stencil(sp.STENCIL_3D27, n, n, n)
     xb, yb = sp.PinnedBuffer(N), sp.PinnedBuffer(N)
-    for chunks in (16, 5, 1):
+    for zero_copy, chunks in ((1, 16), (1, 5), (1, 1), (2, 16), (2, 7), (3, 16), (3, 3), (4, 16), (4, 5)):
+        # 4: the kernel reads y_old from and stores y_new to the pinned buffer; 2: y_old goes up by DMA, chunk c right behind
+        # the x piece its rows wait for; 3 (= 1, automatic): y_new comes down by DMA as well
+        A.set_option("host.zero_copy", zero_copy)
         A.set_option("host.chunks", chunks)
         xb.array[:] = x
         yb.array[:] = y0
         before = sp.launch_count()
         A.spmv_host(xb.array, yb.array)
         assert sp.launch_count() - before == (chunks if chunks > 1 else 1) and A.kernel_name == "csr_sliced_kernel"
-        assert np.array_equal(yb.array, ref), f"{chunks} chunks"
+        assert np.array_equal(yb.array, ref), f"{chunks} chunks, host.zero_copy={zero_copy}"
         A.spmv()  # an asynchronous launch in flight when the next host call starts uploading
+    A.set_option("host.zero_copy", 1)
     # wrap-around columns: row r references (r + 97 k) mod N, k = 0..11, so the last rows reference the first columns
     # and the first chunk's largest column lies in the last piece only for the LAST rows -- the spans must be per chunk
     N2 = 16 * 65536 + 4096
@@ -1290,6 +1294,10 @@ def test_csr_spmv_host_pipelined_upload(oracle):
     B.spmv_host(xb2.array, yb2.array)
     assert B.kernel_name == "csr_sliced_kernel" and sp.launch_count() - before == 16
     assert np.array_equal(yb2.array, want)
+    for form in (2, 4):  # the other forms on the same matrix: y += A x onto what the earlier calls left
+        B.set_option("host.zero_copy", form)
+        B.spmv_host(xb2.array, yb2.array)
+        assert np.array_equal(yb2.array, (2.0 if form == 2 else 3.0) * want)
 
 
 def test_kernels_really_launch():
