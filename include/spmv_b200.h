@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define SPMVB200_VERSION 200 /* 0.2.0: + spmvb200_comm_*, spmvb200_dist_*, spmvb200_exchange_plan, spmvb200_partition_rows_weighted */
+#define SPMVB200_VERSION 210 /* 0.2.0: + spmvb200_comm_*, spmvb200_dist_*, spmvb200_exchange_plan, spmvb200_partition_rows_weighted;
+                                0.2.1: + spmvb200_mm_partition_kway, spmvb200_mm_order_gp_kway, spmvb200_order_from_parts */
 
 typedef enum {
     SPMVB200_OK = 0,
@@ -106,7 +107,9 @@ int64_t spmvb200_launch_count(void);
  * than 0.75 L2, the gathers are not local already -- more than three column blocks touched per 2^20
  * consecutive entries -- and the extra sweeps over y cost less than the gather misses), -1 = never, k > 0 = always, with 2^k
  * columns.  Exports restore the row-major order.  spmvb200_get_option(m, "coo.col_block_log2") tells
- * what was applied to a matrix. */
+ * what was applied to a matrix.
+ * "mm.gp_partitioner" = 1: the graph-partitioning order ("__GP<n>", spmvb200_mm_order_gp) uses the library's own
+ * K-way partitioner instead of being the identity (0, default: the reference's default build, which has no METIS). */
 int spmvb200_set_global_option(const char *key, int64_t value);
 
 /* ---- host side: Matrix Market --------------------------------------------- */
@@ -120,7 +123,8 @@ int spmvb200_mm_parse(const char *text, size_t len, spmvb200_mm_t *out);
  * and .tgz (member <name>/<name>.mtx, :755-757).  A "__RCM" path suffix loads
  * the file without the suffix and applies the reverse Cuthill-McKee order
  * (:786-802); "__GP<n>" is accepted and, like the reference built without
- * METIS, permutes nothing. */
+ * METIS, permutes nothing -- unless the global option "mm.gp_partitioner" is set
+ * (spmvb200_mm_order_gp below). */
 int spmvb200_mm_load(const char *path, spmvb200_mm_t *out);
 /* matrix_market::Matrix(Header, Comments, Size, vector<CoordinateEntryReal>)
  * (matrix-market.hpp:81-84); i, j are 1-based. */
@@ -144,8 +148,23 @@ int spmvb200_mm_sort_column_major(spmvb200_mm_t mm);
 /* find_new_order_RCM (matrix/matrix-market-reorder.cpp:60-170): new_order[old index] = new index,
  * `rows` entries; square real coordinate matrices only. */
 int spmvb200_mm_order_rcm(spmvb200_mm_t mm, int32_t *new_order);
-/* find_new_order_GP without METIS (matrix-market-reorder.cpp:172-180): the identity. */
+/* find_new_order_GP (matrix-market-reorder.cpp:172-278).  The reference partitions the matrix graph with
+ * METIS_PartGraphKway (third-party; absent from its default build and from this image) and groups the rows by
+ * part; built without METIS it returns the identity (:172-180), and so does this call by default.  With the
+ * global option "mm.gp_partitioner" = 1 (also honoured by the "__GP<n>" path suffix of spmvb200_mm_load) it is
+ * spmvb200_mm_order_gp_kway: the library's own K-way partitioner in METIS's place -- a valid partition with the
+ * same balance bound, but not the one METIS would return. */
 int spmvb200_mm_order_gp(spmvb200_mm_t mm, int32_t nparts, int32_t *new_order);
+int spmvb200_mm_order_gp_kway(spmvb200_mm_t mm, int32_t nparts /* <= 1: 16, :232-233 */, int32_t *new_order);
+/* What METIS_PartGraphKway is called for (:236-237): part[v] in [0, nparts) for every row of a square real
+ * coordinate matrix, unit vertex weights, no part larger than max(ceil(n/k), ub*n/k) rows (the reference passes
+ * ub = 1.05 -> ub_permille 1050); the graph is the off-diagonal pattern made undirected.  Level-structure cut from
+ * a pseudo-peripheral vertex per component, then boundary refinement; deterministic.  edgecut (may be NULL) =
+ * undirected edges whose ends lie in different parts. */
+int spmvb200_mm_partition_kway(spmvb200_mm_t mm, int32_t nparts, int32_t ub_permille, int32_t *part, int64_t *edgecut);
+/* The second half of find_new_order_GP (:246-266), exact: rows grouped by part, parts ascending, the rows of a
+ * part in ascending index order; new_order[old index] = new index. */
+int spmvb200_order_from_parts(int32_t n, int32_t nparts, const int32_t *part, int32_t *new_order);
 /* Matrix::permute (matrix-market.cpp:309-333): i, j <- new_order[i-1]+1, new_order[j-1]+1. */
 int spmvb200_mm_permute(spmvb200_mm_t mm, const int32_t *new_order);
 void spmvb200_mm_free(spmvb200_mm_t mm);

@@ -393,6 +393,12 @@ class Oracle:
                                         C.c_int(P), out.ctypes.data_as(C.POINTER(C.c_int64)))
         return out
 
+    def order_from_parts(self, part, nparts: int):
+        part = _i32(part)
+        out = np.zeros(max(part.size, 1), dtype=np.int32)
+        self._check(self.lib.orc_order_from_parts(C.c_int32(part.size), C.c_int32(nparts), _ptr(part, _i32p), _ptr(out, _i32p)))
+        return out[: part.size]
+
     def partition_rows_weighted(self, row_ptr, P, row_weight: float):
         rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
         out = np.zeros(P + 1, dtype=np.int64)

@@ -789,6 +789,30 @@ void orc_partition_rows_weighted(int64_t rows, const int64_t *row_ptr, int P, in
     starts[P] = rows;
 }
 
+/* find_new_order_GP after the METIS call (matrix/matrix-market-reorder.cpp:246-266): histogram of the parts, prefix
+ * sum, permutation[new] = old in ascending old index inside a part, then new_order[old] = new.  (The call itself,
+ * METIS_PartGraphKway :236-237, is third-party code absent from the reference tree and from this image: METIS 5, not
+ * pinned by the reference -- there is nothing to restate; the product's partitioner is checked by properties.) */
+int orc_order_from_parts(int32_t nvtxs, int32_t nparts, const int32_t *part, int32_t *new_order)
+{
+    int32_t i;
+    int32_t *offset = (int32_t *)calloc((size_t)nparts + 1, sizeof(int32_t));
+    int32_t *permutation = (int32_t *)malloc(((size_t)nvtxs + 1) * sizeof(int32_t));
+    if (!offset || !permutation) { free(offset); free(permutation); return -1; }
+    for (i = 0; i < nvtxs; i++) offset[part[i] + 1]++;
+    offset[0] = 0;
+    for (i = 1; i <= nparts; i++) offset[i] += offset[i - 1];
+    for (i = 0; i < nvtxs; i++) {
+        permutation[offset[part[i]]] = i;
+        offset[part[i]]++;
+    }
+    for (i = 0; i < nvtxs; i++) new_order[i] = -1;
+    for (i = 0; i < nvtxs; i++) new_order[permutation[i]] = i;
+    free(offset);
+    free(permutation);
+    return 0;
+}
+
 /* ======================================================================== */
 /* R-MAT edges of the synthetic power-law matrices (BASELINE configs 3, 4)   */
 /* ======================================================================== */

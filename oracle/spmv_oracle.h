@@ -178,6 +178,8 @@ void orc_partition_rows_ref(int64_t rows, int P, int64_t *starts /* P+1 */);
 /* P_nnz: start_p = first row r with row_ptr[r] >= floor(p*nnz/P); start_0 = 0, start_P = rows. */
 void orc_partition_rows_nnz(int64_t rows, const int64_t *row_ptr, int P, int64_t *starts /* P+1 */);
 
+/* matrix-market-reorder.cpp:246-266: rows grouped by part; new_order[old] = new. */
+int orc_order_from_parts(int32_t nvtxs, int32_t nparts, const int32_t *part, int32_t *new_order);
 void orc_partition_rows_weighted(int64_t rows, const int64_t *row_ptr, int P, int64_t row_weight_q10, int64_t *starts /* P+1 */);
 
 /* ---- R-MAT edges: C twin of OUR device generator (generators.cu), for the full-size parity tests ----------- */

@@ -198,11 +198,30 @@ class matrix_market:
         return out[: m.rows]
 
     @staticmethod
-    def find_new_order_GP(m: MatrixMarket, nparts: int):
-        """matrix-market-reorder.cpp:172-180 (the reference without METIS): the identity."""
+    def find_new_order_GP(m: MatrixMarket, nparts: int, partitioner: bool = None):
+        """find_new_order_GP (matrix-market-reorder.cpp:172-278).  partitioner=None: what the global option
+        "mm.gp_partitioner" says (default: the identity, the reference without METIS); True: the library's own K-way
+        partitioner in METIS's place."""
         out = np.zeros(max(m.rows, 1), np.int32)
-        _check(_abi.lib().spmvb200_mm_order_gp(m._h, int(nparts), _p(out, i32p)))
+        fn = _abi.lib().spmvb200_mm_order_gp_kway if partitioner else _abi.lib().spmvb200_mm_order_gp
+        _check(fn(m._h, int(nparts), _p(out, i32p)))
         return out[: m.rows]
+
+    @staticmethod
+    def partition_kway(m: MatrixMarket, nparts: int, ub: float = 1.05):
+        """What the reference calls METIS_PartGraphKway for (:236-237): (part[rows], edgecut)."""
+        part = np.zeros(max(m.rows, 1), np.int32)
+        cut = C.c_int64(0)
+        _check(_abi.lib().spmvb200_mm_partition_kway(m._h, int(nparts), int(round(ub * 1000)), _p(part, i32p), C.byref(cut)))
+        return part[: m.rows], int(cut.value)
+
+    @staticmethod
+    def order_from_parts(part, nparts: int):
+        """The grouping step of find_new_order_GP (:246-266): new_order[old] = new."""
+        part = _i32(part)
+        out = np.zeros(max(part.size, 1), np.int32)
+        _check(_abi.lib().spmvb200_order_from_parts(int(part.size), int(nparts), _p(part, i32p), _p(out, i32p)))
+        return out[: part.size]
 
     @staticmethod
     def _copy(m: MatrixMarket) -> MatrixMarket:

@@ -140,6 +140,9 @@ SIGNATURES = {
     "spmvb200_csr_column_span": (C.c_int, [vp, C.c_int64, C.c_int64, i64p, i64p, i64p, i64p]),
     "spmvb200_mm_order_rcm": (C.c_int, [vp, i32p]),
     "spmvb200_mm_order_gp": (C.c_int, [vp, C.c_int32, i32p]),
+    "spmvb200_mm_order_gp_kway": (C.c_int, [vp, C.c_int32, i32p]),
+    "spmvb200_mm_partition_kway": (C.c_int, [vp, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int64)]),
+    "spmvb200_order_from_parts": (C.c_int, [C.c_int32, C.c_int32, i32p, i32p]),
     "spmvb200_mm_permute": (C.c_int, [vp, i32p]),
     "spmvb200_cache_trace_csr": (C.c_int, [C.c_int64, C.c_int64, i64p, i32p, _ccp, _cmp]),
     "spmvb200_cache_trace_ell": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, i32p, _ccp, _cmp]),

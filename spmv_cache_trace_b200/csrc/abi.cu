@@ -374,6 +374,7 @@ try {
     if (!key) return fail(SPMVB200_ERR_INVALID, "null argument");
     if (!strcmp(key, "force_offsets64")) { g_force_off64 = value ? 1 : 0; return 0; }
     if (!strcmp(key, "coo.col_block_log2")) { g_coo_col_block_log2 = value; return 0; }
+    if (!strcmp(key, "mm.gp_partitioner")) { set_gp_partitioner(value ? 1 : 0); return 0; }
     return fail(SPMVB200_ERR_INVALID, std::string("unknown global option ") + key);
 }
 SPMV_ABI_CATCH

@@ -396,6 +396,7 @@ int mm_load_path(const char * path_c, spmvb200_mm_s ** out)
     // "__RCM" / "__GP<n>" suffixes select a reordering (matrix-market.cpp:786-802): the suffix is cut off,
     // the file is loaded, then the order is computed and applied (RCM first, then GP).
     bool rcm = false, gp = false;
+    int nparts = 0;
     size_t pos = path.rfind("__RCM");
     if (pos != std::string::npos) {
         rcm = true;
@@ -403,15 +404,23 @@ int mm_load_path(const char * path_c, spmvb200_mm_s ** out)
     }
     pos = path.rfind("__GP");
     if (pos != std::string::npos) {
-        gp = true;  // without METIS the reference's graph-partitioning order is the identity
+        // without METIS the reference's graph-partitioning order is the identity; with the global option
+        // "mm.gp_partitioner" the library's own K-way partitioner stands in for METIS (reorder_host.cpp)
+        gp = gp_partitioner() != 0;
+        if (pos + 4 < path.size()) nparts = std::atoi(path.c_str() + pos + 4);  // sscanf("%d"), matrix-market.cpp:797-801
         path.erase(pos);
     }
-    (void)gp;
     int rc = load_plain(path, out);
-    if (rc || !rcm) return rc;
+    if (rc || !(rcm || gp)) return rc;
     std::vector<int32_t> order((size_t)(*out)->rows);
-    rc = mm_order_rcm(*out, order.data());
-    if (rc == 0) rc = mm_permute(*out, order.data());
+    if (rcm) {
+        rc = mm_order_rcm(*out, order.data());
+        if (rc == 0) rc = mm_permute(*out, order.data());
+    }
+    if (rc == 0 && gp) {
+        rc = mm_order_gp_kway(*out, nparts, order.data());
+        if (rc == 0) rc = mm_permute(*out, order.data());
+    }
     if (rc) {
         delete *out;
         *out = nullptr;

@@ -29,5 +29,10 @@ int mm_sort(spmvb200_mm_s * mm, bool row_major);
 // reorder_host.cpp
 int mm_order_rcm(const spmvb200_mm_s * mm, int32_t * new_order);
 int mm_permute(spmvb200_mm_s * mm, const int32_t * new_order);
+int order_from_parts(int32_t n, int32_t nparts, const int32_t * part, int32_t * new_order);
+int mm_partition_kway(const spmvb200_mm_s * mm, int32_t nparts, double ub, int32_t * part, int64_t * edgecut);
+int mm_order_gp_kway(const spmvb200_mm_s * mm, int32_t nparts, int32_t * new_order);
+void set_gp_partitioner(int64_t v);  // global option "mm.gp_partitioner"
+int64_t gp_partitioner();
 
 }  // namespace spmvb200

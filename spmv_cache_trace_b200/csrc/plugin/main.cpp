@@ -106,6 +106,7 @@ int main(int argc, char ** argv)
                                 {"x-gather", required_argument, nullptr, 'x'}, {"cache-bytes", required_argument, nullptr, 1001},
                                 {"line-bytes", required_argument, nullptr, 'l'}, {"trace-config", required_argument, nullptr, 'c'},
                                 {"warmup", no_argument, nullptr, 1002}, {"flush-caches", no_argument, nullptr, 1003},
+                                {"gp-partitioner", no_argument, nullptr, 1004},
                                 {"verbose", no_argument, nullptr, 'v'}, {"help", no_argument, nullptr, 'h'},
                                 {nullptr, 0, nullptr, 0}};
     int c;
@@ -128,14 +129,17 @@ int main(int argc, char ** argv)
         }
         case 1002: case 1003: break;  // --warmup / --flush-caches of the reference: a warm-up run is always done, and
                                       // cache flushing is a CPU notion (the L2-cold protocol lives in bench.py)
+        case 1004: spmvb200_set_global_option("mm.gp_partitioner", 1); break;
         case 'l': line_bytes = std::max(1, std::atoi(optarg)); break;
         case 'v': verbose = true; break;
         default:
             std::cout << "Usage: spmv-b200 --spmv-format FMT --matrix PATH [--profile N] [--threads T | -c TRACE_CONFIG] [--verbose]\n"
-                         "                 [--x-gather PARTS [--cache-bytes B] [--line-bytes L]]\n"
+                         "                 [--x-gather PARTS [--cache-bytes B] [--line-bytes L]] [--gp-partitioner]\n"
                          "  FMT: cuda-csr, cuda-coo, cuda-coo-atomic, cuda-ell, cuda-hybrid\n"
                          "  --x-gather PARTS  cache-model prediction of the x-gather misses for a PARTS-way partition\n"
-                         "                    (default cache: this GPU's L2; default line: the 32 B DRAM sector)\n";
+                         "                    (default cache: this GPU's L2; default line: the 32 B DRAM sector)\n"
+                         "  --gp-partitioner  a PATH ending in __GP<n> is reordered by the built-in K-way graph partitioner\n"
+                         "                    (the reference needs a METIS build for that suffix; default: no reordering)\n";
             return c == 'h' ? EXIT_SUCCESS : EXIT_FAILURE;
         }
     }

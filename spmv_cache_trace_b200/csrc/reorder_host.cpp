@@ -8,11 +8,19 @@
 // (the same library call as the reference's, so equal degrees fall the same way), the whole order
 // reversed at the end.  What differs is cost: the reference rescans all nodes for every component
 // (quadratic on graphs with many isolated vertices); here the nodes are ranked once and a cursor moves
-// forward through them.  "__GP<n>" is the reference's graph-partitioning order, which without METIS
-// is the identity (matrix-market-reorder.cpp:172-180): accepted, nothing permuted.
+// forward through them.
+//
+// "__GP<n>" is the reference's graph-partitioning order (find_new_order_GP, :183-278): a K-way partition of the matrix
+// graph by METIS_PartGraphKway, then the rows grouped by part.  METIS is third-party code that neither the reference's
+// default build nor this image has; without it the reference returns the identity (:172-180), and so does
+// spmvb200_mm_order_gp by default.  The grouping step (:246-266) is restated exactly (order_from_parts); for the
+// partition itself this file has its own K-way partitioner (mm_partition_kway: level-structure cut + boundary
+// refinement, unit vertex weights, the reference's 1.05 imbalance bound), switched in for "__GP<n>" by the global
+// option "mm.gp_partitioner" -- a different partition than METIS would produce, so orders differ from a METIS build's.
 #include "mm_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <numeric>
 #include <stdexcept>
@@ -24,6 +32,12 @@
     catch (const std::exception & e) { return ::spmvb200::fail(SPMVB200_ERR_INVALID, e.what()); }
 
 #include "../../include/spmv_b200.h"
+
+#define SPMV_TRY_HOST(call)            \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
 
 namespace spmvb200 {
 int fail(int code, const std::string & msg);
@@ -88,6 +102,210 @@ int mm_order_rcm(const spmvb200_mm_s * m, int32_t * new_order)
     return 0;
 }
 
+
+// ---- graph partitioning ----------------------------------------------------------------------------------------------
+
+static std::atomic<int64_t> g_gp_partitioner{0};
+void set_gp_partitioner(int64_t v) { g_gp_partitioner.store(v); }
+int64_t gp_partitioner() { return g_gp_partitioner.load(); }
+
+// The second half of find_new_order_GP (matrix-market-reorder.cpp:246-266): count the rows of every part, turn the
+// counts into offsets, give the rows of a part consecutive new indices in ascending old index; new_order[old] = new.
+int order_from_parts(int32_t n, int32_t nparts, const int32_t * part, int32_t * new_order)
+{
+    if (n < 0 || nparts < 1) return fail(SPMVB200_ERR_INVALID, "order_from_parts: bad size");
+    std::vector<int32_t> offset((size_t)nparts + 1, 0);
+    for (int32_t v = 0; v < n; v++) {
+        if (part[v] < 0 || part[v] >= nparts) return fail(SPMVB200_ERR_INVALID, "order_from_parts: part number outside [0, nparts)");
+        offset[(size_t)part[v] + 1]++;
+    }
+    for (int32_t p = 1; p <= nparts; p++) offset[(size_t)p] += offset[(size_t)p - 1];
+    for (int32_t v = 0; v < n; v++) new_order[v] = offset[(size_t)part[v]]++;
+    return 0;
+}
+
+namespace {
+
+// The matrix graph as METIS wants it: undirected, simple (every off-diagonal entry is an edge in both directions,
+// duplicates merged).  The reference hands METIS the directed pattern as stored (:203-227), which is the same graph for
+// the structurally symmetric matrices it is meant for.
+struct Graph {
+    int32_t n = 0;
+    std::vector<int64_t> first;
+    std::vector<int32_t> adj;
+};
+
+Graph build_graph(const spmvb200_mm_s * m)
+{
+    Graph g;
+    g.n = m->rows;
+    const int64_t ne = m->num_entries;
+    std::vector<int64_t> deg((size_t)g.n + 1, 0);
+    for (int64_t e = 0; e < ne; e++)
+        if (m->i[(size_t)e] != m->j[(size_t)e]) { deg[(size_t)m->i[(size_t)e]]++; deg[(size_t)m->j[(size_t)e]]++; }
+    for (int32_t v = 0; v < g.n; v++) deg[(size_t)v + 1] += deg[(size_t)v];
+    std::vector<int32_t> raw((size_t)deg[(size_t)g.n]);
+    {
+        std::vector<int64_t> fill(deg.begin(), deg.end() - 1);
+        for (int64_t e = 0; e < ne; e++) {
+            const int32_t a = m->i[(size_t)e] - 1, b = m->j[(size_t)e] - 1;
+            if (a == b) continue;
+            raw[(size_t)fill[(size_t)a]++] = b;
+            raw[(size_t)fill[(size_t)b]++] = a;
+        }
+    }
+    g.first.assign((size_t)g.n + 1, 0);
+    g.adj.reserve(raw.size() / 2 + 16);
+    for (int32_t v = 0; v < g.n; v++) {
+        auto lo = raw.begin() + deg[(size_t)v], hi = raw.begin() + deg[(size_t)v + 1];
+        std::sort(lo, hi);
+        hi = std::unique(lo, hi);
+        g.adj.insert(g.adj.end(), lo, hi);
+        g.first[(size_t)v + 1] = (int64_t)g.adj.size();
+    }
+    return g;
+}
+
+// Breadth-first order of the component of `start` inside region `rid` (neighbours in ascending index); returns the
+// last vertex reached.
+int32_t bfs(const Graph & g, const std::vector<int32_t> & region, int32_t rid, int32_t start, std::vector<int32_t> & mark,
+            int32_t stamp, std::vector<int32_t> & out)
+{
+    const size_t head0 = out.size();
+    out.push_back(start);
+    mark[(size_t)start] = stamp;
+    for (size_t h = head0; h < out.size(); h++) {
+        const int32_t v = out[h];
+        for (int64_t p = g.first[(size_t)v]; p < g.first[(size_t)v + 1]; p++) {
+            const int32_t w = g.adj[(size_t)p];
+            if (region[(size_t)w] == rid && mark[(size_t)w] != stamp) { mark[(size_t)w] = stamp; out.push_back(w); }
+        }
+    }
+    return out.back();
+}
+
+struct Bisector {
+    const Graph & g;
+    int32_t * part;
+    std::vector<int32_t> region, mark, scratch;
+    int32_t next_region = 0, stamp = 0;
+
+    // `verts` (ascending) get parts [part0, part0 + k): level structure of the induced subgraph from a pseudo-peripheral
+    // vertex of every component, cut in proportion k/2 : k - k/2, both sides recursively.
+    void run(std::vector<int32_t> & verts, int32_t k, int32_t part0)
+    {
+        if (k <= 1 || verts.size() <= 1) {
+            for (int32_t v : verts) part[v] = part0;
+            return;
+        }
+        const int32_t rid = ++next_region;
+        for (int32_t v : verts) region[(size_t)v] = rid;
+        std::vector<int32_t> order;
+        order.reserve(verts.size());
+        for (int32_t v0 : verts) {
+            if (region[(size_t)v0] != rid) continue;  // placed already (its region was flipped below)
+            scratch.clear();
+            const int32_t far1 = bfs(g, region, rid, v0, mark, ++stamp, scratch);
+            scratch.clear();
+            const int32_t far2 = bfs(g, region, rid, far1, mark, ++stamp, scratch);
+            const size_t before = order.size();
+            bfs(g, region, rid, far2, mark, ++stamp, order);
+            for (size_t t = before; t < order.size(); t++) region[(size_t)order[t]] = -rid;  // placed
+        }
+        const int32_t k1 = k / 2;
+        const size_t cut = (size_t)((int64_t)order.size() * k1 / k);
+        std::vector<int32_t> left(order.begin(), order.begin() + (ptrdiff_t)cut), right(order.begin() + (ptrdiff_t)cut, order.end());
+        std::vector<int32_t>().swap(order);
+        std::vector<int32_t>().swap(verts);
+        std::sort(left.begin(), left.end());
+        std::sort(right.begin(), right.end());
+        run(left, k1, part0);
+        run(right, k - k1, part0 + k1);
+    }
+};
+
+}  // namespace
+
+// K-way partition with unit vertex weights; every part holds at most max(ceil(n/k), floor(ub*n/k)) vertices.
+//   1. recursive bisection by level structures: the vertices of a region are ordered breadth-first from a
+//      pseudo-peripheral vertex of every component (the far end of a sweep from the component's lowest vertex, then the
+//      far end of a sweep from there), the order is cut in proportion k/2 : k - k/2 -- edges only join neighbouring
+//      levels, so the cut is one level wide -- and both sides are bisected again until k parts exist;
+//   2. boundary refinement: sweeps over the vertices; a vertex moves to the neighbouring part that holds most of its
+//      neighbours when that lowers the cut (or keeps it and evens the sizes out) and the target has room; until a
+//      sweep moves nothing (at most 16 sweeps).  Every move lowers (cut, imbalance) lexicographically: it terminates.
+// Deterministic.  edgecut = undirected edges whose ends lie in different parts.
+int mm_partition_kway(const spmvb200_mm_s * m, int32_t nparts, double ub, int32_t * part, int64_t * edgecut)
+{
+    if (m->format != 0) return fail(SPMVB200_ERR_INVALID, "Expected matrix in coordinate format");
+    if (m->rows != m->columns) return fail(SPMVB200_ERR_INVALID, "Expected a square matrix");
+    if (m->field != 0) return fail(SPMVB200_ERR_INVALID, "Expected matrix with real values");
+    if (nparts < 1) return fail(SPMVB200_ERR_INVALID, "partition: nparts must be positive");
+    if (!(ub >= 1.0)) return fail(SPMVB200_ERR_INVALID, "partition: the imbalance bound must be at least 1");
+    const Graph g = build_graph(m);
+    const int32_t n = g.n, k = nparts;
+    if (edgecut) *edgecut = 0;
+    if (n == 0) return 0;
+    // 1. recursive bisection
+    std::vector<int32_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    {
+        Bisector b{g, part, std::vector<int32_t>((size_t)n, 0), std::vector<int32_t>((size_t)n, 0), {}, 0, 0};
+        b.scratch.reserve((size_t)n);
+        std::vector<int32_t> all(order);
+        b.run(all, k, 0);
+    }
+    // the refinement sweeps visit the vertices part by part
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t c) { return part[a] < part[c]; });
+    // 2. boundary refinement
+    const int64_t cap = std::max<int64_t>(((int64_t)n + k - 1) / k, (int64_t)(ub * (double)n / (double)k));
+    std::vector<int64_t> size((size_t)k, 0);
+    for (int32_t v = 0; v < n; v++) size[(size_t)part[v]]++;
+    std::vector<int32_t> cnt((size_t)k, 0), touched;
+    for (int sweep = 0; sweep < 16; sweep++) {
+        int64_t moves = 0;
+        for (int32_t t = 0; t < n; t++) {
+            const int32_t v = order[(size_t)t], p = part[v];
+            touched.clear();
+            for (int64_t q = g.first[(size_t)v]; q < g.first[(size_t)v + 1]; q++) {
+                const int32_t pw = part[g.adj[(size_t)q]];
+                if (cnt[(size_t)pw]++ == 0) touched.push_back(pw);
+            }
+            int32_t best = -1;
+            for (int32_t q : touched)
+                if (q != p && (best < 0 || cnt[(size_t)q] > cnt[(size_t)best] || (cnt[(size_t)q] == cnt[(size_t)best] && q < best))) best = q;
+            if (best >= 0 && size[(size_t)p] > 1 && size[(size_t)best] < cap) {
+                const int32_t gain = cnt[(size_t)best] - cnt[(size_t)p];
+                if (gain > 0 || (gain == 0 && size[(size_t)best] + 1 < size[(size_t)p])) {
+                    part[v] = best;
+                    size[(size_t)p]--;
+                    size[(size_t)best]++;
+                    moves++;
+                }
+            }
+            for (int32_t q : touched) cnt[(size_t)q] = 0;
+        }
+        if (!moves) break;
+    }
+    if (edgecut) {
+        int64_t cut = 0;
+        for (int32_t v = 0; v < n; v++)
+            for (int64_t q = g.first[(size_t)v]; q < g.first[(size_t)v + 1]; q++)
+                if (g.adj[(size_t)q] > v && part[g.adj[(size_t)q]] != part[v]) cut++;
+        *edgecut = cut;
+    }
+    return 0;
+}
+
+// find_new_order_GP (matrix-market-reorder.cpp:183-278) with the partitioner above in METIS's place.
+int mm_order_gp_kway(const spmvb200_mm_s * m, int32_t nparts, int32_t * new_order)
+{
+    if (nparts <= 1) nparts = 16;  // :232-233
+    std::vector<int32_t> part((size_t)std::max(m->rows, 1));
+    SPMV_TRY_HOST(mm_partition_kway(m, nparts, 1.05, part.data(), nullptr));  // ubvec = 1.05, :200
+    return order_from_parts(m->rows, nparts, part.data(), new_order);
+}
+
 int mm_permute(spmvb200_mm_s * m, const int32_t * new_order)
 {
     if (m->format != 0) return fail(SPMVB200_ERR_INVALID, "Expected matrix in coordinate format");
@@ -117,10 +335,31 @@ SPMV_ABI_CATCH
 
 int spmvb200_mm_order_gp(spmvb200_mm_t mm, int32_t nparts, int32_t * new_order)
 try {
-    (void)nparts;
     if (!mm || !new_order) return fail(SPMVB200_ERR_INVALID, "null argument");
-    for (int32_t v = 0; v < mm->rows; v++) new_order[v] = v;
+    if (gp_partitioner()) return mm_order_gp_kway(mm, nparts, new_order);
+    for (int32_t v = 0; v < mm->rows; v++) new_order[v] = v;  // the reference without METIS
     return 0;
+}
+SPMV_ABI_CATCH
+
+int spmvb200_mm_order_gp_kway(spmvb200_mm_t mm, int32_t nparts, int32_t * new_order)
+try {
+    if (!mm || !new_order) return fail(SPMVB200_ERR_INVALID, "null argument");
+    return mm_order_gp_kway(mm, nparts, new_order);
+}
+SPMV_ABI_CATCH
+
+int spmvb200_mm_partition_kway(spmvb200_mm_t mm, int32_t nparts, int32_t ub_permille, int32_t * part, int64_t * edgecut)
+try {
+    if (!mm || (!part && mm->rows > 0)) return fail(SPMVB200_ERR_INVALID, "null argument");
+    return mm_partition_kway(mm, nparts, (double)ub_permille / 1000.0, part, edgecut);
+}
+SPMV_ABI_CATCH
+
+int spmvb200_order_from_parts(int32_t n, int32_t nparts, const int32_t * part, int32_t * new_order)
+try {
+    if (n > 0 && (!part || !new_order)) return fail(SPMVB200_ERR_INVALID, "null argument");
+    return order_from_parts(n, nparts, part, new_order);
 }
 SPMV_ABI_CATCH
 

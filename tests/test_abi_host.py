@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_text():
     L = _abi.lib()
-    assert L.spmvb200_version() == 200
+    assert L.spmvb200_version() == 210
     assert isinstance(L.spmvb200_last_error(), bytes)
 
 

@@ -134,6 +134,132 @@ def test_rcm_cost_is_linear_on_many_components():
     assert len(set(order.tolist())) == n
 
 
+# ---- graph-partitioning order (find_new_order_GP, matrix-market-reorder.cpp:183-278) ------------------------------
+
+def _edgecut(i, j, part):
+    """undirected simple edges whose ends lie in different parts"""
+    a, b = np.minimum(i, j) - 1, np.maximum(i, j) - 1
+    keep = a != b
+    e = np.unique(np.stack([a[keep], b[keep]], 1), axis=0)
+    return int((part[e[:, 0]] != part[e[:, 1]]).sum())
+
+
+def _grid7(n, shuffle_seed=None):
+    """3-D 7-point pattern on an n^3 grid (1-based entries), optionally with the vertices renumbered at random"""
+    from oracle.generators_ref import stencil_entries
+    i, j, a = stencil_entries(1, n, n, n)
+    i, j = i.astype(np.int64), j.astype(np.int64)
+    if shuffle_seed is not None:
+        p = np.random.default_rng(shuffle_seed).permutation(n ** 3)
+        i, j = p[i - 1] + 1, p[j - 1] + 1
+    return n ** 3, i.astype(np.int32), j.astype(np.int32), a
+
+
+def test_order_from_parts_matches_the_reference_loops(oracle):
+    """The grouping step after the METIS call (:246-266), restated in oracle/spmv_oracle.c loop for loop."""
+    rng = np.random.default_rng(3)
+    for n, k in ((1, 1), (17, 4), (1000, 16), (4096, 7), (50, 64)):
+        part = rng.integers(0, k, n).astype(np.int32)
+        if n > 20:
+            part[rng.integers(0, n, n // 3)] = k - 1  # uneven parts, possibly empty ones
+        want = oracle.order_from_parts(part, k)
+        got = matrix_market.order_from_parts(part, k)
+        assert np.array_equal(got, want)
+        assert sorted(got.tolist()) == list(range(n))
+        inv = np.argsort(got)  # inv[new] = old: parts ascend, old indices ascend inside a part
+        assert np.all(np.diff(part[inv]) >= 0)
+        for q in range(k):
+            assert np.all(np.diff(inv[part[inv] == q]) > 0)
+    with pytest.raises(sp.matrix_error):
+        matrix_market.order_from_parts(np.array([0, 5], np.int32), 4)
+
+
+@pytest.mark.parametrize("n,k,shuffled", [(12, 8, False), (12, 8, True), (10, 3, True), (16, 16, True)])
+def test_kway_partition_properties(n, k, shuffled):
+    """The METIS stand-in: a valid partition (every part number in range, none empty), inside the reference's balance
+    bound (ubvec = 1.05, :200), deterministic, independent of the vertex numbering up to quality, and with a cut far
+    below what the numbering it was given offers."""
+    N, i, j, a = _grid7(n, 11 if shuffled else None)
+    mm = matrix_market.from_entries(N, N, i, j, a)
+    part, cut = matrix_market.partition_kway(mm, k)
+    assert part.min() == 0 and part.max() == k - 1 and len(np.unique(part)) == k
+    sizes = np.bincount(part, minlength=k)
+    assert sizes.max() <= max(-(-N // k), int(1.05 * N / k))
+    assert cut == _edgecut(i, j, part)
+    part2, cut2 = matrix_market.partition_kway(mm, k)
+    assert np.array_equal(part, part2) and cut == cut2
+    contiguous = (np.arange(N, dtype=np.int64) * k // N).astype(np.int32)  # the reference row partition of this numbering
+    cut_contig = _edgecut(i, j, contiguous)
+    edges = _edgecut(i, j, np.arange(N, dtype=np.int32))  # every edge
+    # recursive level-structure bisection of a grid: no worse than 1.5 x what k axis-aligned slabs cut ((k - 1) n^2 edges)
+    assert cut <= 1.5 * (k - 1) * n * n < edges, (cut, edges)
+    if shuffled:
+        assert cut < cut_contig / 3, (cut, cut_contig)  # a random numbering cuts (k - 1)/k of all edges
+    # errors
+    with pytest.raises(sp.matrix_error):
+        matrix_market.partition_kway(mm, 0)
+    with pytest.raises(sp.matrix_error):
+        matrix_market.partition_kway(matrix_market.from_entries(3, 4, [1], [4], [1.0]), 2)
+
+
+def test_kway_partition_components_isolated_vertices_and_directed_entries():
+    # two chains, a star, isolated vertices; entries given in ONE direction only (the graph is made undirected)
+    i = np.concatenate([np.arange(1, 30), np.arange(41, 70), np.full(15, 80)]).astype(np.int32)
+    j = np.concatenate([np.arange(2, 31), np.arange(42, 71), np.arange(81, 96)]).astype(np.int32)
+    n = 120
+    mm = matrix_market.from_entries(n, n, np.concatenate([i, [5, 5]]), np.concatenate([j, [5, 6]]), np.ones(len(i) + 2))  # + diagonal, + duplicate
+    for k in (1, 2, 5, 120, 200):
+        part, cut = matrix_market.partition_kway(mm, k)
+        assert part.min() >= 0 and part.max() < k
+        assert np.bincount(part, minlength=k).max() <= max(-(-n // k), int(1.05 * n / k))
+        assert cut == _edgecut(np.concatenate([i, [5]]), np.concatenate([j, [6]]), part)
+        if k == 1:
+            assert cut == 0
+    part, cut = matrix_market.partition_kway(mm, 2)
+    assert cut <= 2  # two parts of 60: at most the chains are cut once each
+    empty = matrix_market.from_entries(0, 0, [], [], [])
+    part, cut = matrix_market.partition_kway(empty, 4)
+    assert part.size == 0 and cut == 0
+
+
+def test_gp_order_as_a_layout_lever_for_the_row_partition(tmp_path):
+    """What the reordering is FOR on this path: a shuffled grid makes every rank of the row-partitioned mode reference all
+    of x; after "__RCM" + the graph-partitioning order (the partitioner standing in for METIS) the ranks' rows reference
+    their own slice and a thin halo again -- seen in the exchange plan of the same 8-way row partition."""
+    n, P = 14, 8
+    N, i, j, a = _grid7(n, 5)
+    path = str(tmp_path / "shuffled.mtx")
+    with open(path, "w") as f:
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (N, N, len(i)))
+        for r, c, v in zip(i, j, a):
+            f.write("%d %d %.17g\n" % (r, c, v))
+    plain = matrix_market.load_matrix(path + "__GP%d" % P)  # default: identity, like the reference without METIS
+    assert np.array_equal(plain.row_indices(), i)
+    sp.set_global_option("mm.gp_partitioner", 1)
+    try:
+        gp = matrix_market.load_matrix(path + "__GP%d" % P)
+        both = matrix_market.load_matrix(path + "__GP%d__RCM" % P)  # RCM first, then GP (matrix-market.cpp:817-825)
+        assert np.array_equal(matrix_market.find_new_order_GP(matrix_market.load_matrix(path), P),
+                              matrix_market.find_new_order_GP(matrix_market.load_matrix(path), P, partitioner=True))
+    finally:
+        sp.set_global_option("mm.gp_partitioner", 0)
+    order = matrix_market.find_new_order_GP(matrix_market.load_matrix(path), P, partitioner=True)
+    assert np.array_equal(gp.row_indices(), order[i - 1] + 1) and np.array_equal(gp.column_indices(), order[j - 1] + 1)
+    assert sorted(zip(both.row_indices().tolist(), both.column_indices().tolist())) != sorted(zip(i.tolist(), j.tolist()))
+
+    def remote_columns(mm):
+        """columns outside the rank's own slice that its rows reference, summed over the ranks of the reference partition"""
+        starts = sp.partition.rows_ref(mm.rows, P)
+        r, c = mm.row_indices().astype(np.int64) - 1, mm.column_indices().astype(np.int64) - 1
+        owner_r = np.searchsorted(starts, r, side="right") - 1
+        owner_c = np.searchsorted(starts, c, side="right") - 1
+        far = owner_r != owner_c
+        return len(np.unique(owner_r[far] * mm.rows + c[far]))
+
+    shuffled, grouped, banded = remote_columns(plain), remote_columns(gp), remote_columns(both)
+    assert grouped < shuffled / 3 and banded < shuffled / 3, (shuffled, grouped, banded)
+
+
 if __name__ == "__main__" and "--make-golden" in sys.argv:
     cases = []
     for kind, seed in KINDS:
