@@ -1419,6 +1419,8 @@ static int64_t * option_slot(Matrix * m, const char * key)
     if (!strcmp(key, "csr.entries")) return &m->opt_csr_entries;
     if (!strcmp(key, "csr.rowptr_path")) return &m->opt_csr_rowptr_path;
     if (!strcmp(key, "csr.drop_row_major")) return &m->opt_csr_drop;
+    if (!strcmp(key, "csr.index_runs")) return &m->opt_csr_index_runs;
+    if (!strcmp(key, "csr.regs")) return &m->opt_csr_regs;
     if (!strcmp(key, "ell.rows_per_thread")) return &m->opt_ell_rows;
     if (!strcmp(key, "ell.block")) return &m->opt_ell_block;
     if (!strcmp(key, "coo.stages")) return &m->opt_coo_stages;
@@ -1457,6 +1459,11 @@ try {
         m->coo_colh = nullptr; m->coo_hot_cols = nullptr; m->coo_seg = nullptr;
         m->coo_hot_tried = false;
     }
+    if (*slot != value && slot == &m->opt_csr_index_runs && m->slice_col) {
+        // the slot-major copy was built under the old setting: back to row-major, the next launch / prepare rebuilds it
+        SPMV_CUDA(cudaSetDevice(m->device));
+        SPMV_TRY(csr_drop_sliced(m));
+    }
     *slot = value;
     return 0;
 }
@@ -1471,6 +1478,14 @@ try {
     }
     if (!strcmp(key, "coo.hot_coverage_permille")) {  // read-only: share of the gathers served from the hot-column tables
         *value = m->coo_colh ? (int64_t)(1000.0 * m->coo_hot_coverage + 0.5) : 0;
+        return 0;
+    }
+    if (!strcmp(key, "csr.index_runs_active")) {  // read-only: the sliced kernel's column stream is stored with index runs
+        *value = m->slice_col && m->slice_runs ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(key, "csr.index_columns_stored")) {  // read-only: int32 entries of that stream (= stored entries when plain)
+        *value = m->slice_col ? m->slice_ccount : 0;
         return 0;
     }
     if (!strcmp(key, "coo.hot_segments_built")) {

@@ -85,6 +85,12 @@ struct spmvb200_matrix_s {
     int32_t * flat_rowmap = nullptr;  // non-empty row number -> row
     int32_t * slice_col = nullptr;  // sliced kernel: column_index / value with every 32-row slice stored slot-major
     double * slice_val = nullptr;
+    // index runs of the slot-major copy: slice_col is then a COMPRESSED stream (one int32 for a slot whose 32 columns are
+    // base + lane); per slice a flag word (bit l: slot l is a run) and the slice's offset in the stream
+    uint32_t * slice_flags = nullptr;
+    void * slice_cofs = nullptr;    // uint32_t* or int64_t*, like rp; (rows/32 + 1) entries
+    bool slice_runs = false;
+    int64_t slice_ccount = 0;       // int32 entries in slice_col
     bool slice_unavailable = false;  // the copy could not be allocated: automatic selection stays with the flat kernel
     int64_t csr_maxlen = -1;       // longest row (computed on first use)
 
@@ -155,6 +161,8 @@ struct spmvb200_matrix_s {
     int64_t opt_csr_rmw = 0;      // sliced kernel, y += A*x: 1 = the owning lane updates y with a plain read-modify-write instead of a
                                   // reduction (needs the launches ordered); off by default: measured slower
     int64_t opt_csr_probe = 0;    // 1 regular traffic (values only), 2 irregular traffic (x gather only): csr-matrix-spmv.cpp:35-61
+    int64_t opt_csr_regs = 0;        // (experiment) sliced kernel with index runs: register budget 40 / 48 instead of 32
+    int64_t opt_csr_index_runs = 0;  // sliced kernel: 0 store index runs when they shrink the column stream to <= 3/4, 1 always, -1 never
     int64_t opt_csr_drop = 1;     // sliced kernel: free the row-major column_index/value once the slot-major copy exists (0 = keep both)
     int64_t opt_csr_spare = 0;    // CTA slots per SM left free (for a concurrent NCCL kernel)
     int64_t opt_ell_rows = 0;     // rows per thread (1, 2, 4), 0 = auto
@@ -283,6 +291,7 @@ bool csr_uses_sliced_kernel(Matrix * m);  // would launch_csr run the sliced ker
 // The row-major column_index / value of a CSR matrix may have been dropped in favour of the slot-major copy
 // ("csr.drop_row_major"); everything that reads them calls this first (rebuilds them from the copy).
 int csr_ensure_row_major(Matrix * m);
+int csr_drop_sliced(Matrix * m);  // rebuild the row-major arrays if needed and free the slot-major copy (an option that shapes it changed)
 
 // ---- builders.cu -----------------------------------------------------------------------------
 int matrix_new(Matrix ** out);

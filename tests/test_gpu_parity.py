@@ -953,6 +953,91 @@ def test_sliced_csr_can_drop_and_rebuild_the_row_major_copy(oracle):
     assert_within(A * x, yref, oracle.csr_abs_rowsum(O, x), "flat after drop")
 
 
+def test_sliced_csr_index_runs(oracle):
+    """Index runs of the slot-major copy: a slot whose 32 columns are base + lane is stored as ONE int32.  Same numbers
+    bit for bit, same exported arrays, with the runs on (automatic for a stencil), forced on a matrix that has almost
+    none, with rows longer than 32 entries (slots >= 32 are never runs), 64-bit offsets, row blocks and the row range
+    of the host path; switching the option rebuilds the copy."""
+    nx, ny, nz = 256, 6, 5  # x lines of 8 slices: the 6 that hold no x-boundary row are all runs
+    i, j, a = stencil_entries(2, nx, ny, nz)  # 27-point
+    N = nx * ny * nz
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, N)
+    y0 = rng.uniform(-1, 1, N)
+    O = oracle.csr(N, N, i, j, a)
+    yref = oracle.csr_spmv(O, x, y0)
+    A = sp.generators.stencil(sp.STENCIL_3D27, nx, ny, nz)
+    A.set_x(x); A.set_y(y0); A.spmv(); A.sync()
+    y = A.get_y()
+    assert A.kernel_name == "csr_sliced_kernel" and np.array_equal(y, yref)
+    assert A.get_option("csr.index_runs_active") == 1
+    stored = A.get_option("csr.index_columns_stored")
+    assert 0 < stored < 0.35 * A.num_entries, (stored, A.num_entries)  # 3/4 of the slices store one int32 per slot
+    e = A.export()  # rebuilt from the compressed stream
+    assert np.array_equal(e["row_ptr"], O.row_ptr) and np.array_equal(e["column_index"], O.column_index)
+    assert np.array_equal(e["value"], O.value)
+    assert np.array_equal(A * x, oracle.csr_spmv(O, x))
+    B = A.row_block(N // 3 + 5, 2 * N // 3)  # a block that does not start on a slice of the parent
+    assert np.array_equal(B * x, oracle.csr_spmv(O, x)[N // 3 + 5: 2 * N // 3]) and B.get_option("csr.index_runs_active") == 1
+    assert np.array_equal(A * x, oracle.csr_spmv(O, x))  # (the launch drops the row-major arrays row_block rebuilt)
+    bytes_runs = A.info.device_bytes
+    A.set_option("csr.index_runs", -1)  # the plain slot-major copy: rebuilt on the next launch
+    assert A.get_option("csr.index_runs_active") == 0
+    assert np.array_equal(A * x, oracle.csr_spmv(O, x))
+    assert A.get_option("csr.index_runs_active") == 0 and A.get_option("csr.index_columns_stored") == A.num_entries
+    assert A.info.device_bytes > bytes_runs + 2 * A.num_entries
+    A.set_option("csr.index_runs", 0)
+    assert np.array_equal(A * x, oracle.csr_spmv(O, x)) and A.get_option("csr.index_runs_active") == 1
+    # alpha and the store form (y = alpha A x) of the row-partitioned mode
+    A.set_alpha(0.25); A.set_option("beta0", 1)
+    assert np.array_equal(A * x, 0.25 * oracle.csr_spmv(O, x))
+    A.set_alpha(1.0); A.set_option("beta0", 0)
+
+    # a band of 40 diagonals (slots 32..39 stay explicit), a few irregular rows and empty rows mixed in, 64-bit offsets too
+    rows = 5000
+    offs = np.arange(-20, 20) * 3
+    ii, jj = [], []
+    for r in range(rows):
+        if r % 97 == 0:
+            continue  # empty row
+        c = r + offs
+        c = c[(c >= 0) & (c < rows)]
+        if r % 211 == 5:
+            c = np.unique(rng.integers(0, rows, 33))  # an irregular row breaks the runs of its slice
+        ii.append(np.full(len(c), r)); jj.append(c)
+    ii, jj = np.concatenate(ii), np.concatenate(jj)
+    aa = rng.uniform(-1, 1, len(ii))
+    x2 = rng.uniform(-1, 1, rows)
+    O2 = oracle.csr(rows, rows, (ii + 1).astype(np.int32), (jj + 1).astype(np.int32), aa)
+    y2 = oracle.csr_spmv(O2, x2)
+    mm = matrix_market.from_entries(rows, rows, (ii + 1).astype(np.int32), (jj + 1).astype(np.int32), aa)
+    for force64 in (0, 1):
+        sp.set_global_option("force_offsets64", force64)
+        try:
+            C = csr_matrix.from_matrix_market(mm)
+        finally:
+            sp.set_global_option("force_offsets64", 0)
+        C.set_option("csr.algo", 5)
+        for runs in (1, -1, 0):
+            C.set_option("csr.index_runs", runs)
+            for batch in (4, 2, 8):
+                C.set_option("csr.batch", batch)
+                assert np.array_equal(C * x2, y2), (force64, runs, batch)
+            assert C.get_option("csr.index_runs_active") == (0 if runs < 0 else 1)
+        e2 = C.export()
+        assert np.array_equal(e2["column_index"], O2.column_index) and np.array_equal(e2["value"], O2.value)
+    # a matrix without runs: forced, the stream is as long as the plain one; automatic leaves it alone
+    i3, j3, a3 = ragged_matrix(rng, 3000, 4000, long_rows=(3,), long_len=100, short_max=20)
+    O3 = oracle.csr(3000, 4000, i3, j3, a3)
+    x3 = rng.uniform(-1, 1, 4000)
+    D = csr_matrix.from_matrix_market(matrix_market.from_entries(3000, 4000, i3, j3, a3))
+    D.set_option("csr.algo", 5)
+    assert np.array_equal(D * x3, oracle.csr_spmv(O3, x3)) and D.get_option("csr.index_runs_active") == 0
+    D.set_option("csr.index_runs", 1)
+    assert np.array_equal(D * x3, oracle.csr_spmv(O3, x3)) and D.get_option("csr.index_runs_active") == 1
+    assert D.get_option("csr.index_columns_stored") > 0.9 * D.num_entries
+
+
 def test_launch_ordering_follows_the_data_hazards(oracle):
     """The library skips griddepcontrol.wait only when nothing in flight on its stream writes the launch's x or
     reads its y; every other API call, beta0, overlapping ranges and forced ordering bring the wait back."""
