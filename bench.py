@@ -472,6 +472,13 @@ def run_single_gpu(args):
     achieved = B / (k_ms * 1e-3) / 1e9
     kernel_name = A.kernel_name
     resident = int(A.info.device_bytes)
+    index_runs = None
+    if inf.format == sp.CSR and kernel_name == "csr_sliced_kernel":
+        index_runs = {"active": bool(A.get_option("csr.index_runs_active")),
+                      "column_indices_stored": int(A.get_option("csr.index_columns_stored")), "stored_entries": int(inf.num_entries),
+                      "what": "slot-major copy of the sliced kernel: a (32-row slice, slot) whose columns are base + lane stores ONE "
+                              "int32; values untouched, same summation order, bit-identical results.  algorithmic_bytes keep "
+                              "counting 4 B per column index like the reference's csr_matrix::size()"}
 
     # ---- end to end: host buffers through the C ABI ------------------------------------------------------------------
     e2e_steps = max(3, min(args.steps, 10 if copies == 1 else 50))
@@ -485,6 +492,15 @@ def run_single_gpu(args):
     ycheck = float(np.abs(ys[0].array).max())  # the e2e result is read, not just timed
     sampler.stop()
     clocks = sampler.summary(t0, t1)
+    if index_runs and index_runs["active"] and copies == 1:
+        # the same K steps with every column index stored (the copy is rebuilt): what the index runs are worth
+        A.set_option("csr.index_runs", -1)
+        sp.time_rotating(mats, 2, 0, False)
+        plain_ms, _ = sp.time_rotating(mats, args.steps, 0, False)
+        index_runs["ms_per_step_with_every_index_stored"] = plain_ms / args.steps
+        index_runs["traffic_with_every_index_stored"] = ncu_traffic(wl + "_plain_index")
+        A.set_option("csr.index_runs", 0)
+    traffic = ncu_traffic(wl)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -502,13 +518,17 @@ def run_single_gpu(args):
         "frac_of_8TBs_nominal": value / NOMINAL_HBM_GBS,
         "parity": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(wl), "kernel": kernel_name, "kernel_ms_mean": k_ms,
+                     "traffic": traffic, "dram_gbs": (traffic / (k_ms * 1e-3) / 1e9 if traffic else None),
+                     "dram_frac_of_peak": (traffic / (k_ms * 1e-3) / 1e9 / peak if traffic else None),
+                     "index_runs": index_runs, "kernel": kernel_name, "kernel_ms_mean": k_ms,
                      "isolated_launch_ms_mean": iso_ms, "isolated_launch_ms_median": float(np.median(per)),
                      "isolated_launch_gbs": B / (iso_ms * 1e-3) / 1e9, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(B),
                      "how": "CUDA events on the launching stream around the K launches of the timed region (kernel_ms_mean = "
                             "their average duration); isolated_launch_* = one event pair per launch in a second pass",
-                     "note": "peak is the driver's COPY bandwidth (read+write); a read-dominated stream can exceed it"},
+                     "note": "peak is the driver's COPY bandwidth (read+write); a read-dominated stream can exceed it.  achieved "
+                             "= ALGORITHMIC bytes / time; when index_runs.active the kernel moves fewer bytes than that "
+                             "(traffic, measured by ncu; dram_gbs = traffic / time is the physical DRAM rate)"},
         "e2e": {"value": B / e2e_t / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(8 * (inf.columns + inf.rows)),
                 "d2h_bytes_per_step": int(8 * inf.rows), "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                 "call": "spmvb200_spmv_host (pinned host x, y -> device, kernel, y -> host)", "max_abs_y": ycheck},
