@@ -85,8 +85,10 @@ struct spmvb200_matrix_s {
     int32_t * flat_rowmap = nullptr;  // non-empty row number -> row
     int32_t * slice_col = nullptr;  // sliced kernel: column_index / value with every 32-row slice stored slot-major
     double * slice_val = nullptr;
-    // index runs of the slot-major copy: slice_col is then a COMPRESSED stream (one int32 for a slot whose 32 columns are
-    // base + lane); per slice a flag word (bit l: slot l is a run) and the slice's offset in the stream
+    // index runs of the slot-major copy: slice_col is then a COMPRESSED stream -- a slice whose entries lie on few diagonals
+    // stores its slots by offset (column - row) with one descriptor per slot ({base, mask}, or the base alone when every slot
+    // holds all 32 rows), other slices their explicit columns; per slice a flag word (form + slot count) and the slice's
+    // offset in the stream (kernels_csr_sliced.cu)
     uint32_t * slice_flags = nullptr;
     void * slice_cofs = nullptr;    // uint32_t* or int64_t*, like rp; (rows/32 + 1) entries
     bool slice_runs = false;

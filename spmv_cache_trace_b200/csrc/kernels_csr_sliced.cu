@@ -20,17 +20,23 @@
 // Chosen automatically when the mean row length is at least 10 and the longest row at most twice the
 // mean (lanes idle while the longest row of their slice finishes); "csr.algo" = 5 forces it.
 //
-// INDEX RUNS.  In the slot-major order the 32 column indices of a slot are, for a banded matrix, one arithmetic run:
-// lane i holds column c0 + i (a stencil's rows are shifted copies of each other).  The builder detects that per
-// (slice, slot) -- all active lanes satisfy col == base + lane -- and stores ONE int32 for such a slot instead of up to
-// 32; a flag word per slice (bit l = slot l is a run; slots >= 32 are never runs) and the slice's offset in the
-// compressed column stream tell the kernel which form a slot has.  Values are not touched, every row is still summed
-// left to right from the same numbers: bit-identical results.  27-point 512^3: 88 % of the slots are runs (the rest are
-// the slices that contain a grid-boundary row), the column stream shrinks from 14.4 GB to about 2 GB, and the kernel
-// moves ~34 GB instead of 46 GB per product -- it is HBM-bound, so that is the speed-up.  The algorithmic bytes of the
-// metric keep counting 4 B per stored column index like the reference's csr_matrix::size(); the measured DRAM traffic is
-// reported beside them.  Used when the compressed stream is at most 3/4 of the plain one ("csr.index_runs": 0 auto,
-// 1 always, -1 never); a matrix without runs (R-MAT) keeps the plain slot-major copy.
+// INDEX RUNS ("diagonal" slices).  The rows of a banded matrix are shifted copies of each other: in a 32-row slice the
+// entries lie on a few diagonals, i.e. the set of distinct offsets d = column - row is small.  For such a slice the
+// builder lines the slots up by OFFSET instead of by position in the row: slot k holds the slice's k-th smallest offset,
+// a 32-bit mask says which rows have an entry there, and the 32 column indices of the slot are ONE number -- lane i's
+// column is base_k + i.  The column stream of the slice is then 8 B per slot {base, mask} instead of 4 B per entry, the
+// kernel needs no row_ptr (the masks say which lanes are active) and no ballot, and because all descriptors of a slice
+// arrive with one coalesced load, the gathers of x never wait for a column load: value loads and gathers of a batch are
+// in flight together (one memory round trip per batch instead of two).  Rows at a grid boundary, which lack some
+// neighbours, are simply holes in the masks, so every slice of a stencil qualifies whatever the grid's line length is.
+// Values are not touched and a row's entries still arrive in ascending column order: every row is summed left to right
+// from the same numbers, bit-identical to the reference.  A slice qualifies when no (row, column) pair occurs twice and
+// its descriptors take at most 3/4 of the bytes of its explicit indices; other slices (R-MAT) keep explicit indices
+// in the position-major order described above.  Per slice: a flag word (bit 31: diagonal form, low bits: slot count)
+// and the offset of its part of the column stream.  27-point 512^3: the column stream shrinks from 14.4 GB to 0.9 GB and
+// row_ptr is not read; the kernel is HBM-bound, so the bytes saved are the speed-up.  The algorithmic bytes of the metric
+// keep counting 4 B per stored column index like the reference's csr_matrix::size(); the measured DRAM traffic is
+// reported beside them.  Used when the whole stream shrinks to at most 3/4 ("csr.index_runs": 0 auto, 1 always, -1 never).
 #include "common.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -44,7 +50,19 @@ namespace spmvb200 {
 
 using namespace ptx;
 
-// One warp per slice: which slots are index runs (flag bit l) and how many int32 the slice's compressed column stream takes.
+constexpr uint32_t kSliceDiagonal = 0x80000000u;  // flag word: the slice is stored in diagonal form, low 24 bits = slots
+constexpr uint32_t kSliceDense = 0x40000000u;     // ... and every slot holds all 32 rows: the descriptors are bases only
+constexpr uint32_t kSliceSlots = 0x00ffffffu;
+constexpr int kNoOffset = INT_MAX;
+
+// The offset (column - row) of a lane's next entry, or kNoOffset when its row is exhausted.
+__device__ __forceinline__ int next_offset(const int32_t * __restrict__ col, int64_t lo, int k, int len, int64_t row)
+{
+    return k < len ? (int)((int64_t)col[lo + k] - row) : kNoOffset;
+}
+
+// One warp per slice: does it qualify for the diagonal form, how many slots, how many int32 of the column stream.
+// The lanes' rows are merged by offset: every round takes the smallest pending offset and the lanes that hold it.
 template <typename OffT>
 __global__ void csr_slice_scan_kernel(int64_t rows, const OffT * __restrict__ rp, const int32_t * __restrict__ col,
                                       uint32_t * __restrict__ flags, OffT * __restrict__ clen)
@@ -54,28 +72,33 @@ __global__ void csr_slice_scan_kernel(int64_t rows, const OffT * __restrict__ rp
     if (i - lane >= rows) return;
     const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
     const int len = (int)min(hi - lo, (int64_t)INT_MAX);
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    uint32_t fl = 0;
-    int64_t n = 0;
-    for (int l = 0; l < maxlen; ++l) {
-        const bool active = len > l;
-        const unsigned mask = __ballot_sync(0xffffffffu, active);
-        const int c = active ? col[lo + l] : 0;
-        const int first = __ffs(mask) - 1;
-        const int base = __shfl_sync(0xffffffffu, c, first) - first;  // column lane 0 would hold
-        const bool fits = !active || c == base + lane;
-        const bool run = l < 32 && __popc(mask) >= 2 && __all_sync(0xffffffffu, fits);
-        if (run) fl |= 1u << l;
-        n += run ? 1 : __popc(mask);
+    const int64_t entries = (i - lane + 32 <= rows ? (int64_t)rp[i - lane + 32] : (int64_t)rp[rows]) - (int64_t)rp[i - lane];
+    const int64_t limit = min(entries * 3 / 8, (int64_t)0x00ffffff);  // 8 B per slot <= 3/4 of 4 B per entry
+    int k = 0;
+    int64_t slots = 0;
+    bool ok = entries > 0, dense = true;
+    while (ok) {
+        const int d = next_offset(col, lo, k, len, i);
+        const int dmin = __reduce_min_sync(0xffffffffu, d);
+        if (dmin == kNoOffset) break;
+        bool dup = false;
+        if (d == dmin) {
+            ++k;
+            dup = next_offset(col, lo, k, len, i) == dmin;  // the same (row, column) twice: two entries for one slot
+        }
+        if (!__all_sync(0xffffffffu, d == dmin)) dense = false;
+        if (++slots > limit || __any_sync(0xffffffffu, dup)) ok = false;
     }
     if (lane == 0) {
-        flags[i >> 5] = fl;
-        clen[i >> 5] = (OffT)n;
+        flags[i >> 5] = ok ? (kSliceDiagonal | (dense ? kSliceDense : 0u) | (uint32_t)slots) : 0u;
+        // even lengths: the {base, mask} descriptors are read as 8-byte pairs
+        clen[i >> 5] = (OffT)(!ok ? ((entries + 1) & ~(int64_t)1) : dense ? ((slots + 1) & ~(int64_t)1) : 2 * slots);
     }
 }
 
-// One warp per slice: copy the slice's entries from row-major to slot-major order.  With `flags` the column indices go
-// to the compressed stream (one int32 = the column of lane 0 for a run slot), at the slice's offset cofs[slice].
+// One warp per slice: copy the slice's entries from row-major to slot-major order -- position-major with explicit column
+// indices, or (flag word) offset-major with one {base, mask} descriptor per slot.  Without `flags` the column indices go
+// where the values go (the plain copy: scol and sval are parallel arrays).
 template <typename OffT>
 __global__ void csr_slice_fill_kernel(int64_t rows, const OffT * __restrict__ rp, const int32_t * __restrict__ col,
                                       const double * __restrict__ val, int32_t * __restrict__ scol, double * __restrict__ sval,
@@ -87,23 +110,38 @@ __global__ void csr_slice_fill_kernel(int64_t rows, const OffT * __restrict__ rp
     const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
     const int len = (int)min(hi - lo, (int64_t)INT_MAX);
     int64_t pos = __shfl_sync(0xffffffffu, lo, 0);
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    uint32_t fl = flags ? flags[i >> 5] : 0u;
+    const unsigned below = (1u << lane) - 1u;
+    const uint32_t fl = flags ? flags[i >> 5] : 0u;
     int64_t cpos = flags ? (int64_t)cofs[i >> 5] : pos;
+    if (fl & kSliceDiagonal) {
+        int k = 0;
+        for (;;) {
+            const int d = next_offset(col, lo, k, len, i);
+            const int dmin = __reduce_min_sync(0xffffffffu, d);
+            if (dmin == kNoOffset) break;
+            const bool active = d == dmin;
+            const unsigned mask = __ballot_sync(0xffffffffu, active);
+            if (active) sval[pos + __popc(mask & below)] = val[lo + k++];
+            if (lane == 0) {
+                scol[cpos] = (int32_t)((i + dmin));  // the column lane 0 would hold: lane j's column is this + j
+                if (!(fl & kSliceDense)) scol[cpos + 1] = (int32_t)mask;
+            }
+            pos += __popc(mask);
+            cpos += (fl & kSliceDense) ? 1 : 2;
+        }
+        return;
+    }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
     for (int l = 0; l < maxlen; ++l) {
         const bool active = len > l;
         const unsigned mask = __ballot_sync(0xffffffffu, active);
-        const int rank = __popc(mask & ((1u << lane) - 1u));
-        const bool run = fl & 1u;
-        fl >>= 1;
+        const int rank = __popc(mask & below);
         if (active) {
             sval[pos + rank] = val[lo + l];
-            const int c = col[lo + l];
-            if (!run) scol[cpos + rank] = c;
-            else if (rank == 0) scol[cpos] = c - lane;
+            scol[cpos + rank] = col[lo + l];
         }
         pos += __popc(mask);
-        cpos += run ? 1 : __popc(mask);
+        cpos += __popc(mask);
     }
 }
 
@@ -119,21 +157,35 @@ __global__ void csr_slice_unfill_kernel(int64_t rows, const OffT * __restrict__ 
     const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
     const int len = (int)min(hi - lo, (int64_t)INT_MAX);
     int64_t pos = __shfl_sync(0xffffffffu, lo, 0);
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    uint32_t fl = flags ? flags[i >> 5] : 0u;
+    const unsigned below = (1u << lane) - 1u;
+    const uint32_t fl = flags ? flags[i >> 5] : 0u;
     int64_t cpos = flags ? (int64_t)cofs[i >> 5] : pos;
+    if (fl & kSliceDiagonal) {
+        const int slots = (int)(fl & kSliceSlots);
+        int k = 0;
+        for (int t = 0; t < slots; ++t) {
+            const int base = (fl & kSliceDense) ? scol[cpos + t] : scol[cpos + 2 * t];
+            const unsigned mask = (fl & kSliceDense) ? 0xffffffffu : (unsigned)scol[cpos + 2 * t + 1];
+            if ((mask >> lane) & 1u) {
+                col[lo + k] = base + lane;
+                val[lo + k] = sval[pos + __popc(mask & below)];
+                ++k;
+            }
+            pos += __popc(mask);
+        }
+        return;
+    }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
     for (int l = 0; l < maxlen; ++l) {
         const bool active = len > l;
         const unsigned mask = __ballot_sync(0xffffffffu, active);
-        const int rank = __popc(mask & ((1u << lane) - 1u));
-        const bool run = fl & 1u;
-        fl >>= 1;
+        const int rank = __popc(mask & below);
         if (active) {
-            col[lo + l] = run ? scol[cpos] + lane : scol[cpos + rank];
+            col[lo + l] = scol[cpos + rank];
             val[lo + l] = sval[pos + rank];
         }
         pos += __popc(mask);
-        cpos += run ? 1 : __popc(mask);
+        cpos += __popc(mask);
     }
 }
 
@@ -170,82 +222,112 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
     // rows [row0, rows) of the matrix (row0 a multiple of 32: a warp is a slice)
     const int64_t i = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i - lane >= rows) return;  // whole warp past the end
-    const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
-    const int len = (int)min(hi - lo, (int64_t)INT_MAX);
-    int64_t pos = __shfl_sync(0xffffffffu, lo, 0);  // offset of the slice = row_ptr of its first row
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
     const unsigned below = (1u << lane) - 1u;
     double z = 0.0;
     bool waited = independent != 0;
-    // index runs: the slice's flag word (bit l: slot l is stored as ONE column, lane i holds column + i) and its place
-    // in the compressed column stream; cq counts the int32 consumed so far
-    uint32_t fl = 0;
-    OffT cq = 0;  // position in the compressed column stream (32-bit whenever row_ptr is)
-    if (RUNS) {
-        fl = __ldg(sflags + (i >> 5));
-        cq = __ldg(scofs + (i >> 5));
-    }
-    // The common case of a banded matrix: all 32 rows of the slice have the same length and every slot is a run.  Then
-    // slot l's values are the 32 doubles at pos + 32 l, its column is stream[l] + lane, and ONE coalesced load brings the
-    // whole column stream of the slice (<= 32 int32) into the warp: the gathers no longer wait for a column load, so the
-    // value loads and the gathers of a batch are in flight together -- one memory round trip per batch instead of two.
-    if (RUNS && maxlen <= 32 && fl == (0xffffffffu >> (32 - maxlen)) && __all_sync(0xffffffffu, len == maxlen)) {
-        const int32_t cb = lane < maxlen ? __ldg(scol + (cq + (OffT)lane)) : 0;
-        const double * sv = sval + pos + lane;
-        for (int l0 = 0; l0 < maxlen; l0 += U) {
-            double a[U], xv[U];
+    int len = 0;  // > 0: the row has entries (diagonal form: 1 stands for "some")
+    const uint32_t fl = RUNS ? __ldg(sflags + (i >> 5)) : 0u;
+    if (RUNS && (fl & kSliceDiagonal)) {
+        // Diagonal form: slot k of the slice = its k-th smallest offset (column - row); descriptor {base, mask}: lane j has an
+        // entry iff bit j of mask is set, and its column is base + j.  Values in slot order, active lanes ascending.
+        const int slots = (int)(fl & kSliceSlots);
+        const double * sv = sval + (int64_t)__ldg(rp + (i - lane));  // the slice's entries start at row_ptr of its first row
+        unsigned seen = 0;
+        if (fl & kSliceDense) {
+            // every slot holds all 32 rows (the interior of a grid line): descriptors are bases only, slot t's values are
+            // the 32 doubles at 32 t
+            const int32_t * __restrict__ bases = scol + __ldg(scofs + (i >> 5));
+            sv += lane;
+            for (int t0 = 0; t0 < slots; t0 += 32) {
+                const int32_t mine = t0 + lane < slots ? __ldg(bases + t0 + lane) : 0;
+                const int n = min(32, slots - t0);
+                for (int l0 = 0; l0 < n; l0 += U) {
+                    double a[U], xv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = l0 + u < maxlen ? __ldg(sv + 32 * (l0 + u)) : 0.0;
-            if (!waited) {
+                    for (int u = 0; u < U; ++u) a[u] = l0 + u < n ? __ldg(sv + 32 * (l0 + u)) : 0.0;
+                    if (!waited) {
+                        asm volatile("griddepcontrol.wait;" ::: "memory");
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int32_t base = __shfl_sync(0xffffffffu, mine, (l0 + u) & 31);
+                        xv[u] = l0 + u < n ? ldx(x + base + lane) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (l0 + u < n) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
+                }
+                sv += 32 * n;
+            }
+            seen = 1;
+        } else {
+        const int2 * __restrict__ desc = reinterpret_cast<const int2 *>(scol + __ldg(scofs + (i >> 5)));
+        for (int t0 = 0; t0 < slots; t0 += 32) {
+            const int2 mine = t0 + lane < slots ? __ldg(desc + t0 + lane) : make_int2(0, 0);  // all descriptors: one coalesced load
+            const int n = min(32, slots - t0);
+            for (int l0 = 0; l0 < n; l0 += U) {
+                double a[U], xv[U];
+                int c[U];
+                unsigned act = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {  // slots beyond n read descriptor {0, 0} of an idle lane or a real one: masked off
+                    const unsigned mask = l0 + u < n ? (unsigned)__shfl_sync(0xffffffffu, mine.y, (l0 + u) & 31) : 0u;
+                    c[u] = __shfl_sync(0xffffffffu, mine.x, (l0 + u) & 31) + lane;
+                    const bool active = (mask >> lane) & 1u;
+                    act |= (active ? 1u : 0u) << u;
+                    a[u] = active ? __ldg(sv + __popc(mask & below)) : 0.0;
+                    sv += __popc(mask);
+                }
+                if (!waited) {  // the matrix is immutable; x and y may come from the previous launch
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    waited = true;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] = (act >> u) & 1u ? ldx(x + c[u]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if ((act >> u) & 1u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
+                seen |= act;
+            }
+        }
+        }
+        len = seen ? 1 : 0;
+    } else {
+        const int64_t lo = i < rows ? (int64_t)rp[i] : 0, hi = i < rows ? (int64_t)rp[i + 1] : 0;
+        len = (int)min(hi - lo, (int64_t)INT_MAX);
+        int64_t pos = __shfl_sync(0xffffffffu, lo, 0);  // offset of the slice = row_ptr of its first row
+        // with index runs the explicit columns of this slice sit at its offset in the column stream, else beside the values
+        int64_t cdelta = 0;
+        if (RUNS) cdelta = (int64_t)__ldg(scofs + (i >> 5)) - pos;
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        for (int l0 = 0; l0 < maxlen; l0 += U) {
+            int c[U];
+            double a[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {  // warp-uniform trip count: every lane takes part in the ballots
+                const bool active = len > l0 + u;
+                const unsigned mask = __ballot_sync(0xffffffffu, active);
+                const int64_t p = pos + __popc(mask & below);
+                // Plain read-only loads (L1 allocation, normal L2 policy), unlike the other kernels' streams: a
+                // slot's 128 / 256 B of a slice start wherever the previous slot ended, so consecutive requests share
+                // sectors, and with L1::no_allocate + L2 evict-first the shared sectors were fetched from DRAM twice
+                // (6.06 GB read for 5.73 GB on 27-point 256^3; 512^3: 7.31 -> 7.00 ms with plain loads).
+                c[u] = active ? __ldg(scol + (RUNS ? p + cdelta : p)) : 0;
+                a[u] = active ? __ldg(sval + p) : 0.0;
+                pos += __popc(mask);
+            }
+            if (!waited) {  // the matrix is immutable; x and y may come from the previous launch
                 asm volatile("griddepcontrol.wait;" ::: "memory");
                 waited = true;
             }
+            double xv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int32_t base = __shfl_sync(0xffffffffu, cb, (l0 + u) & 31);
-                xv[u] = l0 + u < maxlen ? ldx(x + base + lane) : 0.0;
-            }
+            for (int u = 0; u < U; ++u) xv[u] = len > l0 + u ? ldx(x + c[u]) : 0.0;
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (l0 + u < maxlen) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
+                if (len > l0 + u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
         }
-    } else
-    for (int l0 = 0; l0 < maxlen; l0 += U) {
-        int c[U];
-        double a[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {  // warp-uniform trip count: every lane takes part in the ballots
-            const bool active = len > l0 + u;
-            const unsigned mask = __ballot_sync(0xffffffffu, active);
-            const int64_t p = pos + __popc(mask & below);
-            if (RUNS) {
-                const bool run = fl & 1u;  // warp-uniform
-                fl >>= 1;
-                const int32_t raw = active ? __ldg(scol + (cq + (OffT)(run ? 0 : __popc(mask & below)))) : 0;
-                c[u] = run ? raw + lane : raw;
-                a[u] = active ? __ldg(sval + p) : 0.0;
-                pos += __popc(mask);
-                cq += (OffT)(run ? 1 : __popc(mask));
-                continue;
-            }
-            // Plain read-only loads (L1 allocation, normal L2 policy), unlike the other kernels' streams: a
-            // slot's 128 / 256 B of a slice start wherever the previous slot ended, so consecutive requests share
-            // sectors, and with L1::no_allocate + L2 evict-first the shared sectors were fetched from DRAM twice
-            // (6.06 GB read for 5.73 GB on 27-point 256^3; 512^3: 7.31 -> 7.00 ms with plain loads).
-            c[u] = active ? __ldg(scol + p) : 0;
-            a[u] = active ? __ldg(sval + p) : 0.0;
-            pos += __popc(mask);
-        }
-        if (!waited) {  // the matrix is immutable; x and y may come from the previous launch
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            waited = true;
-        }
-        double xv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = len > l0 + u ? ldx(x + c[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (len > l0 + u) z = __dadd_rn(z, __dmul_rn(a[u], xv[u]));
     }
     if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
     // Zero-copy form (spmvb200_spmv_host with pinned buffers): y_old is read from and y_new written to mapped HOST
@@ -394,20 +476,17 @@ __global__ void csr_chunk_colmax_kernel(int64_t rows, int64_t rows_per_chunk, co
     if (!flags) {
         const int64_t lo = (int64_t)rp[r0], hi = (int64_t)rp[min(r0 + 32, rows)];
         for (int64_t k = lo + lane; k < hi; k += 32) best = max(best, __ldg(scol + k));
-    } else {  // compressed column stream: walk the slots like the SpMV kernel does
-        const int64_t i = r0 + lane;
-        const int len = i < rows ? (int)min((int64_t)rp[i + 1] - (int64_t)rp[i], (int64_t)INT_MAX) : 0;
-        const int maxlen = __reduce_max_sync(0xffffffffu, len);
-        uint32_t fl = flags[slice];
-        int64_t cpos = (int64_t)cofs[slice];
-        for (int l = 0; l < maxlen; ++l) {
-            const bool active = len > l;
-            const unsigned mask = __ballot_sync(0xffffffffu, active);
-            const bool run = fl & 1u;
-            fl >>= 1;
-            if (active) best = max(best, run ? __ldg(scol + cpos) + lane : __ldg(scol + cpos + __popc(mask & ((1u << lane) - 1u))));
-            cpos += run ? 1 : __popc(mask);
+    } else if (flags[slice] & kSliceDiagonal) {  // descriptors {base, mask}: the largest column of a slot is base + highest lane
+        const int slots = (int)(flags[slice] & kSliceSlots);
+        const bool dense = flags[slice] & kSliceDense;
+        const int64_t cpos = (int64_t)cofs[slice];
+        for (int t = lane; t < slots; t += 32) {
+            const unsigned mask = dense ? 0xffffffffu : (unsigned)__ldg(scol + cpos + 2 * t + 1);
+            if (mask) best = max(best, __ldg(scol + cpos + (dense ? t : 2 * t)) + 31 - __clz(mask));
         }
+    } else {  // explicit columns at the slice's place in the column stream
+        const int64_t n = (int64_t)rp[min(r0 + 32, rows)] - (int64_t)rp[r0], cpos = (int64_t)cofs[slice];
+        for (int64_t k = lane; k < n; k += 32) best = max(best, __ldg(scol + cpos + k));
     }
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0 && best >= 0) atomicMax(colmax + r0 / rows_per_chunk, best);
@@ -453,8 +532,6 @@ int launch_csr_sliced(Matrix * m)
     do {                                                                                                                  \
         if (m->slice_runs && UU == 4 && TT == 128 && m->opt_csr_regs == 40)                                               \
             SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT, false, true, (UU == 4 && TT == 128 ? 40 : 32)>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, SPMV_SLICED_ARGS(OFF))); \
-        else if (m->slice_runs && UU == 4 && TT == 128 && m->opt_csr_regs == 48)                                          \
-            SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT, false, true, (UU == 4 && TT == 128 ? 48 : 32)>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, SPMV_SLICED_ARGS(OFF))); \
         else if (m->slice_runs)                                                                                           \
             SPMV_CUDA(launch_kernel(csr_sliced_kernel<OFF, UU, TT, false, true>, (unsigned)grid, (unsigned)TT, 0, m->stream, rm.pdl, SPMV_SLICED_ARGS(OFF))); \
         else                                                                                                              \

@@ -1,12 +1,7 @@
-# index runs of the sliced CSR kernel: tests, short-row matrices, ncu traffic of the headline kernel
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_dist.py -m gpu -q -x -k "sliced or spmv_host or ping_pong or stencil or push or alpha or config5 or dist" > gpurun_out/w3_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/w3_pytest.log
-python tools/run_workload.py c1_csr --copies 17 --steps 2000 --warmup 200 --sweep csr.algo=0,5 > gpurun_out/w3_sweep.log 2>&1
-python tools/run_workload.py c2_csr --copies 8 --steps 2000 --warmup 200 --sweep csr.algo=0,5 >> gpurun_out/w3_sweep.log 2>&1
-cat gpurun_out/w3_sweep.log
-W="python tools/run_workload.py c5_csr --steps 2 --warmup 1"
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:csr_sliced -s 1 -c 2 --csv \
-    --log-file gpurun_out/r03_traffic_c5_csr.csv $W > gpurun_out/w3_ncu_c5.log 2>&1
-echo "c5 traffic rc=$?"; tail -3 gpurun_out/r03_traffic_c5_csr.csv | cut -c100-420
-W2="python tools/run_workload.py c5s_csr --steps 2 --warmup 1"
-$W2 > gpurun_out/w3_plain_c5s.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:csr_sliced -s 1 -c 1 -o gpurun_out/r03_prof_c5s_csr_runs -f $W2 > gpurun_out/w3_ncu_c5s.log 2>&1
-echo "c5s full rc=$?"; tail -2 gpurun_out/w3_ncu_c5s.log
+# diagonal slices of the sliced CSR kernel: tests, then timings
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "sliced or spmv_host or ping_pong or alpha or config1 or stencil" > gpurun_out/w4_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/w4_pytest.log
+python tools/run_workload.py c5s_csr --steps 20 --sweep csr.index_runs=-1,0 --sweep csr.regs=0,40 > gpurun_out/w4_sweep.log 2>&1
+python tools/run_workload.py c5_csr --steps 10 --opt csr.index_runs=0 --sweep csr.batch=4,8 --sweep csr.regs=0,40 >> gpurun_out/w4_sweep.log 2>&1
+python tools/run_workload.py c1_csr --copies 17 --steps 2000 --warmup 200 --sweep csr.algo=0,5 >> gpurun_out/w4_sweep.log 2>&1
+python tools/run_workload.py c2_csr --copies 8 --steps 2000 --warmup 200 --sweep csr.algo=0,5 >> gpurun_out/w4_sweep.log 2>&1
+cat gpurun_out/w4_sweep.log
