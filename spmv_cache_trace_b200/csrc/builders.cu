@@ -79,7 +79,7 @@ void matrix_free(Matrix * m)
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    cudaFree(m->rp); cudaFree(m->col); cudaFree(m->val); cudaFree(m->tile_row); cudaFree(m->span_row); cudaFree(m->flat_meta); cudaFree(m->flat_rowmap); cudaFree(m->slice_col); cudaFree(m->slice_val); cudaFree(m->slice_flags); cudaFree(m->slice_cofs);
+    cudaFree(m->rp); cudaFree(m->col); cudaFree(m->val); cudaFree(m->tile_row); cudaFree(m->span_row); cudaFree(m->flat_meta); cudaFree(m->flat_rowmap); cudaFree(m->slice_col); cudaFree(m->slice_val); cudaFree(m->slice_flags); cudaFree(m->slice_cofs); cudaFree(m->slice_meta);
     cudaFree(m->ell_col); cudaFree(m->ell_val);
     cudaFree(m->coo_row); cudaFree(m->coo_col); cudaFree(m->coo_val);
     cudaFree(m->coo_colh); cudaFree(m->coo_hot_cols); cudaFree(m->coo_seg);

@@ -91,6 +91,7 @@ struct spmvb200_matrix_s {
     // offset in the stream (kernels_csr_sliced.cu)
     uint32_t * slice_flags = nullptr;
     void * slice_cofs = nullptr;    // uint32_t* or int64_t*, like rp; (rows/32 + 1) entries
+    void * slice_meta = nullptr;    // {flags, cofs, row_ptr[32 s], -} per slice in one 16 / 32-byte record (what the SpMV kernel reads)
     bool slice_runs = false;
     int64_t slice_ccount = 0;       // int32 entries in slice_col
     bool slice_unavailable = false;  // the copy could not be allocated: automatic selection stays with the flat kernel

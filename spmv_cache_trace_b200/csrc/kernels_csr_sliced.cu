@@ -209,13 +209,40 @@ int csr_ensure_row_major(Matrix * m)
     return 0;
 }
 
+// What the SpMV kernel needs to know about a slice, in ONE 16- or 32-byte record (one broadcast load at the start of a warp's
+// life instead of three dependent ones): the flag word, the slice's place in the column stream, and its place in the values
+// (= row_ptr of its first row).
+template <typename OffT>
+struct SliceMeta {
+    OffT flags, cofs, vofs, pad;
+};
+
+__device__ __forceinline__ void load_slice_meta(const SliceMeta<uint32_t> * p, uint32_t & fl, int64_t & cofs, int64_t & vofs)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    fl = v.x; cofs = v.y; vofs = v.z;
+}
+__device__ __forceinline__ void load_slice_meta(const SliceMeta<int64_t> * p, uint32_t & fl, int64_t & cofs, int64_t & vofs)
+{
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(p)), b = __ldg(reinterpret_cast<const longlong2 *>(p) + 1);
+    fl = (uint32_t)a.x; cofs = a.y; vofs = b.x;
+}
+
+template <typename OffT>
+__global__ void csr_slice_meta_kernel(int64_t nslices, const OffT * __restrict__ rp, const uint32_t * __restrict__ flags,
+                                      const OffT * __restrict__ cofs, SliceMeta<OffT> * __restrict__ meta)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslices) meta[s] = SliceMeta<OffT>{(OffT)flags[s], cofs[s], rp[32 * s], 0};
+}
+
 template <typename OffT, int U, int THREADS, bool PUSH = false, bool RUNS = false, int REGS = (U <= 4 ? 32 : 64)>
 __global__ void __launch_bounds__(THREADS, 65536 / REGS / THREADS)
 csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double alpha, const OffT * __restrict__ rp,
                   const int32_t * __restrict__ scol, const double * __restrict__ sval, const double * __restrict__ x,
                   double * __restrict__ y, const double * __restrict__ y_in_host, double * __restrict__ y_out_host,
                   double * push0, int64_t push0_lo, int64_t push0_hi, double * push1, int64_t push1_lo, int64_t push1_hi,
-                  const uint32_t * __restrict__ sflags, const OffT * __restrict__ scofs)
+                  const SliceMeta<OffT> * __restrict__ smeta)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
@@ -226,17 +253,19 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
     double z = 0.0;
     bool waited = independent != 0;
     int len = 0;  // > 0: the row has entries (diagonal form: 1 stands for "some")
-    const uint32_t fl = RUNS ? __ldg(sflags + (i >> 5)) : 0u;
+    uint32_t fl = 0;
+    int64_t cofs = 0, vofs = 0;
+    if (RUNS) load_slice_meta(smeta + (i >> 5), fl, cofs, vofs);
     if (RUNS && (fl & kSliceDiagonal)) {
         // Diagonal form: slot k of the slice = its k-th smallest offset (column - row); descriptor {base, mask}: lane j has an
         // entry iff bit j of mask is set, and its column is base + j.  Values in slot order, active lanes ascending.
         const int slots = (int)(fl & kSliceSlots);
-        const double * sv = sval + (int64_t)__ldg(rp + (i - lane));  // the slice's entries start at row_ptr of its first row
+        const double * sv = sval + vofs;  // the slice's entries start at row_ptr of its first row
         unsigned seen = 0;
         if (fl & kSliceDense) {
             // every slot holds all 32 rows (the interior of a grid line): descriptors are bases only, slot t's values are
             // the 32 doubles at 32 t
-            const int32_t * __restrict__ bases = scol + __ldg(scofs + (i >> 5));
+            const int32_t * __restrict__ bases = scol + cofs;
             sv += lane;
             for (int t0 = 0; t0 < slots; t0 += 32) {
                 const int32_t mine = t0 + lane < slots ? __ldg(bases + t0 + lane) : 0;
@@ -262,7 +291,7 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
             }
             seen = 1;
         } else {
-        const int2 * __restrict__ desc = reinterpret_cast<const int2 *>(scol + __ldg(scofs + (i >> 5)));
+        const int2 * __restrict__ desc = reinterpret_cast<const int2 *>(scol + cofs);
         for (int t0 = 0; t0 < slots; t0 += 32) {
             const int2 mine = t0 + lane < slots ? __ldg(desc + t0 + lane) : make_int2(0, 0);  // all descriptors: one coalesced load
             const int n = min(32, slots - t0);
@@ -299,7 +328,7 @@ csr_sliced_kernel(int64_t row0, int64_t rows, int independent, int store, double
         int64_t pos = __shfl_sync(0xffffffffu, lo, 0);  // offset of the slice = row_ptr of its first row
         // with index runs the explicit columns of this slice sit at its offset in the column stream, else beside the values
         int64_t cdelta = 0;
-        if (RUNS) cdelta = (int64_t)__ldg(scofs + (i >> 5)) - pos;
+        if (RUNS) cdelta = cofs - pos;
         const int maxlen = __reduce_max_sync(0xffffffffu, len);
         for (int l0 = 0; l0 < maxlen; l0 += U) {
             int c[U];
@@ -398,8 +427,10 @@ static void csr_free_index_runs(Matrix * m)
     const int64_t nslices = (m->rows + 31) / 32;
     if (m->slice_flags) { cudaFree(m->slice_flags); m->device_bytes -= 4 * nslices; }
     if (m->slice_cofs) { cudaFree(m->slice_cofs); m->device_bytes -= (m->off64 ? 8 : 4) * (nslices + 1); }
+    if (m->slice_meta) { cudaFree(m->slice_meta); m->device_bytes -= (m->off64 ? 32 : 16) * nslices; }
     m->slice_flags = nullptr;
     m->slice_cofs = nullptr;
+    m->slice_meta = nullptr;
     m->slice_runs = false;
 }
 
@@ -440,6 +471,18 @@ static int csr_build_sliced(Matrix * m)
     if (m->off64) csr_slice_fill_kernel<int64_t><<<grid, 128, 0, m->stream>>>(m->rows, (const int64_t *)m->rp, m->col, m->val, m->slice_col, m->slice_val, m->slice_flags, (const int64_t *)m->slice_cofs);
     else csr_slice_fill_kernel<uint32_t><<<grid, 128, 0, m->stream>>>(m->rows, (const uint32_t *)m->rp, m->col, m->val, m->slice_col, m->slice_val, m->slice_flags, (const uint32_t *)m->slice_cofs);
     SPMV_CUDA(cudaGetLastError());
+    if (m->slice_runs) {  // the fused per-slice records the SpMV kernel reads
+        const size_t bytes = (m->off64 ? 32 : 16) * (size_t)nslices;
+        if (cudaMalloc(&m->slice_meta, bytes ? bytes : 16) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SPMVB200_ERR_NOMEM, "out of device memory for the slice records");
+        }
+        m->device_bytes += (int64_t)bytes;
+        const unsigned g2 = (unsigned)((nslices + 255) / 256);
+        if (m->off64) csr_slice_meta_kernel<int64_t><<<g2, 256, 0, m->stream>>>(nslices, (const int64_t *)m->rp, m->slice_flags, (const int64_t *)m->slice_cofs, (SliceMeta<int64_t> *)m->slice_meta);
+        else csr_slice_meta_kernel<uint32_t><<<g2, 256, 0, m->stream>>>(nslices, (const uint32_t *)m->rp, m->slice_flags, (const uint32_t *)m->slice_cofs, (SliceMeta<uint32_t> *)m->slice_meta);
+        SPMV_CUDA(cudaGetLastError());
+    }
     m->aux_dirty = true;
     return csr_drop_row_major(m);
 }
@@ -527,7 +570,7 @@ int launch_csr_sliced(Matrix * m)
     row0, row1, rm.independent, store, m->alpha, (const OFF *)m->rp, (const int32_t *)m->slice_col,                       \
         (const double *)m->slice_val, (const double *)m->x, m->y, (const double *)m->host_y_in, m->host_y_out,            \
         m->push_y[0], m->push_lo[0], m->push_hi[0], m->push_y[1], m->push_lo[1], m->push_hi[1],                            \
-        (const uint32_t *)m->slice_flags, (const OFF *)m->slice_cofs
+        (const SliceMeta<OFF> *)m->slice_meta
 #define SPMV_SLICED(OFF, UU, TT)                                                                                          \
     do {                                                                                                                  \
         if (m->slice_runs && UU == 4 && TT == 128 && m->opt_csr_regs == 40)                                               \
