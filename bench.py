@@ -476,9 +476,10 @@ def run_single_gpu(args):
     if inf.format == sp.CSR and kernel_name == "csr_sliced_kernel":
         index_runs = {"active": bool(A.get_option("csr.index_runs_active")),
                       "column_indices_stored": int(A.get_option("csr.index_columns_stored")), "stored_entries": int(inf.num_entries),
-                      "what": "slot-major copy of the sliced kernel: a (32-row slice, slot) whose columns are base + lane stores ONE "
-                              "int32; values untouched, same summation order, bit-identical results.  algorithmic_bytes keep "
-                              "counting 4 B per column index like the reference's csr_matrix::size()"}
+                      "what": "slot-major copy of the sliced kernel: a 32-row slice whose entries lie on few diagonals stores its "
+                              "slots by offset (column - row), one descriptor per slot instead of up to 32 column indices, and needs "
+                              "no row_ptr; values untouched, same summation order, bit-identical results.  algorithmic_bytes keep "
+                              "counting 4 B per column index and row_ptr like the reference's csr_matrix::size()"}
 
     # ---- end to end: host buffers through the C ABI ------------------------------------------------------------------
     e2e_steps = max(3, min(args.steps, 10 if copies == 1 else 50))
