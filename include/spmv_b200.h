@@ -322,7 +322,12 @@ int spmvb200_time_copy(int64_t bytes, int copies, int warmup, int reps, float *m
  *               rows rebuild the row numbers from row_ptr instead of the row map), 5 sliced (lane per row on a slot-major copy of
  *               the entries; "csr.batch" 2|4|8 slots in flight; "csr.drop_row_major" (default 1) = free the row-major
  *               column_index/value once that copy exists, so the matrix is resident once -- they are rebuilt on
- *               demand by export, convert, row_block, column_span and the other kernels; 0 = keep both copies); "csr.rmw" (sliced kernel, y += A*x): the lane that owns a row adds to y
+ *               demand by export, convert, row_block, column_span and the other kernels; 0 = keep both copies;
+ *               "csr.index_runs": the copy's column stream is stored by DIAGONAL where a 32-row slice's entries lie on few
+ *               diagonals -- one {base, mask} descriptor per slot (offset = column - row) instead of up to 32 column
+ *               indices, no row_ptr read; values and summation order untouched, results bit-identical -- 0 = when that
+ *               shrinks the stream to <= 3/4 (banded matrices), 1 = always, -1 = never; changing it rebuilds the copy;
+ *               "csr.regs" 40: (experiment) that kernel with a 40-register budget); "csr.rmw" (sliced kernel, y += A*x): the lane that owns a row adds to y
  *               with a plain load and store instead of a reduction -- the launches are then ordered; 1 = on (default off:
  *               measured slower); "csr.probe" 1 = regular traffic
  *               (y_i += sum a_k, values streamed, no gather), 2 = irregular traffic (y_i += sum x[j_k], the
@@ -353,7 +358,9 @@ int spmvb200_time_copy(int64_t bytes, int copies, int warmup, int reps, float *m
  *               into the pinned buffer by the kernel; 4 = the kernel reads y_old from and stores y_new
  *               to the pinned buffer. */
 int spmvb200_set_option(spmvb200_matrix_t m, const char *key, int64_t value);
-/* Also answers the read-only keys "coo.col_block_log2" (what the builder applied), "coo.hot_coverage_permille" and
+/* Also answers the read-only keys "csr.index_runs_active" (the sliced kernel's copy is stored by diagonal) and
+ * "csr.index_columns_stored" (int32 entries of its column stream; = stored entries when plain),
+ * "coo.col_block_log2" (what the builder applied), "coo.hot_coverage_permille" and
  * "coo.hot_segments_built" (the hot-column tables, if built), and
  * "last_launch.overlapped" / "last_launch.pdl" (how the library ordered the last kernel of this matrix). */
 int spmvb200_get_option(spmvb200_matrix_t m, const char *key, int64_t *value);
