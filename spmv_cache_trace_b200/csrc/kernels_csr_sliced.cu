@@ -24,17 +24,19 @@
 // entries lie on a few diagonals, i.e. the set of distinct offsets d = column - row is small.  For such a slice the
 // builder lines the slots up by OFFSET instead of by position in the row: slot k holds the slice's k-th smallest offset,
 // a 32-bit mask says which rows have an entry there, and the 32 column indices of the slot are ONE number -- lane i's
-// column is base_k + i.  The column stream of the slice is then 8 B per slot {base, mask} instead of 4 B per entry, the
-// kernel needs no row_ptr (the masks say which lanes are active) and no ballot, and because all descriptors of a slice
-// arrive with one coalesced load, the gathers of x never wait for a column load: value loads and gathers of a batch are
-// in flight together (one memory round trip per batch instead of two).  Rows at a grid boundary, which lack some
-// neighbours, are simply holes in the masks, so every slice of a stencil qualifies whatever the grid's line length is.
+// column is base_k + i.  The column stream of the slice is then 8 B per slot {base, mask} -- 4 B, the base alone, when every
+// slot holds all 32 rows ("dense": the interior of a grid line) -- instead of 4 B per entry, the kernel needs no row_ptr
+// (the masks say which lanes are active) and no ballot, and because all descriptors of a slice arrive with one coalesced
+// load, the gathers of x never wait for a column load: value loads and gathers of a batch are in flight together (one
+// memory round trip per batch instead of two).  Rows at a grid boundary, which lack some neighbours, are simply holes in
+// the masks, so every slice of a stencil qualifies whatever the grid's line length is.
 // Values are not touched and a row's entries still arrive in ascending column order: every row is summed left to right
 // from the same numbers, bit-identical to the reference.  A slice qualifies when no (row, column) pair occurs twice and
 // its descriptors take at most 3/4 of the bytes of its explicit indices; other slices (R-MAT) keep explicit indices
-// in the position-major order described above.  Per slice: a flag word (bit 31: diagonal form, low bits: slot count)
-// and the offset of its part of the column stream.  27-point 512^3: the column stream shrinks from 14.4 GB to 0.9 GB and
-// row_ptr is not read; the kernel is HBM-bound, so the bytes saved are the speed-up.  The algorithmic bytes of the metric
+// in the position-major order described above.  Per slice: a flag word (bit 31: diagonal form, bit 30: dense, low bits:
+// slot count) and the offset of its part of the column stream, fused with the slice's value offset into one 16-byte record
+// for the SpMV kernel.  27-point 512^3: the column stream shrinks from 14.4 GB to 0.5 GB and row_ptr is not read
+// (33.6 GB moved per product instead of 49.2 GB, 7.40 -> 5.12 ms; profiles/r03_traffic_c5_csr.csv).  The algorithmic bytes of the metric
 // keep counting 4 B per stored column index like the reference's csr_matrix::size(); the measured DRAM traffic is
 // reported beside them.  Used when the whole stream shrinks to at most 3/4 ("csr.index_runs": 0 auto, 1 always, -1 never).
 #include "common.cuh"
@@ -441,7 +443,9 @@ static int csr_build_sliced(Matrix * m)
     int64_t ccount = m->stored;
     int rc = alloc_streamed(m, &m->slice_val, m->stored);
     // index runs ("csr.index_runs": 0 auto, 1 always, -1 never): one int32 per (slice, slot) whose columns are base + lane
-    if (rc == 0 && m->opt_csr_index_runs >= 0) {
+    // (32-bit stream offsets must hold stored + one pad per slice in the worst case)
+    const bool offsets_fit = m->off64 || m->stored + nslices < ((int64_t)1 << 32);
+    if (rc == 0 && m->opt_csr_index_runs >= 0 && offsets_fit) {
         rc = dev_alloc(m, &m->slice_flags, nslices);
         if (rc == 0) {
             if (m->off64) rc = dev_alloc(m, (int64_t **)&m->slice_cofs, nslices + 1);
