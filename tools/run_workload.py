@@ -29,6 +29,10 @@ def factory(name):
         "c3s_csr": lambda: g.rmat(21, 16, 0x5EED0003, fmt=sp.CSR),
         "c3_csr": lambda: g.rmat(24, 16, 0x5EED0003, fmt=sp.CSR),
         "c4s_hyb": lambda: g.rmat(22, 32, 0x5EED0004, fmt=sp.HYB),
+        # short-row stencils at a size where launch effects no longer matter (flat vs sliced + diagonal slices)
+        "big7_csr": lambda: g.stencil(sp.STENCIL_3D7, 400, 400, 400, sp.CSR),
+        "big5_csr": lambda: g.stencil(sp.STENCIL_2D5, 8000, 8000, 1, sp.CSR),
+        "big7_ell": lambda: g.stencil(sp.STENCIL_3D7, 400, 400, 400, sp.ELL),
     }
     return extra[name] if name in extra else make_workload(sp, name)[0]
 
