@@ -260,7 +260,41 @@ def test_gp_order_as_a_layout_lever_for_the_row_partition(tmp_path):
     assert grouped < shuffled / 3 and banded < shuffled / 3, (shuffled, grouped, banded)
 
 
+GP_GOLD = os.path.join(HERE, "golden", "gp_partitions.json")
+GP_CASES = [("grid", 9, 4, None), ("grid", 9, 4, 3), ("grid", 12, 8, 11), ("random_sym", 1, 5, None), ("components", 2, 3, None)]
+
+
+def _gp_case(kind, a, k, shuffle):
+    if kind == "grid":
+        N, i, j, v = _grid7(a, shuffle)
+    else:
+        N, i, j, v = graph(kind, a)
+    return matrix_market.from_entries(N, N, i, j, v), k
+
+
+def test_kway_partition_golden():
+    """The partitioner is deterministic: committed partitions (made by `python tests/test_reorder.py --make-golden`)
+    pin it against accidental changes; the orders derived from them go through the exact grouping step."""
+    gold = json.load(open(GP_GOLD))
+    assert len(gold["cases"]) == len(GP_CASES)
+    for g, case in zip(gold["cases"], GP_CASES):
+        mm, k = _gp_case(*case)
+        part, cut = matrix_market.partition_kway(mm, k)
+        assert part.tolist() == g["part"] and cut == g["edgecut"], case
+        assert matrix_market.find_new_order_GP(mm, k, partitioner=True).tolist() == g["new_order"], case
+
+
 if __name__ == "__main__" and "--make-golden" in sys.argv:
+    gp = []
+    for case in GP_CASES:
+        mm, k = _gp_case(*case)
+        part, cut = matrix_market.partition_kway(mm, k)
+        gp.append({"case": list(case), "part": part.tolist(), "edgecut": cut,
+                   "new_order": matrix_market.find_new_order_GP(mm, k, partitioner=True).tolist()})
+    json.dump({"generator": "python tests/test_reorder.py --make-golden (spmvb200_mm_partition_kway, this repository's partitioner)",
+               "cases": gp}, open(GP_GOLD, "w"))
+    print("wrote", GP_GOLD)
+
     cases = []
     for kind, seed in KINDS:
         n, i, j, a = graph(kind, seed)
