@@ -108,3 +108,38 @@ def test_round2_gpu_lines_are_one_workload_with_parity(name):
         if n == 2:
             h = line["c4_hyb"]
             assert h["parity"]["ok"] and h["single_gpu"]["speedup"] > 1.5 and h["nonzeros"] == 2103842462
+
+
+@pytest.mark.parametrize("name", ["r03_bench_n1.json", "r03_bench_n2.json", "r03_bench_n4.json", "r03_bench_n8.json"])
+def test_round2_final_lines_with_the_diagonal_slices(name):
+    """The final lines of round 2: the sliced CSR kernel stores its column stream by diagonal, so the effective bandwidth
+    (ALGORITHMIC bytes / time) exceeds the measured peak -- the line must then carry the measured traffic, a physical DRAM
+    rate that does not, and the time of the same steps with every index stored."""
+    line = last_json_line(open(os.path.join(ROOT, "profiles", name)).read())
+    assert BASE_KEYS <= set(line), sorted(BASE_KEYS - set(line))
+    assert line["config"]["workload"] == "c5_csr" and line["config"]["algorithmic_bytes"] == 46001250212
+    assert line["parity"]["ok"] is True and line["parity"]["bad_rows"] == 0 and line["parity"]["rows_checked"] >= 1_000_000
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < line["value"]
+    c = line["clocks"]
+    assert c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    n = line["n_gpus"]
+    if n == 1:
+        ir = r["index_runs"]
+        assert ir["active"] is True and ir["column_indices_stored"] < 0.1 * ir["stored_entries"]
+        assert r["traffic"] < r["algorithmic_bytes_per_launch"]             # fewer bytes moved than the metric counts ...
+        assert r["dram_gbs"] < 1.05 * r["peak"] < r["achieved"]              # ... at a physical rate the memory can deliver
+        assert abs(r["dram_gbs"] - r["traffic"] / (r["kernel_ms_mean"] * 1e-3) / 1e9) < 1e-6
+        assert ir["ms_per_step_with_every_index_stored"] > 1.3 * line["ms_per_step"]
+        assert ir["traffic_with_every_index_stored"] > r["algorithmic_bytes_per_launch"]
+        assert line["config"]["resident_bytes"] < 0.75 * 46001250212
+        for k in ("c1_csr", "c1_ell"):
+            assert line["targets"][k]["frac_of_8TBs_pipelined"] >= 0.70
+    else:
+        assert line["single_gpu"]["speedup"] > 0.9 * n
+        v = line["exchange_variants"]
+        assert all(v[k]["parity"]["ok"] for k in ("allgather", "allgather_peer", "halo", "halo_peer", "halo_push"))
+        if n == 2:
+            assert line["c4_hyb"]["parity"]["ok"] and line["c4_hyb"]["single_gpu"]["speedup"] > 1.5
